@@ -1,0 +1,100 @@
+/* yv6.h -- C ABI of libyolov6_b200.so: the sm_100a kernels under the YOLOv6 hot path.
+ *
+ * The reference (meituan/YOLOv6 @ e86a483) has no native boundary: its hot path is PyTorch ops
+ * behind a Python API.  This library sits *under* that API: the host side in
+ * `yolov6_b200/` keeps the reference's Python signatures and calls these entry points through
+ * ctypes with raw device pointers.  Every entry point
+ *   - is `extern "C"`, takes plain pointers / sizes / a `cudaStream_t` passed as `void*`,
+ *   - is asynchronous on that stream and allocates nothing the caller has to free,
+ *   - returns 0 on success or a negative YV6_ERR_* code; `yv6_last_error()` then holds the message
+ *     (the Python side raises RuntimeError, matching the reference's failure contract,
+ *     yolov6/models/losses/loss.py:105 `except RuntimeError`).
+ *
+ * Layout conventions: activations are NHWC (channels innermost), bf16 unless stated; weights are
+ * KRSC = [Cout][kh][kw][Cin] bf16; all strides are in ELEMENTS of the tensor's dtype.
+ */
+#ifndef YV6_H_
+#define YV6_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YV6_ABI_VERSION 1
+
+enum {
+  YV6_OK = 0,
+  YV6_ERR_ARG = -1,     /* invalid argument / unsupported shape */
+  YV6_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed */
+  YV6_ERR_STATE = -3    /* handle not usable (wrong device, destroyed, ...) */
+};
+
+enum { YV6_ACT_NONE = 0, YV6_ACT_RELU = 1, YV6_ACT_SILU = 2, YV6_ACT_SIGMOID = 3 };
+enum { YV6_DT_BF16 = 0, YV6_DT_F32 = 1, YV6_DT_U8 = 2 };
+
+typedef struct yv6_handle yv6_handle;
+
+/* Per-device context: SM count, driver entry points (cuTensorMapEncodeTiled), scratch space. */
+int yv6_create(int device, yv6_handle** out);
+int yv6_destroy(yv6_handle* h);
+/* Thread-local message of the last failing call on this thread. */
+const char* yv6_last_error(void);
+int yv6_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused convolution: y = act(conv(x, w) + bias) [+ alpha * residual]
+ *
+ * Replaces, in deploy form, ConvModule.forward_fuse (yolov6/layers/common.py:50-54),
+ * RepVGGBlock.forward with `rbr_reparam` (common.py:247-248), BottleRep's `+ alpha*x`
+ * (common.py:605-608), the 1x1 convs of BiFusion / BepC3 / (CSP)SPPF (common.py:699-718,
+ * 639-650, 140-158), the head stems / cls_preds / reg_preds incl. the sigmoid of
+ * effidehead.py:85,112, and -- through y_*_stride/offset -- `torch.cat` of the necks
+ * (reppan.py:228,232) and ConvTranspose2d k2 s2 (common.py:181-194, four 1x1 launches that
+ * scatter to the 2x2 sub-grid).
+ *
+ * Implicit GEMM on tcgen05: M = output pixels (tile = BWxBHxBI box, <=128 rows), N = Cout,
+ * K = kh*kw*Cin.  A tiles are TMA box loads of the NHWC input shifted per filter tap (zero fill
+ * out of bounds = padding; elementStrides = conv stride), B tiles are TMA loads of the KRSC
+ * weights, accumulators live in TMEM, epilogue fuses bias/activation/residual/dtype/slice.
+ *
+ * nsplit = 1: bf16 operands, fp32 accumulate.
+ * nsplit = 3: "bf16x3" fp32-equivalent mode -- x, w and y are three bf16 planes (hi, mid, lo) whose
+ *             sum is the fp32 value; six plane-pair products are accumulated in fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct yv6_conv_desc {
+  /* input */
+  const void* x;            /* bf16, pixel (n,h,w) channel c at ((n*H+h)*W+w)*x_c_total + c     */
+  int32_t N, H, W, Cin;     /* Cin % 16 == 0                                                    */
+  int32_t x_c_total;        /* channel pitch of the buffer x lives in (>= Cin, % 8 == 0)        */
+  int64_t x_plane_stride;   /* elements between bf16x3 planes (ignored when nsplit == 1)        */
+  /* weights / bias */
+  const void* w;            /* bf16 KRSC [Cout][kh][kw][Cin]                                    */
+  int64_t w_plane_stride;   /* elements between weight planes (nsplit == 3)                     */
+  const float* bias;        /* fp32, length >= round_up(Cout, 256) (zero padded), or NULL       */
+  int32_t Cout, kh, kw, stride, pad;
+  int32_t act;              /* YV6_ACT_*                                                        */
+  /* output: element (n,ho,wo,co) at y + n*y_img_stride + ho*y_h_stride + wo*y_w_stride + co   */
+  void* y;
+  int32_t y_dtype;          /* YV6_DT_BF16 or YV6_DT_F32                                        */
+  int64_t y_img_stride, y_h_stride, y_w_stride;
+  int64_t y_plane_stride;   /* nsplit == 3 and bf16 output only                                 */
+  /* optional residual (bf16, same dtype/planes as x): y += alpha * res[...]                   */
+  const void* res;
+  float alpha;
+  int64_t res_img_stride, res_h_stride, res_w_stride, res_plane_stride;
+  int32_t nsplit;           /* 1 or 3                                                           */
+  /* tuning overrides, 0 = auto */
+  int32_t force_bw, force_bh, force_bi, force_bn, force_stages, force_grid;
+  int32_t force_direct;     /* 1 = epilogue writes global memory directly instead of smem + TMA store */
+} yv6_conv_desc;
+
+int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);
+/* Reports the tile plan yv6_conv_fwd would use: out[0..7] = BW,BH,BI,BN,KB,stages,grid,tiles. */
+int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YV6_H_ */

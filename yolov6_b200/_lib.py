@@ -1,0 +1,98 @@
+"""ctypes binding of libyolov6_b200.so (C ABI declared in include/yv6.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing, or was built
+without the requested symbol, loading fails loudly with RuntimeError.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyolov6_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
+DT_BF16, DT_F32, DT_U8 = 0, 1, 2
+ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU, "sigmoid": ACT_SIGMOID}
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `yv6_conv_desc` (include/yv6.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("x_c_total", C.c_int32), ("x_plane_stride", C.c_int64),
+        ("w", C.c_void_p), ("w_plane_stride", C.c_int64), ("bias", C.c_void_p),
+        ("Cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("act", C.c_int32),
+        ("y", C.c_void_p), ("y_dtype", C.c_int32),
+        ("y_img_stride", C.c_int64), ("y_h_stride", C.c_int64), ("y_w_stride", C.c_int64),
+        ("y_plane_stride", C.c_int64),
+        ("res", C.c_void_p), ("alpha", C.c_float),
+        ("res_img_stride", C.c_int64), ("res_h_stride", C.c_int64), ("res_w_stride", C.c_int64),
+        ("res_plane_stride", C.c_int64),
+        ("nsplit", C.c_int32),
+        ("force_bw", C.c_int32), ("force_bh", C.c_int32), ("force_bi", C.c_int32), ("force_bn", C.c_int32),
+        ("force_stages", C.c_int32), ("force_grid", C.c_int32), ("force_direct", C.c_int32),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+
+_SIGNATURES = {
+    "yv6_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "yv6_destroy": (C.c_int, [C.c_void_p]),
+    "yv6_last_error": (C.c_char_p, []),
+    "yv6_abi_version": (C.c_int, []),
+    "yv6_conv_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p]),
+    "yv6_conv_plan": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.POINTER(C.c_int32)]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load the shared library once; raise RuntimeError if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(yolov6_b200 has no CPU/PyTorch fallback for its CUDA path)")
+            l = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                try:
+                    fn = getattr(l, name)
+                except AttributeError as e:
+                    raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
+                fn.restype = res
+                fn.argtypes = args
+            _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"yolov6_b200 kernel call failed ({rc}): {lib().yv6_last_error().decode()}")
+
+
+def handle(device_index=0):
+    """Per-device `yv6_handle*` (created lazily, cached for the life of the process)."""
+    h = _handles.get(device_index)
+    if h is None:
+        p = C.c_void_p()
+        check(lib().yv6_create(int(device_index), C.byref(p)))
+        h = _handles[device_index] = p
+    return h
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)

@@ -1,0 +1,683 @@
+// yv6_conv_igemm.cu -- fused implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Computes, for NHWC bf16 activations and KRSC bf16 weights,
+//     y = act(conv(x, w) + bias) [+ alpha * residual]
+// which in deploy form is every 3x3 / 1x1 conv of the YOLOv6 backbones, necks and head:
+// ConvModule.forward_fuse (reference yolov6/layers/common.py:50-54), RepVGGBlock with
+// rbr_reparam (common.py:247-248), BottleRep's shortcut (common.py:605-608), the 1x1s of
+// BiFusion/BepC3/CSPSPPF, the head stems and preds (effidehead.py:72-118) and, through the
+// output strides, torch.cat (reppan.py:228,232) and ConvTranspose2d k2s2 (common.py:181-194).
+//
+// Design (B200-first, im2col-free):
+//   * GEMM view: M = output pixels, N = Cout, K = taps x Cin.  One M tile is a BW x BH x BI box of
+//     output pixels (<= 128 rows).  For filter tap (r,s) the A tile is that same box of the INPUT
+//     shifted by (r-pad, s-pad): one TMA box load from a 5-D tensor map (C, W, H, N, plane) with
+//     zero fill out of bounds (= conv padding) and elementStrides = conv stride.  The box lands in
+//     shared memory as `rows` consecutive K-major rows in the 128/64/32-byte swizzle that
+//     tcgen05.mma consumes directly -- no im2col buffer, no index math on the SMs.
+//   * B tile = [BN x KB] slice of the weights, one TMA load from a 3-D map (K, Cout, plane).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread, tcgen05.mma cta_group::1,
+//     M=128, N=BN<=256, K=16), warps 2..5 = epilogue (tcgen05.ld -> bias/act/residual -> global).
+//   * persistent CTAs (grid = #SMs) over a static tile schedule; smem ring of `stages` K-blocks
+//     (producer runs ahead across tiles), double-buffered TMEM accumulators so the epilogue of
+//     tile i overlaps the mainloop of tile i+1.
+//   * bf16x3 mode (nsplit=3): same kernel, K loop additionally runs over six (plane_a, plane_b)
+//     pairs, giving fp32-equivalent products with fp32 accumulation.
+#include <algorithm>
+#include <cstdarg>
+
+#include "yv6_common.cuh"
+#include "yv6_handle.h"
+
+namespace yv6 {
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 12;
+constexpr int kTileRows = 128;
+
+struct ConvKParams {
+  int32_t BW, BH, BI, rows;
+  int32_t tiles_w, tiles_h, tiles_i, tiles_n, num_tiles;
+  int32_t N, Ho, Wo, Cout, BN;
+  int32_t taps, kw, stride, pad, Cin;
+  int32_t cin_blocks, kb_elems, kb_bytes, ksteps;
+  int32_t sbo_bytes, layout_type;
+  int32_t npairs;
+  int32_t stages, a_stage_bytes, b_stage_bytes;
+  int32_t tmem_cols;
+  int32_t act, y_dtype, out_planes, res_planes;
+  void* y;
+  int64_t y_img_stride, y_h_stride, y_w_stride, y_plane_stride;
+  const __nv_bfloat16* res;
+  float alpha;
+  int64_t res_img_stride, res_h_stride, res_w_stride, res_plane_stride;
+  const float* bias;
+  int32_t tma_store;      // 1: stage the tile in smem and TMA-store it, 0: direct global stores
+  int32_t c_chunk;        // output columns per staged chunk: 64 (bf16) or 32 (fp32) -> 128-byte rows
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct TileCoord {
+  int w0, h0, i0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord t;
+  int nt = tile % p.tiles_n;
+  int m = tile / p.tiles_n;
+  int tw = m % p.tiles_w;
+  m /= p.tiles_w;
+  int th = m % p.tiles_h;
+  int ti = m / p.tiles_h;
+  t.w0 = tw * p.BW;
+  t.h0 = th * p.BH;
+  t.i0 = ti * p.BI;
+  t.n0 = nt * p.BN;
+  return t;
+}
+
+// bf16x3 plane pairs, smallest products first; the plain bf16 mode uses the last entry only.
+__constant__ int kPairA[6] = {0, 1, 2, 0, 1, 0};
+__constant__ int kPairB[6] = {2, 1, 0, 1, 0, 0};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Store 16 consecutive output channels of one pixel.
+__device__ __forceinline__ void store_chunk(const ConvKParams& p, int64_t off, int n, int ncol,
+                                            const float (&v)[16]) {
+  if (p.y_dtype == YV6_DT_F32) {
+    float* y = reinterpret_cast<float*>(p.y) + off + n;
+    if (ncol == 16 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+      float4* y4 = reinterpret_cast<float4*>(y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < ncol; ++j) y[j] = v[j];
+    }
+    return;
+  }
+  float rem[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) rem[j] = v[j];
+  for (int pl = 0; pl < p.out_planes; ++pl) {
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + pl * p.y_plane_stride + off + n;
+    if (ncol == 16 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+      uint4 q0, q1;
+      q0.x = pack_bf16x2(rem[0], rem[1]);
+      q0.y = pack_bf16x2(rem[2], rem[3]);
+      q0.z = pack_bf16x2(rem[4], rem[5]);
+      q0.w = pack_bf16x2(rem[6], rem[7]);
+      q1.x = pack_bf16x2(rem[8], rem[9]);
+      q1.y = pack_bf16x2(rem[10], rem[11]);
+      q1.z = pack_bf16x2(rem[12], rem[13]);
+      q1.w = pack_bf16x2(rem[14], rem[15]);
+      reinterpret_cast<uint4*>(y)[0] = q0;
+      reinterpret_cast<uint4*>(y)[1] = q1;
+    } else {
+      for (int j = 0; j < ncol; ++j) y[j] = __float2bfloat16_rn(rem[j]);
+    }
+    if (pl + 1 < p.out_planes) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rem[j] -= __bfloat162float(__float2bfloat16_rn(rem[j]));
+    }
+  }
+}
+
+constexpr int kCBufBytes = kTileRows * 128;  // one staged output chunk: 128 rows x 128 B
+
+// bias + activation (+ residual) for 16 consecutive output channels of one pixel
+__device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32_t (&r)[16], int n, int ncol,
+                                              bool valid, int64_t roff, float (&v)[16]) {
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+      v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+      v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+      v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  }
+  if (p.act == YV6_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (p.act != YV6_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
+  }
+  if (p.res != nullptr && valid && ncol > 0) {
+    for (int pl = 0; pl < p.res_planes; ++pl) {
+      const __nv_bfloat16* rp = p.res + pl * p.res_plane_stride + roff + n;
+      if (ncol == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+          v[2 * j] += p.alpha * __low2float(b2);
+          v[2 * j + 1] += p.alpha * __high2float(b2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ncol) v[j] += p.alpha * __bfloat162float(rp[j]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * p.a_stage_bytes;
+  uint8_t* sC = sB + (size_t)p.stages * p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * kCBufBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int kblocks = p.npairs * p.taps * p.cin_blocks;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(p.rows * p.kb_bytes + p.BN * p.kb_bytes);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int pi = 0; pi < p.npairs; ++pi) {
+          const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            const int cx = t.w0 * p.stride + s - p.pad;
+            const int cy = t.h0 * p.stride + r - p.pad;
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_expect_tx(&full[stage], tx);
+              tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage],
+                          cb * p.kb_elems, cx, cy, t.i0, pa);
+              tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage],
+                          tap * p.Cin + cb * p.kb_elems, t.n0, pb);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_stage_bytes);
+          const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_stage_bytes);
+          for (int k = 0; k < p.ksteps; ++k) {
+            const uint64_t ad = umma_smem_desc(a_addr + k * 32, p.sbo_bytes, p.layout_type);
+            const uint64_t bd = umma_smem_desc(b_addr + k * 32, p.sbo_bytes, p.layout_type);
+            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int bw = row % p.BW;
+    const int tq = row / p.BW;
+    const int bh = tq % p.BH;
+    const int bi = tq / p.BH;
+    const bool issuer = (threadIdx.x == 64);  // first epilogue thread issues the TMA stores
+    const uint32_t row_smem = (uint32_t)row * 128u;
+    const uint32_t row_xor = (uint32_t)(row & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cbuf = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int img = t.i0 + bi, ho = t.h0 + bh, wo = t.w0 + bw;
+      const bool valid = (row < p.rows) && (img < p.N) && (ho < p.Ho) && (wo < p.Wo);
+      const int64_t off = (int64_t)img * p.y_img_stride + (int64_t)ho * p.y_h_stride +
+                          (int64_t)wo * p.y_w_stride;
+      const int64_t roff = (int64_t)img * p.res_img_stride + (int64_t)ho * p.res_h_stride +
+                           (int64_t)wo * p.res_w_stride;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      if (p.tma_store) {
+        // ---- stage 128-byte rows in swizzled smem, one TMA store per chunk (and plane) ----
+        const bool f32 = (p.y_dtype == YV6_DT_F32);
+        for (int c0 = 0; c0 < p.BN; c0 += p.c_chunk) {
+          const int nsub = min(p.c_chunk, p.BN - c0) >> 4;  // 16-column groups in this chunk (<= 4)
+          uint32_t r[4][16];
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            if (s < nsub) tmem_ld16(taddr + (uint32_t)(c0 + 16 * s), r[s]);
+          tmem_ld_wait();
+          float v[4][16];
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            if (s < nsub) {
+              const int n = t.n0 + c0 + 16 * s;
+              epilogue_math(p, r[s], n, min(16, p.Cout - n), valid, roff, v[s]);
+            }
+          for (int pl = 0; pl < p.out_planes; ++pl) {
+            uint8_t* buf = sC + cbuf * kCBufBytes;
+            if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer is done
+            epi_bar_sync();
+            if (row < p.rows) {
+              const uint32_t base = smem_u32(buf) + row_smem;
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                if (s < nsub) {
+                  if (f32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const uint32_t a = base + ((((uint32_t)(4 * s + j)) ^ row_xor) << 4);
+                      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[s][4 * j]),
+                                   "f"(v[s][4 * j + 1]), "f"(v[s][4 * j + 2]), "f"(v[s][4 * j + 3])
+                                   : "memory");
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      const uint32_t a = base + ((((uint32_t)(2 * s + j)) ^ row_xor) << 4);
+                      const uint32_t w0 = pack_bf16x2(v[s][8 * j + 0], v[s][8 * j + 1]);
+                      const uint32_t w1 = pack_bf16x2(v[s][8 * j + 2], v[s][8 * j + 3]);
+                      const uint32_t w2 = pack_bf16x2(v[s][8 * j + 4], v[s][8 * j + 5]);
+                      const uint32_t w3 = pack_bf16x2(v[s][8 * j + 6], v[s][8 * j + 7]);
+                      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1),
+                                   "r"(w2), "r"(w3)
+                                   : "memory");
+                    }
+                  }
+                }
+            }
+            fence_proxy_async_smem();
+            epi_bar_sync();
+            if (issuer) {
+              tma_store_5d(&tmC, buf, t.n0 + c0, t.w0, t.h0, t.i0, pl);
+              tma_store_commit();
+            }
+            cbuf ^= 1;
+            if (pl + 1 < p.out_planes) {  // bf16x3: peel the next plane off the remainder
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[s][j] -= __bfloat162float(__float2bfloat16_rn(v[s][j]));
+            }
+          }
+        }
+      } else {
+        // ---- fallback: direct global stores (outputs whose strides TMA cannot express) ----
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int n = t.n0 + c0;
+          const int ncol = min(16, p.Cout - n);
+          float v[16];
+          epilogue_math(p, r, n, ncol, valid, roff, v);
+          if (valid && ncol > 0) store_chunk(p, off, n, ncol, v);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (issuer && p.tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tile planning, tensor-map encoding, launch
+// ------------------------------------------------------------------------------------------------
+struct ConvPlan {
+  ConvKParams k;
+  int grid;
+  size_t smem_bytes;
+  CUtensorMapSwizzle swz;
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan) {
+  YV6_REQUIRE(d != nullptr, "conv: null descriptor");
+  YV6_REQUIRE(d->x && d->w && d->y, "conv: null tensor pointer");
+  YV6_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "conv: bad input shape %dx%dx%d", d->N, d->H, d->W);
+  YV6_REQUIRE(d->Cin > 0 && d->Cin % 16 == 0, "conv: Cin=%d must be a positive multiple of 16", d->Cin);
+  YV6_REQUIRE(d->x_c_total >= d->Cin && d->x_c_total % 8 == 0, "conv: bad x_c_total=%d", d->x_c_total);
+  YV6_REQUIRE(d->Cout > 0, "conv: Cout=%d", d->Cout);
+  YV6_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "conv: kernel %dx%d unsupported", d->kh, d->kw);
+  YV6_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
+  YV6_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "conv: nsplit must be 1 or 3");
+  YV6_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0,
+              "conv: x / w must be 16-byte aligned");
+  YV6_REQUIRE(d->y_dtype == YV6_DT_BF16 || d->y_dtype == YV6_DT_F32, "conv: bad y_dtype");
+
+  ConvKParams& k = plan->k;
+  memset(&k, 0, sizeof(k));
+  k.N = d->N;
+  k.Ho = (d->H + 2 * d->pad - d->kh) / d->stride + 1;
+  k.Wo = (d->W + 2 * d->pad - d->kw) / d->stride + 1;
+  YV6_REQUIRE(k.Ho > 0 && k.Wo > 0, "conv: empty output");
+  k.Cout = d->Cout;
+  k.Cin = d->Cin;
+  k.taps = d->kh * d->kw;
+  k.kw = d->kw;
+  k.stride = d->stride;
+  k.pad = d->pad;
+
+  // K block = largest of 64/32/16 channels dividing Cin -> 128/64/32-byte swizzle
+  k.kb_elems = (d->Cin % 64 == 0) ? 64 : (d->Cin % 32 == 0) ? 32 : 16;
+  k.kb_bytes = k.kb_elems * 2;
+  k.ksteps = k.kb_elems / 16;
+  k.cin_blocks = d->Cin / k.kb_elems;
+  k.sbo_bytes = 8 * k.kb_bytes;
+  k.layout_type = (k.kb_bytes == 128) ? 2 : (k.kb_bytes == 64) ? 4 : 6;
+  plan->swz = (k.kb_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+              : (k.kb_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                   : CU_TENSOR_MAP_SWIZZLE_32B;
+  k.npairs = (d->nsplit == 3) ? 6 : 1;
+
+  // output staging: 128-byte rows -> 64 bf16 or 32 fp32 columns per TMA-stored chunk
+  const int esz = (d->y_dtype == YV6_DT_F32) ? 4 : 2;
+  k.c_chunk = 128 / esz;
+  k.tma_store = (d->force_direct == 0) && ((d->y_w_stride * esz) % 16 == 0) && ((d->y_h_stride * esz) % 16 == 0) &&
+                ((d->y_img_stride * esz) % 16 == 0) && ((d->y_plane_stride * esz) % 16 == 0) &&
+                ((reinterpret_cast<uintptr_t>(d->y) & 15) == 0);
+  // N tiling is chosen together with the M tiling below
+  const int bn_align = k.c_chunk;  // with several N tiles, a tile must end on a staged-chunk boundary
+  // M tiling: BW x BH x BI box of output pixels, <= 128 rows, fewest tiles wins
+  if (d->force_bw > 0) {
+    k.BW = d->force_bw;
+    k.BH = std::max(1, d->force_bh);
+    k.BI = std::max(1, d->force_bi);
+    YV6_REQUIRE(k.BW * k.BH * k.BI <= kTileRows && k.BW * d->stride <= 256 && k.BH * d->stride <= 256,
+                "conv: forced tile %dx%dx%d invalid", k.BW, k.BH, k.BI);
+  } else {
+    long best_tiles = -1;
+    int bestw = 1, besth = 1, besti = 1;
+    const int maxbw = std::min(std::min(k.Wo, kTileRows), 256 / d->stride);
+    for (int bw = 1; bw <= maxbw; ++bw) {
+      const int maxbh = std::min(std::min(k.Ho, kTileRows / bw), 256 / d->stride);
+      for (int bh = 1; bh <= maxbh; ++bh) {
+        int bi = 1;
+        if (bw >= k.Wo && bh >= k.Ho) bi = std::max(1, std::min(d->N, kTileRows / (bw * bh)));
+        long tiles = (long)ceil_div(k.Wo, bw) * ceil_div(k.Ho, bh) * ceil_div(d->N, bi);
+        if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && bw > bestw)) {
+          best_tiles = tiles;
+          bestw = bw;
+          besth = bh;
+          besti = bi;
+        }
+      }
+    }
+    k.BW = bestw;
+    k.BH = besth;
+    k.BI = besti;
+  }
+  const long m_tiles = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
+  // N tiling: BN <= 256, multiple of 16; pick the split whose wave count x tile cost is smallest
+  // (a 448-tile layer on 148 SMs runs 4 waves at BN=256 but 7 half-cost waves at BN=128).
+  if (d->force_bn > 0) {
+    YV6_REQUIRE(d->force_bn % 16 == 0 && d->force_bn <= 256, "conv: force_bn must be a multiple of 16 <= 256");
+    k.BN = d->force_bn;
+  } else {
+    double best_cost = -1;
+    int best_bn = 0;
+    const int nt_min = ceil_div(d->Cout, 256);
+    for (int nt = nt_min; nt <= nt_min * 4; ++nt) {
+      int bn = ceil_div(ceil_div(d->Cout, nt), 16) * 16;
+      if (nt > 1) bn = ceil_div(bn, bn_align) * bn_align;
+      if (bn > 256 || (nt > 1 && bn < 64)) continue;
+      const long tiles = m_tiles * ceil_div(d->Cout, bn);
+      const double waves = (double)ceil_div((int)std::min<long>(tiles, 1l << 30), h->num_sms);
+      const double cost = waves * (bn + 48.0);  // +48: per-tile fixed cost and A re-reads favour wide tiles
+      if (best_cost < 0 || cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best_bn = bn;
+      }
+    }
+    k.BN = best_bn;
+  }
+  YV6_REQUIRE(k.BN >= 16, "conv: could not choose BN for Cout=%d", d->Cout);
+  k.tiles_n = ceil_div(d->Cout, k.BN);
+  if (k.tiles_n > 1 && k.tma_store && (k.BN % bn_align) != 0) k.tma_store = 0;
+  k.rows = k.BW * k.BH * k.BI;
+  k.tiles_w = ceil_div(k.Wo, k.BW);
+  k.tiles_h = ceil_div(k.Ho, k.BH);
+  k.tiles_i = ceil_div(d->N, k.BI);
+  const long nt = (long)k.tiles_w * k.tiles_h * k.tiles_i * k.tiles_n;
+  YV6_REQUIRE(nt < (1l << 30), "conv: too many tiles");
+  k.num_tiles = (int)nt;
+
+  // smem ring
+  k.a_stage_bytes = kTileRows * k.kb_bytes;
+  k.b_stage_bytes = ((k.BN * k.kb_bytes + 1023) / 1024) * 1024;
+  const int stage_bytes = k.a_stage_bytes + k.b_stage_bytes;
+  const int budget = h->max_smem_optin - 1024 - 512 - 2 * kCBufBytes;
+  int stages = std::min(kMaxStages, budget / stage_bytes);
+  if (d->force_stages > 0) stages = std::min(stages, d->force_stages);
+  YV6_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
+  k.stages = stages;
+  plan->smem_bytes = (size_t)stages * stage_bytes + 2 * kCBufBytes + 1024 + 512;
+
+  int cols = 32;
+  while (cols < 2 * k.BN) cols *= 2;
+  k.tmem_cols = cols;
+
+  k.act = d->act;
+  k.y_dtype = d->y_dtype;
+  k.out_planes = (d->nsplit == 3 && d->y_dtype == YV6_DT_BF16) ? 3 : 1;
+  k.res_planes = (d->nsplit == 3) ? 3 : 1;
+  k.y = d->y;
+  k.y_img_stride = d->y_img_stride;
+  k.y_h_stride = d->y_h_stride;
+  k.y_w_stride = d->y_w_stride;
+  k.y_plane_stride = d->y_plane_stride;
+  k.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
+  k.alpha = d->alpha;
+  k.res_img_stride = d->res_img_stride;
+  k.res_h_stride = d->res_h_stride;
+  k.res_w_stride = d->res_w_stride;
+  k.res_plane_stride = d->res_plane_stride;
+  k.bias = d->bias;
+
+  plan->grid = std::min(k.num_tiles, h->num_sms);
+  if (d->force_grid > 0) plan->grid = std::min(k.num_tiles, d->force_grid);
+  return YV6_OK;
+}
+
+}  // namespace yv6
+
+using namespace yv6;
+
+extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out8) {
+  YV6_REQUIRE(h != nullptr && out8 != nullptr, "conv_plan: null argument");
+  ConvPlan plan;
+  int rc = plan_conv(h, d, &plan);
+  if (rc != YV6_OK) return rc;
+  out8[0] = plan.k.BW;
+  out8[1] = plan.k.BH;
+  out8[2] = plan.k.BI;
+  out8[3] = plan.k.BN;
+  out8[4] = plan.k.kb_elems;
+  out8[5] = plan.k.stages;
+  out8[6] = plan.grid;
+  out8[7] = plan.k.num_tiles;
+  return YV6_OK;
+}
+
+extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream) {
+  YV6_REQUIRE(h != nullptr, "conv_fwd: null handle");
+  ConvPlan plan;
+  int rc = plan_conv(h, d, &plan);
+  if (rc != YV6_OK) return rc;
+  const ConvKParams& k = plan.k;
+  YV6_REQUIRE(h->encode_tiled != nullptr, "conv_fwd: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+
+  // A: (C, W, H, N, plane) over the input (channel slice of a wider NHWC buffer allowed)
+  CUtensorMap tmA, tmB, tmC;
+  {
+    const uint64_t planes = (d->nsplit == 3) ? 3 : 1;
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N, planes};
+    const uint64_t pix = (uint64_t)d->x_c_total * 2;
+    uint64_t plane_stride = (d->nsplit == 3) ? (uint64_t)d->x_plane_stride * 2
+                                             : (uint64_t)d->N * d->H * d->W * pix;
+    YV6_REQUIRE(plane_stride % 16 == 0, "conv: x_plane_stride must be a multiple of 8 elements");
+    cuuint64_t strides[4] = {pix, pix * d->W, pix * d->W * d->H, plane_stride};
+    cuuint32_t box[5] = {(cuuint32_t)k.kb_elems, (cuuint32_t)(k.BW * d->stride), (cuuint32_t)(k.BH * d->stride),
+                         (cuuint32_t)k.BI, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
+    CUresult cr = h->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->x), dims,
+                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, plan.swz,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      yv6_set_error("conv: cuTensorMapEncodeTiled(A) failed with %d (C=%d W=%d H=%d N=%d box=%u,%u,%u,%u)", (int)cr,
+                    d->Cin, d->W, d->H, d->N, box[0], box[1], box[2], box[3]);
+      return YV6_ERR_CUDA;
+    }
+  }
+  {
+    const uint64_t planes = (d->nsplit == 3) ? 3 : 1;
+    const uint64_t ktot = (uint64_t)k.taps * d->Cin;
+    cuuint64_t dims[3] = {ktot, (cuuint64_t)d->Cout, planes};
+    uint64_t plane_stride = (d->nsplit == 3) ? (uint64_t)d->w_plane_stride * 2 : ktot * 2 * d->Cout;
+    YV6_REQUIRE(plane_stride % 16 == 0, "conv: w_plane_stride must be a multiple of 8 elements");
+    cuuint64_t strides[2] = {ktot * 2, plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)k.kb_elems, (cuuint32_t)k.BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = h->encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), dims,
+                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, plan.swz,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      yv6_set_error("conv: cuTensorMapEncodeTiled(B) failed with %d", (int)cr);
+      return YV6_ERR_CUDA;
+    }
+  }
+
+  // C: (Cout, Wo, Ho, N, plane) over the output view; one box = one staged chunk of one tile
+  if (k.tma_store) {
+    const uint64_t esz = (d->y_dtype == YV6_DT_F32) ? 4 : 2;
+    const uint64_t planes = (uint64_t)k.out_planes;
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cout, (cuuint64_t)k.Wo, (cuuint64_t)k.Ho, (cuuint64_t)d->N, planes};
+    uint64_t plane_stride = (planes > 1) ? (uint64_t)d->y_plane_stride * esz : (uint64_t)d->y_img_stride * esz * d->N;
+    if (plane_stride == 0) plane_stride = 16;
+    cuuint64_t strides[4] = {(uint64_t)d->y_w_stride * esz, (uint64_t)d->y_h_stride * esz,
+                             (uint64_t)d->y_img_stride * esz, plane_stride};
+    cuuint32_t box[5] = {(cuuint32_t)k.c_chunk, (cuuint32_t)k.BW, (cuuint32_t)k.BH, (cuuint32_t)k.BI, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = h->encode_tiled(&tmC, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                  5, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      yv6_set_error("conv: cuTensorMapEncodeTiled(C) failed with %d (Cout=%d Wo=%d Ho=%d N=%d strides=%llu,%llu,%llu)",
+                    (int)cr, d->Cout, k.Wo, k.Ho, d->N, (unsigned long long)strides[0],
+                    (unsigned long long)strides[1], (unsigned long long)strides[2]);
+      return YV6_ERR_CUDA;
+    }
+  } else {
+    tmC = tmA;  // unused by the kernel
+  }
+
+  static bool configured = false;
+  if (!configured) {
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->max_smem_optin));
+    configured = true;
+  }
+  conv_igemm_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
