@@ -1,0 +1,46 @@
+"""Pins oracle/nms.py (incl. the restated torchvision greedy NMS) bit-exactly against the reference's
+non_max_suppression outputs stored by tests/golden/make_golden.py."""
+import numpy as np
+
+from conftest import golden_json, golden_npz
+from oracle import fabricate as fab
+from oracle import nms as onms
+
+
+def test_nms_oracle_bit_exact_vs_reference():
+    g = golden_npz("nms.npz")
+    total = 0
+    for i, (B, A, nc, seed, kw) in enumerate(golden_json("nms_cases.json")):
+        p = fab.synthetic_predictions(B, A, nc, seed)
+        assert abs(fab.checksum(p) - float(g[f"c{i}_checksum"])) <= 1e-9 * abs(float(g[f"c{i}_checksum"])), "RNG drift"
+        out = onms.non_max_suppression(p.numpy(), **kw)
+        counts = np.array([o.shape[0] for o in out])
+        assert np.array_equal(counts, g[f"c{i}_counts"]), (i, counts, g[f"c{i}_counts"])
+        rows = np.concatenate(out) if counts.sum() else np.zeros((0, 6), np.float32)
+        assert np.array_equal(rows, g[f"c{i}_rows"]), f"case {i}: kept rows differ"
+        total += int(counts.sum())
+    assert total > 3000
+
+
+def test_greedy_nms_semantics():
+    # ties keep the lower index; IoU == thr is kept (strict >); float IoU vs double threshold
+    boxes = np.array([[0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 30, 30], [20, 20, 30, 30]], np.float32)
+    scores = np.array([0.5, 0.5, 0.5, 0.5], np.float32)
+    assert onms.greedy_nms(boxes, scores, 0.5).tolist() == [0, 2]
+    b = np.array([[0, 0, 2, 1], [1, 0, 3, 1]], np.float32)  # IoU = 1/3 (float32) > 1/3 (double) -> suppressed
+    assert onms.greedy_nms(b, np.array([0.9, 0.8], np.float32), 1.0 / 3.0).tolist() == [0]
+    assert onms.greedy_nms(b, np.array([0.9, 0.8], np.float32), 0.34).tolist() == [0, 1]
+    assert onms.greedy_nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5).shape == (0,)
+
+
+def test_nms_empty_and_class_offset():
+    p = fab.synthetic_predictions(2, 50, 4, seed=9).numpy()
+    assert all(o.shape == (0, 6) for o in onms.non_max_suppression(p, conf_thres=1.0))
+    # identical boxes of different classes survive unless agnostic
+    q = np.zeros((1, 2, 9), np.float32)
+    q[0, :, :4] = [100, 100, 50, 50]
+    q[0, :, 4] = 1
+    q[0, 0, 5] = 0.9
+    q[0, 1, 7] = 0.8
+    assert onms.non_max_suppression(q, 0.25, 0.45)[0].shape[0] == 2
+    assert onms.non_max_suppression(q, 0.25, 0.45, agnostic=True)[0].shape[0] == 1

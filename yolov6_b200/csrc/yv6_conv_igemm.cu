@@ -239,29 +239,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(p.rows * p.kb_bytes + p.BN * p.kb_bytes);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int pi = 0; pi < p.npairs; ++pi) {
-          const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int r = tap / p.kw, s = tap - r * p.kw;
-            const int cx = t.w0 * p.stride + s - p.pad;
-            const int cy = t.h0 * p.stride + r - p.pad;
-            for (int cb = 0; cb < p.cin_blocks; ++cb) {
-              mbar_wait(&empty[stage], phase ^ 1);
+    // The whole warp walks the schedule (keeps control flow convergent so addresses / coordinates
+    // live in uniform registers); one elected lane arms the barrier and issues the two TMA loads.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = (uint32_t)(p.rows * p.kb_bytes + p.BN * p.kb_bytes);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int pi = 0; pi < p.npairs; ++pi) {
+        const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          const int cx = t.w0 * p.stride + s - p.pad;
+          const int cy = t.h0 * p.stride + r - p.pad;
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(&full[stage], tx);
-              tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage],
-                          cb * p.kb_elems, cx, cy, t.i0, pa);
+              tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], cb * p.kb_elems, cx, cy,
+                          t.i0, pa);
               tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage],
                           tap * p.Cin + cb * p.kb_elems, t.n0, pb);
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
+            }
+            __syncwarp();
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
             }
           }
         }
@@ -269,36 +272,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // Warp-convergent loop; the elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are
+    // a constant high word plus (smem address >> 4), advanced by 2 (= 32 bytes) per K=16 step.
+    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.BN);
+    const uint64_t desc_const = umma_smem_desc(0, (uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
+    const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
+    const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)p.b_stage_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_stage_bytes);
-          const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_stage_bytes);
-          for (int k = 0; k < p.ksteps; ++k) {
-            const uint64_t ad = umma_smem_desc(a_addr + k * 32, p.sbo_bytes, p.layout_type);
-            const uint64_t bd = umma_smem_desc(b_addr + k * 32, p.sbo_bytes, p.layout_type);
-            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+        const uint64_t ad = desc_const | (uint64_t)(a_base + (uint32_t)stage * a_step);
+        const uint64_t bd = desc_const | (uint64_t)(b_base + (uint32_t)stage * b_step);
+        if (elect_one()) {
+          umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(kb != 0));
+          if (p.ksteps > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          if (p.ksteps > 2) {
+            umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+            umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ================================ epilogue ================================
