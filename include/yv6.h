@@ -94,6 +94,60 @@ int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);
 /* Reports the tile plan yv6_conv_fwd would use: out[0..7] = BW,BH,BI,BN,KB,stages,grid,tiles. */
 int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out8);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stem: first 3x3 stride-2 conv on the 3-channel NCHW image, deploy form of `backbone.stem`
+ * (reference yolov6/models/efficientrep.py:28-33), fused with the input conversion of
+ * Trainer.prepro_data / Inferer.process_image (core/engine.py:407-410, core/inferer.py:162-171):
+ * x is NCHW fp32 in [0,1] or NCHW uint8 (then scaled by in_scale = 1/255 on the fly).
+ * Output NHWC bf16 (1 or 3 planes).  w / bias are HOST pointers (27*Cout + Cout floats travel as
+ * kernel parameters): w is fp32 KRSC [Cout][3][3][3].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct yv6_stem_desc {
+  const void* x;            /* device, [N,3,H,W] fp32 or uint8                                  */
+  int32_t x_dtype;          /* YV6_DT_F32 or YV6_DT_U8                                          */
+  float in_scale;           /* multiplier for uint8 input (1/255)                               */
+  int32_t N, H, W;
+  const float* w;           /* HOST fp32 [Cout][3][3][3]                                        */
+  const float* bias;        /* HOST fp32 [Cout] or NULL                                         */
+  int32_t Cout, act;        /* Cout in {16,32,48,64}                                            */
+  void* y;                  /* device bf16 [planes][N,H/2,W/2,Cout]                             */
+  int64_t y_plane_stride;
+  int32_t nsplit;           /* 1 or 3                                                           */
+} yv6_stem_desc;
+int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream);
+
+/* SPPF / CSPSPPF pooling (reference yolov6/layers/common.py:106-112,150-158): buf is the 4C-wide
+ * NHWC concat buffer whose channel slice [0,C) holds x; writes the 5x5 / 9x9 / 13x13 clipped-window
+ * maxima (= three chained MaxPool2d(5,1,2)) into slices [C,2C), [2C,3C), [3C,4C). */
+int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int32_t W, int32_t C, int32_t c_total,
+                  int32_t nsplit, int64_t plane_stride, void* stream);
+
+/* Eval-mode head decode (reference yolov6/models/effidehead.py:106-139, assigners/anchor_generator.py
+ * :13-33, utils/general.py:32-43): cls [B,A,nc] fp32 (post-sigmoid), reg [B,A,reg_ch] fp32 (ltrb, or
+ * 4*(reg_max+1) DFL logits) -> out [B,A,5+nc] = (cx,cy,w,h in pixels, 1, cls).  Levels are given by
+ * their grid sizes and strides; A = sum(lvl_h*lvl_w). */
+int yv6_head_decode(yv6_handle* h, const float* cls, const float* reg, float* out, int32_t B, int32_t nc,
+                    int32_t reg_ch, int32_t nl, const int32_t* lvl_h, const int32_t* lvl_w,
+                    const float* lvl_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched NMS: reference yolov6/utils/nms.py:31-105 (`non_max_suppression`) including the greedy
+ * suppression of torchvision.ops.nms (nms.py:96), for ALL images in one call.
+ *   pred [B,A,5+nc] fp32 (xywh, obj, cls).  Candidate rule, class-offset boxes (+cls*4096), stable
+ *   descending order, float-IoU-vs-double-threshold comparison and max_nms = 30000 truncation follow
+ *   the reference's CPU path bit for bit (fp32 ops issued without FMA contraction).
+ *   class_mask: NULL or nc bytes (1 = keep class) -- the `classes` filter.
+ * Outputs: out [B,max_det,6] (xyxy, conf, cls), out_count [B], out_src [B,max_det,2] (anchor, class).
+ * workspace: device scratch of at least yv6_nms_workspace_bytes(B, A, nc, multi_label) bytes.
+ * overflow (device int32, may be NULL) is set to 1 if an image produced more candidates than the
+ * workspace holds (only possible with multi_label and > 65536 (anchor, class) pairs above conf).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yv6_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc, int32_t multi_label);
+int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int32_t A, int32_t nc, float conf_thres,
+                    double iou_thres, int32_t agnostic, int32_t multi_label, const uint8_t* class_mask,
+                    int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,17 @@ class ConvDesc(C.Structure):
     ]
 
 
+class StemDesc(C.Structure):
+    """Mirror of `yv6_stem_desc` (include/yv6.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("x_dtype", C.c_int32), ("in_scale", C.c_float),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("w", C.POINTER(C.c_float)), ("bias", C.POINTER(C.c_float)),
+        ("Cout", C.c_int32), ("act", C.c_int32),
+        ("y", C.c_void_p), ("y_plane_stride", C.c_int64), ("nsplit", C.c_int32),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 _handles = {}
@@ -46,6 +57,16 @@ _SIGNATURES = {
     "yv6_abi_version": (C.c_int, []),
     "yv6_conv_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p]),
     "yv6_conv_plan": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.POINTER(C.c_int32)]),
+    "yv6_stem_fwd": (C.c_int, [C.c_void_p, C.POINTER(StemDesc), C.c_void_p]),
+    "yv6_sppf_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int64, C.c_void_p]),
+    "yv6_head_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                  C.c_void_p]),
+    "yv6_nms_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "yv6_nms_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double,
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 

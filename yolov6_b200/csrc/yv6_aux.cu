@@ -1,0 +1,314 @@
+// yv6_aux.cu -- the HBM-bound helpers around the conv kernel (sm_100a, CUDA cores):
+//   * yv6_stem_fwd   : first 3x3 s2 conv on the 3-channel NCHW image (fp32 or uint8/255) -> NHWC bf16
+//   * yv6_sppf_pool  : the three chained 5x5 max-pools of (CSP)SPPF written straight into concat slices
+//   * yv6_head_decode: DFL expectation + ltrb -> xywh + x stride + [xywh, 1, cls] assembly
+#include "yv6_common.cuh"
+#include "yv6_handle.h"
+
+namespace yv6 {
+
+// ------------------------------------------------------------------------------------------------
+// stem: reference RepVGGBlock / ConvBNSiLU `backbone.stem` (efficientrep.py:28-33) in deploy form,
+// fused with the input conversion of Trainer.prepro_data / Inferer.process_image
+// (engine.py:407-410, inferer.py:162-171: uint8 -> float / 255, NCHW).
+// One thread = one output pixel, all Cout channels; the 27*Cout weights ride in the kernel
+// parameter (constant bank) so every FFMA takes its weight operand straight from c[0][..].
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemMaxCout = 64;
+struct StemParams {
+  float w[27 * kStemMaxCout];  // [tap(r,s)][cin][cout]
+  float b[kStemMaxCout];
+  const void* x;
+  __nv_bfloat16* y;
+  int64_t y_plane_stride;
+  int32_t N, H, W, Ho, Wo;
+  int32_t x_u8, act, planes;
+  float in_scale;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemParams p) {
+  __shared__ __align__(16) __nv_bfloat16 tile[128 * COUT];
+  const int64_t total = (int64_t)p.N * p.Ho * p.Wo;
+  const int64_t pix0 = (int64_t)blockIdx.x * 128;
+  const int64_t pix = pix0 + threadIdx.x;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = p.b[c];
+  if (pix < total) {
+    const int wo = (int)(pix % p.Wo);
+    const int ho = (int)((pix / p.Wo) % p.Ho);
+    const int n = (int)(pix / ((int64_t)p.Wo * p.Ho));
+    float in[27];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = 2 * ho - 1 + r;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int wi = 2 * wo - 1 + s;
+        const bool ok = (hi >= 0) && (hi < p.H) && (wi >= 0) && (wi < p.W);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = 0.f;
+          if (ok) {
+            const int64_t idx = (((int64_t)n * 3 + c) * p.H + hi) * p.W + wi;
+            v = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + idx) * p.in_scale
+                       : __ldg(reinterpret_cast<const float*>(p.x) + idx);
+          }
+          in[(r * 3 + s) * 3 + c] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(in[k], p.w[k * COUT + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = act_apply(acc[c], p.act);
+  }
+  // stage the 128 x COUT tile so that global stores are full, coalesced 16-byte vectors
+  const int nvec = 128 * COUT / 8;
+  const int64_t left = total - pix0;
+  const int64_t valid_elems = (left < 128 ? left : (int64_t)128) * COUT;
+  for (int pl = 0; pl < p.planes; ++pl) {
+    if (pl) __syncthreads();
+#pragma unroll
+    for (int c = 0; c < COUT; c += 2) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(acc[c], acc[c + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(&tile[threadIdx.x * COUT + c]) = v;
+      if (pl + 1 < p.planes) {
+        acc[c] -= __low2float(v);
+        acc[c + 1] -= __high2float(v);
+      }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(p.y + pl * p.y_plane_stride + pix0 * COUT);
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+    for (int i = threadIdx.x; i < nvec; i += 128)
+      if ((int64_t)i * 8 < valid_elems) dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPPF pooling: reference SPPFModule / CSPSPPFModule (common.py:106-112, 150-158):
+//   y1 = pool5(x), y2 = pool5(y1), y3 = pool5(y2), cat([x, y1, y2, y3]).
+// With -inf padding the chained pools equal 5x5 / 9x9 / 13x13 windows clipped to the image, so one
+// pass computes all three.  x lives in channel slice 0 of the 4C-wide concat buffer; the results
+// are written to slices 1..3 of the same buffer.  One thread = one pixel x 8 channels.
+// ------------------------------------------------------------------------------------------------
+struct PoolParams {
+  __nv_bfloat16* buf;  // [planes][N,H,W,c_total]
+  int64_t plane_stride;
+  int32_t N, H, W, C, c_total, planes;
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    v[2 * j] = __low2float(b2);
+    v[2 * j + 1] = __high2float(b2);
+  }
+}
+
+__global__ void __launch_bounds__(256) sppf_pool_kernel(const PoolParams p) {
+  const int cgs = p.C / 8;
+  const int64_t total = (int64_t)p.N * p.H * p.W * cgs;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = (int)(idx % cgs);
+  const int w = (int)((idx / cgs) % p.W);
+  const int h = (int)((idx / ((int64_t)cgs * p.W)) % p.H);
+  const int n = (int)(idx / ((int64_t)cgs * p.W * p.H));
+  float m5[8], m9[8], m13[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m5[j] = m9[j] = m13[j] = -INFINITY;
+  for (int dy = -6; dy <= 6; ++dy) {
+    const int hh = h + dy;
+    if (hh < 0 || hh >= p.H) continue;
+    for (int dx = -6; dx <= 6; ++dx) {
+      const int ww = w + dx;
+      if (ww < 0 || ww >= p.W) continue;
+      const int64_t off = (((int64_t)n * p.H + hh) * p.W + ww) * p.c_total + cg * 8;
+      float v[8];
+      load8(p.buf + off, v);
+      for (int pl = 1; pl < p.planes; ++pl) {
+        float t[8];
+        load8(p.buf + pl * p.plane_stride + off, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+      const int ad = max(abs(dy), abs(dx));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        m13[j] = fmaxf(m13[j], v[j]);
+        if (ad <= 4) m9[j] = fmaxf(m9[j], v[j]);
+        if (ad <= 2) m5[j] = fmaxf(m5[j], v[j]);
+      }
+    }
+  }
+  const int64_t o = (((int64_t)n * p.H + h) * p.W + w) * p.c_total + cg * 8;
+  float* res[3] = {m5, m9, m13};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float* m = res[k];
+    for (int pl = 0; pl < p.planes; ++pl) {
+      uint32_t wds[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+        wds[j] = *reinterpret_cast<uint32_t*>(&b2);
+        m[2 * j] -= __low2float(b2);
+        m[2 * j + 1] -= __high2float(b2);
+      }
+      *reinterpret_cast<uint4*>(p.buf + pl * p.plane_stride + o + (int64_t)(k + 1) * p.C) =
+          make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head decode: eval tail of Detect.forward (effidehead.py:106-139), generate_anchors(is_eval)
+// (anchor_generator.py:13-33) and dist2bbox(xywh) (general.py:32-43).  One warp per anchor row:
+// lanes stream the nc class scores (already sigmoid-ed by the cls_pred conv epilogue), lanes 0..3
+// decode one box side each.  fp32 ops are explicit round-to-nearest (no FMA contraction) in the
+// reference's order so that box bits match the reference's fp32 path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxLevels = 6;
+struct DecodeParams {
+  const float* cls;  // [B, A, nc]
+  const float* reg;  // [B, A, R]
+  float* out;        // [B, A, 5 + nc]
+  int32_t B, A, nc, R, reg_max, nl;
+  int32_t lvl_off[kMaxLevels + 1];
+  int32_t lvl_w[kMaxLevels];
+  float lvl_stride[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant__ DecodeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (int64_t)p.B * p.A) return;
+  const int a = (int)(row % p.A);
+  const float* cls = p.cls + row * p.nc;
+  float* out = p.out + row * (5 + p.nc);
+  for (int c = lane; c < p.nc; c += 32) out[5 + c] = __ldg(cls + c);
+  // distances: plain ltrb (R == 4) or DFL expectation over reg_max+1 bins per side
+  float dist = 0.f;
+  if (lane < 4) {
+    const float* reg = p.reg + row * p.R;
+    if (p.R == 4) {
+      dist = __ldg(reg + lane);
+    } else {
+      const int nb = p.reg_max + 1;
+      const float* l = reg + lane * nb;
+      float mx = -INFINITY;
+      for (int i = 0; i < nb; ++i) mx = fmaxf(mx, __ldg(l + i));
+      float den = 0.f;
+      for (int i = 0; i < nb; ++i) den += expf(__ldg(l + i) - mx);
+      float e = 0.f;
+      for (int i = 0; i < nb; ++i) e = __fadd_rn(e, __fmul_rn(expf(__ldg(l + i) - mx) / den, (float)i));
+      dist = e;
+    }
+  }
+  const float dl = __shfl_sync(0xffffffffu, dist, 0), dt = __shfl_sync(0xffffffffu, dist, 1);
+  const float dr = __shfl_sync(0xffffffffu, dist, 2), db = __shfl_sync(0xffffffffu, dist, 3);
+  if (lane == 0) {
+    int lvl = 0;
+    while (lvl + 1 < p.nl && a >= p.lvl_off[lvl + 1]) ++lvl;
+    const int local = a - p.lvl_off[lvl];
+    const float ax = (float)(local % p.lvl_w[lvl]) + 0.5f;
+    const float ay = (float)(local / p.lvl_w[lvl]) + 0.5f;
+    const float s = p.lvl_stride[lvl];
+    const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt);
+    const float x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+    out[0] = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), s);
+    out[1] = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), s);
+    out[2] = __fmul_rn(__fsub_rn(x2, x1), s);
+    out[3] = __fmul_rn(__fsub_rn(y2, y1), s);
+    out[4] = 1.0f;
+  }
+}
+
+}  // namespace yv6
+
+using namespace yv6;
+
+extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream) {
+  YV6_REQUIRE(h && d && d->x && d->w && d->y, "stem: null argument");
+  YV6_REQUIRE(d->Cout > 0 && d->Cout <= kStemMaxCout && d->Cout % 16 == 0, "stem: Cout=%d must be 16/32/48/64", d->Cout);
+  YV6_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "stem: nsplit must be 1 or 3");
+  YV6_REQUIRE(d->x_dtype == YV6_DT_F32 || d->x_dtype == YV6_DT_U8, "stem: image must be fp32 or uint8");
+  StemParams p;
+  // weights arrive as host fp32 KRSC [Cout][3][3][3]; re-order to [tap][cin][cout]
+  for (int co = 0; co < d->Cout; ++co)
+    for (int k = 0; k < 27; ++k) p.w[k * d->Cout + co] = d->w[co * 27 + k];
+  for (int co = 0; co < d->Cout; ++co) p.b[co] = d->bias ? d->bias[co] : 0.f;
+  p.x = d->x;
+  p.y = reinterpret_cast<__nv_bfloat16*>(d->y);
+  p.y_plane_stride = d->y_plane_stride;
+  p.N = d->N;
+  p.H = d->H;
+  p.W = d->W;
+  p.Ho = (d->H + 2 - 3) / 2 + 1;
+  p.Wo = (d->W + 2 - 3) / 2 + 1;
+  p.x_u8 = (d->x_dtype == YV6_DT_U8);
+  p.in_scale = d->in_scale;
+  p.act = d->act;
+  p.planes = d->nsplit;
+  const int64_t total = (int64_t)p.N * p.Ho * p.Wo;
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (d->Cout) {
+    case 16: stem_kernel<16><<<grid, 128, 0, s>>>(p); break;
+    case 32: stem_kernel<32><<<grid, 128, 0, s>>>(p); break;
+    case 48: stem_kernel<48><<<grid, 128, 0, s>>>(p); break;
+    default: stem_kernel<64><<<grid, 128, 0, s>>>(p); break;
+  }
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
+
+extern "C" int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int32_t W, int32_t C, int32_t c_total,
+                             int32_t nsplit, int64_t plane_stride, void* stream) {
+  YV6_REQUIRE(h && buf, "sppf_pool: null argument");
+  YV6_REQUIRE(C % 8 == 0 && c_total >= 4 * C && c_total % 8 == 0, "sppf_pool: bad channels C=%d c_total=%d", C, c_total);
+  PoolParams p{reinterpret_cast<__nv_bfloat16*>(buf), plane_stride, N, H, W, C, c_total, nsplit == 3 ? 3 : 1};
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  sppf_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
+
+extern "C" int yv6_head_decode(yv6_handle* h, const float* cls, const float* reg, float* out, int32_t B, int32_t nc,
+                               int32_t reg_ch, int32_t nl, const int32_t* lvl_h, const int32_t* lvl_w,
+                               const float* lvl_stride, void* stream) {
+  YV6_REQUIRE(h && cls && reg && out && lvl_h && lvl_w && lvl_stride, "head_decode: null argument");
+  YV6_REQUIRE(nl >= 1 && nl <= kMaxLevels, "head_decode: nl=%d out of range", nl);
+  YV6_REQUIRE(reg_ch == 4 || reg_ch % 4 == 0, "head_decode: reg_ch=%d", reg_ch);
+  DecodeParams p;
+  p.cls = cls;
+  p.reg = reg;
+  p.out = out;
+  p.B = B;
+  p.nc = nc;
+  p.R = reg_ch;
+  p.reg_max = reg_ch / 4 - 1;
+  p.nl = nl;
+  int off = 0;
+  for (int l = 0; l < nl; ++l) {
+    p.lvl_off[l] = off;
+    p.lvl_w[l] = lvl_w[l];
+    p.lvl_stride[l] = lvl_stride[l];
+    off += lvl_h[l] * lvl_w[l];
+  }
+  p.lvl_off[nl] = off;
+  p.A = off;
+  const int64_t rows = (int64_t)B * p.A;
+  head_decode_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
