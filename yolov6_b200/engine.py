@@ -214,3 +214,31 @@ class InferEngine:
             buf = buf[0] if self.nsplit == 3 else buf
             out.append(buf[..., t.c_off:t.c_off + t.c].permute(0, 3, 1, 2))
         return out
+
+    def profile_convs(self, x, steps=5, stream=None):
+        """Roofline instrumentation for bench.py: CUDA events around every conv_igemm launch.
+        Returns (conv-kernel ms per forward, algorithmic conv FLOPs per forward, launches per forward)."""
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        plan = self._plan(N, H, W, x.dtype if x.dtype == torch.uint8 else torch.float32)
+        self.forward(x, stream)
+        torch.cuda.synchronize()
+        sp = _lib.stream_ptr(stream)
+        convs = [d for kind, d in plan["calls"] if kind == "conv"]
+        flops = 0.0
+        for d in convs:
+            ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
+            wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
+            flops += 2.0 * d.N * ho * wo * d.Cout * d.Cin * d.kh * d.kw
+        total_ms = 0.0
+        for _ in range(steps):
+            evs = []
+            for d in convs:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(self.lib.yv6_conv_fwd(self.handle, C.byref(d), sp))
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            total_ms += sum(a.elapsed_time(b) for a, b in evs)
+        return total_ms / steps, flops, len(convs)
