@@ -148,6 +148,78 @@ int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int32_t A, int3
                     int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training-side irregular work: target preprocessing, label assignment, fused loss.
+ * Compact assignment format shared by the assigners and the loss:
+ *   gt      [B,G,5] float64  (class, x1, y1, x2, y2 in pixels; pad rows = -1,0,0,0,0)
+ *   gt_idx  [B,A]   int32    assigned gt row (0 for background, as in the reference)
+ *   fg      [B,A]   uint8    foreground mask
+ *   norm    [B,A]   float64  target score of the assigned class (TAL: normalised alignment metric,
+ *                            ATSS: IoU(gt, pred)); 0 for background
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ComputeLoss.preprocess (reference yolov6/models/losses/loss.py:184-192) on the device: ragged
+ * targets [n,6] fp32 (img, cls, cx, cy, w, h normalised) -> gt [B,G,5] float64 and gt_count [B]
+ * (rows per image; rows beyond G are dropped and show up as gt_count > G). */
+int yv6_targets_pad(yv6_handle* h, const float* targets, int32_t n, int32_t B, int32_t G, float scale_w,
+                    float scale_h, double* gt, int32_t* gt_count, void* stream);
+
+int64_t yv6_assign_workspace_bytes(int32_t B, int32_t A, int32_t G);
+
+/* TaskAlignedAssigner.forward (reference yolov6/assigners/tal_assigner.py:22-173,
+ * assigner_utils.py:25-89).  pd_scores [B,A,nc] fp32, pd_bboxes [B,A,4] fp32 xyxy pixels,
+ * anc_points [A,2] fp32 pixels, mask_gt [B,G] uint8. */
+int yv6_tal_assign(yv6_handle* h, const float* pd_scores, const float* pd_bboxes, const float* anc_points,
+                   const double* gt, const uint8_t* mask_gt, int32_t B, int32_t A, int32_t G, int32_t nc,
+                   int32_t topk, double alpha, double beta, double eps, int32_t* gt_idx, uint8_t* fg,
+                   double* norm, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ATSSAssigner.forward (reference yolov6/assigners/atss_assigner.py:18-161): anc_bboxes [A,4] fp32,
+ * n_level_bboxes = HOST array of per-level anchor counts, pd_bboxes [B,A,4] fp32 pixels or NULL. */
+int yv6_atss_assign(yv6_handle* h, const float* anc_bboxes, const int32_t* n_level_bboxes, int32_t nl,
+                    const double* gt, const uint8_t* mask_gt, const float* pd_bboxes, int32_t B, int32_t A,
+                    int32_t G, int32_t nc, int32_t topk, int32_t* gt_idx, uint8_t* fg, double* norm,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Dense (reference-shaped) assigner outputs for the drop-in API: labels int64 [B,A], bboxes float64
+ * [B,A,4], scores float64 [B,A,nc], fg uint8 [B,A].  bg_label < 0: TAL convention (background keeps
+ * gt 0's clamped label, tal_assigner.py:159-165); bg_label >= 0: ATSS (background = bg_label). */
+int yv6_assign_expand(yv6_handle* h, const double* gt, const int32_t* gt_idx, const uint8_t* fg,
+                      const double* norm, int32_t B, int32_t A, int32_t G, int32_t nc, int32_t bg_label,
+                      int64_t* labels, double* bboxes, double* scores, uint8_t* fg_out, void* stream);
+
+/* ComputeLoss.bbox_decode (loss.py:194-198) + dist2bbox (utils/general.py:32-38): pred_distri
+ * [B,A,reg_ch] -> boxes [B,A,4] xyxy in stride units, or pixels when scale_to_pixels != 0
+ * (the `pred_bboxes * stride_tensor` handed to the assigners, loss.py:94,100). strides: [A] fp32. */
+int yv6_box_decode(yv6_handle* h, const float* pred_distri, const float* anc_points, const float* strides,
+                   int32_t B, int32_t A, int32_t reg_ch, int32_t scale_to_pixels, float* boxes, void* stream);
+
+/* Fused VFL + IoU (giou/siou/ciou/diou) + DFL loss, forward and backward (loss.py:157-182, 201-278;
+ * utils/figure_iou.py:23-100).  out (device float64[8]): [0] loss, [1] w_iou*iou, [2] w_dfl*dfl,
+ * [3] w_cls*cls (= reference loss_items order), [4] target_scores_sum, [5] num_pos.
+ * grad_* receive d(loss * grad_scale)/d(pred_*), fp32, every element written. */
+typedef struct yv6_loss_desc {
+  const float* pred_scores;  /* [B,A,nc] post-sigmoid */
+  const float* pred_distri;  /* [B,A,reg_ch] */
+  const float* anc_points;   /* [A,2] pixels */
+  const float* strides;      /* [A] */
+  const double* gt;          /* [B,G,5] */
+  const int32_t* gt_idx;
+  const uint8_t* fg;
+  const double* norm;
+  int32_t B, A, G, nc, reg_ch;
+  int32_t iou_type;          /* 0 giou, 1 siou, 2 ciou, 3 diou */
+  double w_cls, w_iou, w_dfl;
+  double grad_scale;
+  float* grad_scores;
+  float* grad_distri;
+  double* out;
+  void* workspace;
+  int64_t workspace_bytes;   /* >= yv6_det_loss_workspace_bytes(B, A) */
+} yv6_loss_desc;
+int64_t yv6_det_loss_workspace_bytes(int32_t B, int32_t A);
+int yv6_det_loss(yv6_handle* h, const yv6_loss_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

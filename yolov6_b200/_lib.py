@@ -46,6 +46,19 @@ class StemDesc(C.Structure):
     ]
 
 
+class LossDesc(C.Structure):
+    """Mirror of `yv6_loss_desc` (include/yv6.h)."""
+    _fields_ = [
+        ("pred_scores", C.c_void_p), ("pred_distri", C.c_void_p), ("anc_points", C.c_void_p), ("strides", C.c_void_p),
+        ("gt", C.c_void_p), ("gt_idx", C.c_void_p), ("fg", C.c_void_p), ("norm", C.c_void_p),
+        ("B", C.c_int32), ("A", C.c_int32), ("G", C.c_int32), ("nc", C.c_int32), ("reg_ch", C.c_int32),
+        ("iou_type", C.c_int32),
+        ("w_cls", C.c_double), ("w_iou", C.c_double), ("w_dfl", C.c_double), ("grad_scale", C.c_double),
+        ("grad_scores", C.c_void_p), ("grad_distri", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 _handles = {}
@@ -63,6 +76,22 @@ _SIGNATURES = {
     "yv6_head_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
                                   C.c_void_p]),
+    "yv6_targets_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yv6_assign_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "yv6_tal_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "yv6_atss_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "yv6_assign_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "yv6_box_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_void_p, C.c_void_p]),
+    "yv6_det_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "yv6_det_loss": (C.c_int, [C.c_void_p, C.POINTER(LossDesc), C.c_void_p]),
     "yv6_nms_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "yv6_nms_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

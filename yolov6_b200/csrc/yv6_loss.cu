@@ -15,6 +15,8 @@
 //         chains through ltrb decode / DFL softmax, and adds the DFL cross-entropy terms;
 //       - normalisation by target_scores_sum (if > 1) and the loss weights are applied on the device
 //         (no host sync); partial sums are reduced in a fixed order (deterministic).
+#include <algorithm>
+
 #include "yv6_common.cuh"
 #include "yv6_handle.h"
 

@@ -1,0 +1,103 @@
+"""Drop-in `ComputeLoss` backed by the sm_100a assignment + fused loss kernels.
+
+Same constructor and call signature as the reference (yolov6/models/losses/loss.py:14-182):
+    ComputeLoss(fpn_strides, grid_cell_size, grid_cell_offset, num_classes, ori_img_size, warmup_epoch,
+                use_dfl, reg_max, iou_type, loss_weight)
+    loss, loss_items = compute_loss(outputs, targets, epoch_num, step_num, batch_height, batch_width)
+`loss` is a float64 scalar that is differentiable w.r.t. pred_scores / pred_distri (the gradients are
+produced by the same kernel launch as the forward values); `loss_items` = [iou, dfl, cls] weighted and
+detached (loss.py:179-182).  The whole path (target padding, box decode, TAL or ATSS, VFL + IoU + DFL,
+normalisation) runs on the device with no host synchronisation; failures surface as RuntimeError.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .assigners import _p, atss_compact, generate_anchors_train, tal_compact
+
+IOU_TYPES = {"giou": 0, "siou": 1, "ciou": 2, "diou": 3}
+
+
+class _DetLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_scores, pred_distri, state):
+        ctx.save_for_backward(state["grad_scores"], state["grad_distri"])
+        ctx.shapes = (pred_scores.dtype, pred_distri.dtype)
+        return state["out"][0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gs, gd = ctx.saved_tensors
+        return (gs * grad_out).to(ctx.shapes[0]), (gd * grad_out).to(ctx.shapes[1]), None
+
+
+class ComputeLoss:
+    def __init__(self, fpn_strides=[8, 16, 32], grid_cell_size=5.0, grid_cell_offset=0.5, num_classes=80,
+                 ori_img_size=640, warmup_epoch=4, use_dfl=True, reg_max=16, iou_type='giou',
+                 loss_weight={'class': 1.0, 'iou': 2.5, 'dfl': 0.5}):
+        self.fpn_strides = list(fpn_strides)
+        self.grid_cell_size, self.grid_cell_offset = grid_cell_size, grid_cell_offset
+        self.num_classes, self.ori_img_size = num_classes, ori_img_size
+        self.warmup_epoch = warmup_epoch
+        self.use_dfl, self.reg_max = use_dfl, reg_max
+        self.iou_type = iou_type.lower()
+        if self.iou_type not in IOU_TYPES:
+            raise ValueError(f"unknown iou_type {iou_type}")
+        self.loss_weight = loss_weight
+        self._anchor_key, self._anchors = None, None
+        self.last_assignment = None
+
+    def _get_anchors(self, sizes, device):
+        key = (tuple(sizes), str(device))
+        if key != self._anchor_key:       # cached like loss.py:63-69
+            self._anchors = generate_anchors_train(sizes, self.fpn_strides, device, self.grid_cell_size, self.grid_cell_offset)
+            self._anchor_key = key
+        return self._anchors
+
+    def __call__(self, outputs, targets, epoch_num, step_num, batch_height, batch_width):
+        feats, pred_scores, pred_distri = outputs
+        dev = pred_scores.device
+        if dev.type != "cuda":
+            raise RuntimeError("yolov6_b200.ComputeLoss runs on CUDA tensors only (no CPU fallback)")
+        sizes = [tuple(f.shape[2:]) for f in feats]
+        anchors, anchor_points, n_list, stride_t = self._get_anchors(sizes, dev)
+        B, A, nc = pred_scores.shape
+        R = pred_distri.shape[2]
+        lib, h, sp = _lib.lib(), _lib.handle(dev.index or 0), _lib.stream_ptr()
+        ps = pred_scores.detach().float().contiguous()
+        pd = pred_distri.detach().float().contiguous()
+        strides = stride_t.reshape(-1).contiguous()
+        # targets -> padded float64 gts (loss.py:184-192); G = n rows is an upper bound that needs no host sync
+        tg = targets.detach().float().contiguous().to(dev)
+        n = tg.shape[0]
+        G = max(n, 1)
+        gt = torch.empty(B, G, 5, dtype=torch.float64, device=dev)
+        gt_count = torch.empty(B, dtype=torch.int32, device=dev)
+        _lib.check(lib.yv6_targets_pad(h, _p(tg), n, B, G, float(batch_width), float(batch_height), _p(gt), _p(gt_count), sp))
+        mask = (gt[:, :, 1:].sum(-1) > 0).to(torch.uint8).contiguous()          # loss.py:79
+        # predicted boxes in pixels for the assigner (loss.py:82-83, 94/100)
+        pboxes = torch.empty(B, A, 4, dtype=torch.float32, device=dev)
+        _lib.check(lib.yv6_box_decode(h, _p(pd), _p(anchor_points), _p(strides), B, A, R, 1, _p(pboxes), sp))
+        if epoch_num < self.warmup_epoch:
+            c = atss_compact(anchors, n_list, gt, mask, pboxes, nc, 9)
+        else:
+            c = tal_compact(ps, pboxes, anchor_points, gt, mask, 13, 1.0, 6.0)
+        self.last_assignment = c
+        d = _lib.LossDesc()
+        grad_scores = torch.empty_like(ps)
+        grad_distri = torch.empty_like(pd)
+        out = torch.zeros(8, dtype=torch.float64, device=dev)
+        ws = torch.empty(int(lib.yv6_det_loss_workspace_bytes(B, A)), dtype=torch.uint8, device=dev)
+        d.pred_scores, d.pred_distri, d.anc_points, d.strides = ps.data_ptr(), pd.data_ptr(), anchor_points.data_ptr(), strides.data_ptr()
+        d.gt, d.gt_idx, d.fg, d.norm = gt.data_ptr(), c.gt_idx.data_ptr(), c.fg.data_ptr(), c.norm.data_ptr()
+        d.B, d.A, d.G, d.nc, d.reg_ch = B, A, G, nc, R
+        d.iou_type = IOU_TYPES[self.iou_type]
+        d.w_cls, d.w_iou, d.w_dfl = float(self.loss_weight['class']), float(self.loss_weight['iou']), float(self.loss_weight['dfl'])
+        d.grad_scale = 1.0
+        d.grad_scores, d.grad_distri, d.out = grad_scores.data_ptr(), grad_distri.data_ptr(), out.data_ptr()
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.yv6_det_loss(h, C.byref(d), sp))
+        state = {"grad_scores": grad_scores, "grad_distri": grad_distri, "out": out}
+        loss = _DetLossFn.apply(pred_scores, pred_distri, state)
+        return loss, out[1:4].detach().clone()
