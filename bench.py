@@ -137,13 +137,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle import fabricate as fab   # weights / images only (test infrastructure; not on the timed path)
     from yolov6_b200.model import build_model
     from yolov6_b200.nms import nms_batched
+    from yolov6_b200.synth import randomize_
 
-    sd = fab.fabricate_state_dict(load_keys(args.model), seed=0)
-    model = build_model(args.model, 80, dev)
-    model.load_state_dict(sd)
+    model = randomize_(build_model(args.model, 80, dev), seed=0)   # seeded synthetic checkpoint
     model.eval().set_precision(args.precision)
     eng = model.engine()
     B, S = args.batch, args.size
@@ -151,15 +149,32 @@ def main():
     host_u8 = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8).pin_memory() for _ in range(2)]
     dev_f32 = [h.to(dev).float() / 255 for h in host_u8]   # 157 MB each > 126 MB L2
 
-    def step_device(i):
-        pred = eng.forward(dev_f32[i & 1])
-        return nms_batched(pred, **NMS_KW)
+    from yolov6_b200.pipeline import DetectPipeline
+    use_graph = not args.no_graph
+    if use_graph:
+        # steady state = one CUDA-graph launch per batch (yolov6_b200/pipeline.py); two pipelines with
+        # separate static buffers alternate so that consecutive steps never reuse a cached input
+        pipes_dev = [DetectPipeline(model, B, S, S, host_input=False, **NMS_KW) for _ in range(2)]
+        pipes_e2e = [DetectPipeline(model, B, S, S, host_input=True, **NMS_KW) for _ in range(2)]
+        for i in range(2):
+            pipes_dev[i].x_dev.copy_(dev_f32[i])
+            pipes_e2e[i].x_host.copy_(host_u8[i])
 
-    def step_e2e(i):
-        x = host_u8[i & 1].to(dev, non_blocking=True)
-        pred = eng.forward(x)
-        out, count, _, _ = nms_batched(pred, **NMS_KW)
-        return out.cpu(), count.cpu()
+        def step_device(i):
+            pipes_dev[i & 1].launch()
+
+        def step_e2e(i):
+            pipes_e2e[i & 1].launch()          # H2D (39 MB u8) -> kernels -> D2H detections, all in the graph
+    else:
+        def step_device(i):
+            pred = eng.forward(dev_f32[i & 1])
+            return nms_batched(pred, **NMS_KW)
+
+        def step_e2e(i):
+            x = host_u8[i & 1].to(dev, non_blocking=True)
+            pred = eng.forward(x)
+            out, count, _, _ = nms_batched(pred, **NMS_KW)
+            return out.cpu(), count.cpu()
 
     def barrier():
         if world > 1:
@@ -207,7 +222,8 @@ def main():
         "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-equivalent)", "data": "synthetic",
         "config": {"workload": f"{args.model} {S}x{S} bs{B}/GPU inference: forward + decode + batched NMS",
                    "nms": NMS_KW, "weights": "seeded random (oracle/fabricate.py)", "parallelism": f"dp{world} image-sharded, no collective",
-                   "l2": "inputs (157 MB fp32 per batch, two alternating buffers) exceed the 126 MB L2"},
+                   "l2": "inputs (157 MB fp32 per batch, two alternating buffers) exceed the 126 MB L2",
+                   "launch": "one CUDA graph per batch (DetectPipeline)" if use_graph else "eager ctypes launches"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * NMS_KW["max_det"] * 6 * 4 + B * 4},
         "gpu_launches": (eng.launch_count(B, S, S) + nms_launches) * args.steps,
@@ -219,10 +235,11 @@ def main():
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
-        from oracle import model as om
+        from oracle import model as om        # CPU-baseline leg: the checker, timed on the host cores
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        xs = fab.synthetic_images(args.ref_batch, S, S, seed=0)
+        xs = torch.rand(args.ref_batch, 3, S, S, generator=torch.Generator().manual_seed(0))
         cpu_reference_step(sd, om.CONFIGS[args.model], xs[:1], NMS_KW)
         t0 = time.perf_counter()
         for _ in range(args.steps_ref):

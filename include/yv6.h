@@ -88,11 +88,13 @@ typedef struct yv6_conv_desc {
   /* tuning overrides, 0 = auto */
   int32_t force_bw, force_bh, force_bi, force_bn, force_stages, force_grid;
   int32_t force_direct;     /* 1 = epilogue writes global memory directly instead of smem + TMA store */
+  int32_t force_halo;       /* 3x3 s1 halo-reuse mainloop: 0 = auto, 1 = force on (if eligible), -1 = off */
 } yv6_conv_desc;
 
 int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);
-/* Reports the tile plan yv6_conv_fwd would use: out[0..7] = BW,BH,BI,BN,KB,stages,grid,tiles. */
-int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out8);
+/* Reports the tile plan yv6_conv_fwd would use: out[0..9] = BW,BH,BI,BN,KB,stages,grid,tiles,halo,
+ * (A stages * 100 + B resident). */
+int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out10);
 
 /* ------------------------------------------------------------------------------------------------
  * Stem: first 3x3 stride-2 conv on the 3-channel NCHW image, deploy form of `backbone.stem`

@@ -50,7 +50,10 @@ def test_compute_loss_matches_reference_golden(case):
     nz = scores.cpu().nonzero().numpy().astype(np.int32)
     assert np.array_equal(nz, g[f"{name}_scores_idx"])
     np.testing.assert_allclose(scores.cpu()[scores.cpu() != 0].numpy(), g[f"{name}_scores_val"], rtol=1e-9 if epoch >= warm else 1e-6)
-    np.testing.assert_allclose(bboxes.cpu().numpy()[fg], g[f"{name}_bboxes_fg"], rtol=1e-12)
+    # the golden boxes were captured after the reference's in-place `target_bboxes /= stride_tensor` (loss.py:158)
+    stride_col = torch.cat([torch.full((h * w,), float(s), dtype=torch.float64) for (h, w), s in zip(sizes, strides)])
+    got_boxes = (bboxes.cpu() / stride_col.view(1, -1, 1)).numpy()[fg]
+    np.testing.assert_allclose(got_boxes, g[f"{name}_bboxes_fg"], rtol=1e-12)
     assert abs(loss.item() - float(g[f"{name}_loss"])) <= 1e-6 * abs(float(g[f"{name}_loss"]))
     np.testing.assert_allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=1e-6, atol=1e-9)
     gs = psd.grad.cpu()

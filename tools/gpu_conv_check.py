@@ -188,6 +188,13 @@ if __name__ == "__main__":
     run_case("3x3_x3_residual", 2, 20, 20, 64, 64, 3, 1, nsplit=3, use_res=True)
     run_case("3x3_big_bs8_160", 8, 160, 160, 64, 64, 3, 1)
     run_case("3x3_s2_stem_like", 2, 64, 64, 16, 32, 3, 2)
+    run_case("nohalo_3x3_c128_40", 2, 40, 40, 128, 128, 3, 1, force=dict(halo=-1))
+    run_case("halo_3x3_c64_s1_odd", 3, 23, 17, 64, 96, 3, 1, force=dict(halo=1))
+    run_case("halo_3x3_c256_bn256", 2, 32, 32, 256, 256, 3, 1, force=dict(halo=1))
+    run_case("halo_3x3_c512_ntiles", 2, 16, 16, 512, 512, 3, 1, force=dict(halo=1))
+    run_case("halo_3x3_x3", 2, 24, 24, 64, 64, 3, 1, nsplit=3, force=dict(halo=1))
+    run_case("halo_3x3_res_slices", 2, 24, 24, 64, 64, 3, 1, use_res=True, x_extra=64, y_extra=64, force=dict(halo=1))
+    run_case("halo_3x3_silu_c128_cout80_f32", 2, 24, 24, 128, 80, 3, 1, act="silu", out_f32=True, force=dict(halo=1))
     run_case("direct_3x3_c128", 2, 40, 40, 128, 128, 3, 1, force=dict(direct=1))
     run_case("direct_1x1_cout80_f32", 2, 20, 20, 128, 80, 1, 1, act="sigmoid", out_f32=True, force=dict(direct=1))
     run_case("3x3_cout96_partial_chunk", 2, 20, 20, 64, 96, 3, 1)
@@ -213,6 +220,11 @@ if __name__ == "__main__":
     bench_case("1x1_512_256@20", B, 20, 20, 512, 256, 1, 1)
     bench_case("1x1_384_128@40", B, 40, 40, 384, 128, 1, 1)
     bench_case("1x1_128_128@80", B, 80, 80, 128, 128, 1, 1)
+    for nm in ("s1_64@160", "s1_128@80", "s1_256@40", "s1_512@20", "s1_128@40", "s1_256@20", "s1_64@80"):
+        H_, W_, ci, co, k_, st = BENCH_SHAPES[nm]
+        bench_case(nm + "_nohalo", B, H_, W_, ci, co, k_, st, force=dict(halo=-1))
+    bench_case("s1_512@20_halo", B, 20, 20, 512, 512, 3, 1, force=dict(halo=1))
+    bench_case("s1_256@20_halo", B, 20, 20, 256, 256, 3, 1, force=dict(halo=1))
     bench_case("s1_256@40_bn128", B, 40, 40, 256, 256, 3, 1, force=dict(bn=128))
     bench_case("s1_256@40_bn256", B, 40, 40, 256, 256, 3, 1, force=dict(bn=256))
     bench_case("s1_256@40_direct", B, 40, 40, 256, 256, 3, 1, force=dict(direct=1))

@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("res_plane_stride", C.c_int64),
         ("nsplit", C.c_int32),
         ("force_bw", C.c_int32), ("force_bh", C.c_int32), ("force_bi", C.c_int32), ("force_bn", C.c_int32),
-        ("force_stages", C.c_int32), ("force_grid", C.c_int32), ("force_direct", C.c_int32),
+        ("force_stages", C.c_int32), ("force_grid", C.c_int32), ("force_direct", C.c_int32), ("force_halo", C.c_int32),
     ]
 
 

@@ -230,15 +230,54 @@ class InferEngine:
             ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
             wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
             flops += 2.0 * d.N * ho * wo * d.Cout * d.Cin * d.kh * d.kw
+        # one event pair around the back-to-back conv launches of a forward (launch gaps between the
+        # kernels are part of the step, so they stay in the denominator)
         total_ms = 0.0
         for _ in range(steps):
-            evs = []
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             for d in convs:
+                _lib.check(self.lib.yv6_conv_fwd(self.handle, C.byref(d), sp))
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms / steps, flops, len(convs)
+
+    def profile_layers(self, x, iters=10, stream=None):
+        """Per-launch timing table (name, shape, ms, TFLOP/s) with an L2 flush before every launch."""
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        plan = self._plan(N, H, W, x.dtype if x.dtype == torch.uint8 else torch.float32)
+        self.forward(x, stream)
+        torch.cuda.synchronize()
+        sp = _lib.stream_ptr(stream)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+        names = []
+        for op in self.g.ops:
+            if op.kind in ("conv", "pred"):
+                names.append(op.name)
+            elif op.kind == "convT":
+                names.extend([f"{op.name}[{q}]" for q in range(4)])
+        rows = []
+        convs = [d for kind, d in plan["calls"] if kind == "conv"]
+        for name, d in zip(names, convs):
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _lib.check(self.lib.yv6_conv_fwd(self.handle, C.byref(d), sp))
                 e1.record()
-                evs.append((e0, e1))
-            torch.cuda.synchronize()
-            total_ms += sum(a.elapsed_time(b) for a, b in evs)
-        return total_ms / steps, flops, len(convs)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
+            wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
+            fl = 2.0 * d.N * ho * wo * d.Cout * d.Cin * d.kh * d.kw
+            by = 2.0 * d.N * (d.H * d.W * d.Cin + ho * wo * d.Cout)
+            out = (C.c_int32 * 10)()
+            _lib.check(self.lib.yv6_conv_plan(self.handle, C.byref(d), out))
+            rows.append(dict(name=name, cin=d.Cin, cout=d.Cout, k=d.kh, s=d.stride, hw=f"{ho}x{wo}", ms=ms,
+                             tflops=fl / ms / 1e9, gbs=by / ms / 1e6, plan=list(out)))
+        return rows

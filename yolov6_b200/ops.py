@@ -96,6 +96,6 @@ def conv_plan(x_shape, w_shape, stride=1, nsplit=1, force=None, device=0):
     if force:
         for k, v in force.items():
             setattr(d, "force_" + k, int(v))
-    out = (C.c_int32 * 8)()
+    out = (C.c_int32 * 10)()
     _lib.check(_lib.lib().yv6_conv_plan(_lib.handle(device), C.byref(d), out))
-    return dict(zip(("BW", "BH", "BI", "BN", "KB", "stages", "grid", "tiles"), list(out)))
+    return dict(zip(("BW", "BH", "BI", "BN", "KB", "stages", "grid", "tiles", "halo", "a_res"), list(out)))

@@ -1,0 +1,37 @@
+"""Synthetic checkpoints for benchmarking without network access.
+
+`randomize_(model, seed)` fills a freshly built model with seeded weights whose activations stay O(1)
+through ~70 layers and whose head emits a realistic spread of scores (a random-init YOLOv6 head emits
+~0.01 everywhere -- Detect.initialize_biases, reference effidehead.py:49-65 -- so NMS would have nothing
+to do).  BatchNorm statistics are randomised so that folding is non-trivial.
+"""
+import torch
+
+
+@torch.no_grad()
+def randomize_(model, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for name, t in model.state_dict().items():
+        shape = tuple(t.shape)
+        if name.endswith("num_batches_tracked") or name.startswith("detect.proj"):
+            continue
+        if name.endswith("running_mean"):
+            v = torch.randn(shape, generator=g) * 0.1
+        elif name.endswith("running_var"):
+            v = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith("alpha"):
+            v = torch.rand(shape, generator=g) + 0.5
+        elif ".cls_preds." in name:
+            # logits ~ N(-7, ~1.5): ~1% of the (anchor, class) pairs exceed the eval threshold 0.03, a few
+            # thousand NMS candidates per 640x640 image -- the regime of a trained detector
+            v = torch.randn(shape, generator=g) * (18.0 / shape[1] ** 0.5) if name.endswith("weight") else torch.full(shape, -7.0)
+        elif ".reg_preds." in name:
+            v = torch.randn(shape, generator=g) * (2.0 / shape[1] ** 0.5) if name.endswith("weight") else torch.full(shape, 1.0)
+        elif len(shape) == 4:
+            v = torch.randn(shape, generator=g) * (1.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+        elif name.endswith("weight"):
+            v = torch.rand(shape, generator=g) * 0.4 + 0.35
+        else:
+            v = torch.randn(shape, generator=g) * 0.1
+        t.copy_(v.to(t.device, t.dtype))
+    return model
