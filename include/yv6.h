@@ -87,7 +87,7 @@ typedef struct yv6_conv_desc {
   int32_t nsplit;           /* 1 or 3                                                           */
   /* tuning overrides, 0 = auto */
   int32_t force_bw, force_bh, force_bi, force_bn, force_stages, force_grid;
-  int32_t force_direct;     /* 1 = epilogue writes global memory directly instead of smem + TMA store */
+  int32_t force_direct;     /* epilogue store path: 0 auto, 1 direct global stores, 2 block-level (not per-warp) TMA store */
   int32_t force_halo;       /* 3x3 s1 halo-reuse mainloop: 0 = auto, 1 = force on (if eligible), -1 = off */
 } yv6_conv_desc;
 

@@ -87,7 +87,7 @@ def run_case(name, N, H, W, Cin, Cout, k, stride, act="relu", out_f32=False, nsp
         print(f"ERROR {name}: {e!r}", flush=True)
 
 
-def bench_case(name, N, H, W, Cin, Cout, k, stride, nsplit=1, force=None, iters=20):
+def bench_case(name, N, H, W, Cin, Cout, k, stride, nsplit=1, force=None, iters=20, act="relu", out_f32=False):
     xb = torch.randn(N, H, W, Cin, device=dev).to(torch.bfloat16)
     wb = (torch.randn(Cout, k, k, Cin, device=dev) / (k * k * Cin) ** 0.5).to(torch.bfloat16)
     if nsplit == 3:
@@ -95,17 +95,17 @@ def bench_case(name, N, H, W, Cin, Cout, k, stride, nsplit=1, force=None, iters=
         wb = torch.stack([wb, wb, wb])
     bias = ops.pad_bias(torch.zeros(Cout, device=dev), Cout)
     Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
-    y = torch.empty((3, N, Ho, Wo, Cout) if nsplit == 3 else (N, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
+    y = torch.empty((3, N, Ho, Wo, Cout) if nsplit == 3 else (N, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     try:
         for _ in range(3):
-            ops.conv_fwd(xb, wb, bias, y, stride=stride, act="relu", nsplit=nsplit, force=force)
+            ops.conv_fwd(xb, wb, bias, y, stride=stride, act=act, nsplit=nsplit, force=force)
         ts = []
         for _ in range(iters):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv_fwd(xb, wb, bias, y, stride=stride, act="relu", nsplit=nsplit, force=force)
+            ops.conv_fwd(xb, wb, bias, y, stride=stride, act=act, nsplit=nsplit, force=force)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -196,6 +196,13 @@ if __name__ == "__main__":
     run_case("halo_3x3_res_slices", 2, 24, 24, 64, 64, 3, 1, use_res=True, x_extra=64, y_extra=64, force=dict(halo=1))
     run_case("halo_3x3_silu_c128_cout80_f32", 2, 24, 24, 128, 80, 3, 1, act="silu", out_f32=True, force=dict(halo=1))
     run_case("direct_3x3_c128", 2, 40, 40, 128, 128, 3, 1, force=dict(direct=1))
+    run_case("blockstore_3x3_c128", 2, 40, 40, 128, 128, 3, 1, force=dict(direct=2))
+    run_case("blockstore_x3_cout80_f32", 2, 24, 24, 64, 80, 1, 1, nsplit=3, act="sigmoid", out_f32=True, force=dict(direct=2))
+    run_case("warpstore_bw32", 2, 64, 64, 64, 64, 3, 1, force=dict(bw=32, bh=4, halo=-1))
+    run_case("warpstore_bw128_1x1", 1, 4, 256, 64, 64, 1, 1, force=dict(bw=128, bh=1))
+    run_case("warpstore_bw4_s2", 2, 40, 40, 64, 64, 3, 2, force=dict(bw=4, bh=32))
+    run_case("persistent_many_tiles_grid3", 4, 64, 64, 64, 64, 3, 1, force=dict(grid=3))
+    run_case("persistent_grid2_nohalo_odd_tiles", 3, 48, 40, 64, 96, 3, 1, force=dict(grid=2, halo=-1))
     run_case("direct_1x1_cout80_f32", 2, 20, 20, 128, 80, 1, 1, act="sigmoid", out_f32=True, force=dict(direct=1))
     run_case("3x3_cout96_partial_chunk", 2, 20, 20, 64, 96, 3, 1)
     run_case("3x3_cout32", 2, 20, 20, 64, 32, 3, 1)
@@ -225,6 +232,10 @@ if __name__ == "__main__":
         bench_case(nm + "_nohalo", B, H_, W_, ci, co, k_, st, force=dict(halo=-1))
     bench_case("s1_512@20_halo", B, 20, 20, 512, 512, 3, 1, force=dict(halo=1))
     bench_case("s1_256@20_halo", B, 20, 20, 256, 256, 3, 1, force=dict(halo=1))
+    bench_case("1x1_64_64@80_silu", B, 80, 80, 64, 64, 1, 1, act="silu")
+    bench_case("3x3_64_64@80_silu", B, 80, 80, 64, 64, 3, 1, act="silu")
+    bench_case("1x1_64_80@80_sigmoid_f32", B, 80, 80, 64, 80, 1, 1, act="sigmoid", out_f32=True)
+    bench_case("1x1_64_64@160", B, 160, 160, 64, 64, 1, 1)
     bench_case("s1_256@40_bn128", B, 40, 40, 256, 256, 3, 1, force=dict(bn=128))
     bench_case("s1_256@40_bn256", B, 40, 40, 256, 256, 3, 1, force=dict(bn=256))
     bench_case("s1_256@40_direct", B, 40, 40, 256, 256, 3, 1, force=dict(direct=1))

@@ -31,7 +31,7 @@
 
 namespace yv6 {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups (TMEM acc 0 / 1)
 constexpr int kMaxStages = 12;
 constexpr int kTileRows = 128;
 
@@ -87,7 +87,9 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int group) {  // the 128 threads of one epilogue group
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
 
 struct TileCoord {
   int w0, h0, i0, n0;
@@ -158,6 +160,7 @@ __device__ __forceinline__ void store_chunk(const ConvKParams& p, int64_t off, i
 }
 
 constexpr int kCBufBytes = kTileRows * 128;  // one staged output chunk: 128 rows x 128 B
+constexpr int kCBufCount = 4;               // two per epilogue group
 
 // bias + activation (+ residual) for 16 consecutive output channels of one pixel
 __device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32_t (&r)[16], int n, int ncol,
@@ -179,9 +182,12 @@ __device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32
   if (p.act == YV6_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else if (p.act != YV6_ACT_NONE) {
+  } else if (p.act == YV6_ACT_SILU) {       // x * sigmoid(x); ex2/rcp approximations are ~1e-7 relative
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
+    for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+  } else if (p.act == YV6_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
   }
   if (p.res != nullptr && valid && ncol > 0) {
     for (int pl = 0; pl < p.res_planes; ++pl) {
@@ -214,7 +220,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.a_region_bytes;
   uint8_t* sC = sB + (size_t)p.b_region_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * kCBufBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kCBufCount * kCBufBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -416,19 +422,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ================================ epilogue ================================
+    // Two groups of four warps; group g owns TMEM accumulator g, i.e. every second tile of this CTA, so
+    // an epilogue may take up to two mainloop times before it stalls the MMA warp.
+    const int group = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int bw = row % p.BW;
     const int tq = row / p.BW;
     const int bh = tq % p.BH;
     const int bi = tq / p.BH;
-    const bool issuer = (threadIdx.x == 64);  // first epilogue thread issues the TMA stores
-    const uint32_t row_smem = (uint32_t)row * 128u;
-    const uint32_t row_xor = (uint32_t)(row & 7);
-    int acc = 0;
+    uint8_t* gC = sC + group * 2 * kCBufBytes;  // this group's two staging buffers
+    const bool f32 = (p.y_dtype == YV6_DT_F32);
     uint32_t acc_phase = 0;
     int cbuf = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int img = t.i0 + bi, ho = t.h0 + bh, wo = t.w0 + bw;
       const bool valid = (row < p.rows) && (img < p.N) && (ho < p.Ho) && (wo < p.Wo);
@@ -436,71 +443,120 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                           (int64_t)wo * p.y_w_stride;
       const int64_t roff = (int64_t)img * p.res_img_stride + (int64_t)ho * p.res_h_stride +
                            (int64_t)wo * p.res_w_stride;
-      mbar_wait(&tfull[acc], acc_phase);
+      mbar_wait(&tfull[group], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-      if (p.tma_store) {
-        // ---- stage 128-byte rows in swizzled smem, one TMA store per chunk (and plane) ----
-        const bool f32 = (p.y_dtype == YV6_DT_F32);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * p.BN);
+      if (p.tma_store == 2) {
+        // ---- per-warp stores: the 32 rows of this warp form a box of the output, so each warp stages
+        //      its rows (4 KB, swizzled) and issues its own TMA store -- no block-level barrier at all.
+        const int wrow0 = q * 32;
+        const int sw0 = t.w0 + wrow0 % p.BW, sh0 = t.h0 + wrow0 / p.BW;
+        const uint32_t lrow = (uint32_t)lane * 128u, lxor = (uint32_t)(lane & 7);
         for (int c0 = 0; c0 < p.BN; c0 += p.c_chunk) {
-          const int nsub = min(p.c_chunk, p.BN - c0) >> 4;  // 16-column groups in this chunk (<= 4)
-          uint32_t r[4][16];
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < nsub) tmem_ld16(taddr + (uint32_t)(c0 + 16 * s), r[s]);
-          tmem_ld_wait();
-          float v[4][16];
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < nsub) {
-              const int n = t.n0 + c0 + 16 * s;
-              epilogue_math(p, r[s], n, min(16, p.Cout - n), valid, roff, v[s]);
-            }
+          const int nsub = min(p.c_chunk, p.BN - c0) >> 4;
           for (int pl = 0; pl < p.out_planes; ++pl) {
-            uint8_t* buf = sC + cbuf * kCBufBytes;
-            if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer is done
-            epi_bar_sync();
-            if (row < p.rows) {
-              const uint32_t base = smem_u32(buf) + row_smem;
+            uint8_t* buf = gC + cbuf * kCBufBytes + q * 4096;
+            if (lane == 0) tma_store_wait_read<1>();  // this warp's store from two chunks ago has read its buffer
+            __syncwarp();
+            const uint32_t base = smem_u32(buf) + lrow;
+            uint32_t r[2][16];
+            tmem_ld16(taddr + (uint32_t)c0, r[0]);
 #pragma unroll
-              for (int s = 0; s < 4; ++s)
-                if (s < nsub) {
+            for (int sb = 0; sb < 4; ++sb) {
+              if (sb < nsub) {
+                tmem_ld_wait();
+                if (sb + 1 < nsub) tmem_ld16(taddr + (uint32_t)(c0 + 16 * (sb + 1)), r[(sb + 1) & 1]);
+                const int n = t.n0 + c0 + 16 * sb;
+                float v[16];
+                epilogue_math(p, r[sb & 1], n, min(16, p.Cout - n), valid, roff, v);
+                for (int k = 0; k < pl; ++k) {  // bf16x3: peel the planes already written
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+                }
+                if (f32) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t a = base + ((((uint32_t)(4 * sb + j)) ^ lxor) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                 : "memory");
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const uint32_t a = base + ((((uint32_t)(2 * sb + j)) ^ lxor) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                                 "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                                 "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                                 : "memory");
+                  }
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_5d(&tmC, buf, t.n0 + c0, sw0, sh0, t.i0, pl);
+              tma_store_commit();
+            }
+            cbuf ^= 1;
+          }
+        }
+      } else if (p.tma_store == 1) {
+        // ---- block-level store: tiles whose warps do not map to boxes (e.g. 20x5): the group stages the
+        //      whole 128-row chunk, synchronises on its named barrier, one thread issues the TMA store.
+        const bool issuer = (q == 2 && lane == 0);  // first thread of the group
+        const uint32_t row_smem = (uint32_t)row * 128u, row_xor = (uint32_t)(row & 7);
+        for (int c0 = 0; c0 < p.BN; c0 += p.c_chunk) {
+          const int nsub = min(p.c_chunk, p.BN - c0) >> 4;
+          for (int pl = 0; pl < p.out_planes; ++pl) {
+            uint8_t* buf = gC + cbuf * kCBufBytes;
+            if (issuer) tma_store_wait_read<1>();
+            epi_bar_sync(group);
+            const uint32_t base = smem_u32(buf) + row_smem;
+            uint32_t r[2][16];
+            tmem_ld16(taddr + (uint32_t)c0, r[0]);
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb) {
+              if (sb < nsub) {
+                tmem_ld_wait();
+                if (sb + 1 < nsub) tmem_ld16(taddr + (uint32_t)(c0 + 16 * (sb + 1)), r[(sb + 1) & 1]);
+                const int n = t.n0 + c0 + 16 * sb;
+                float v[16];
+                epilogue_math(p, r[sb & 1], n, min(16, p.Cout - n), valid, roff, v);
+                for (int k = 0; k < pl; ++k) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+                }
+                if (row < p.rows) {
                   if (f32) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                      const uint32_t a = base + ((((uint32_t)(4 * s + j)) ^ row_xor) << 4);
-                      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[s][4 * j]),
-                                   "f"(v[s][4 * j + 1]), "f"(v[s][4 * j + 2]), "f"(v[s][4 * j + 3])
+                      const uint32_t a = base + ((((uint32_t)(4 * sb + j)) ^ row_xor) << 4);
+                      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                   "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
                                    : "memory");
                     }
                   } else {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                      const uint32_t a = base + ((((uint32_t)(2 * s + j)) ^ row_xor) << 4);
-                      const uint32_t w0 = pack_bf16x2(v[s][8 * j + 0], v[s][8 * j + 1]);
-                      const uint32_t w1 = pack_bf16x2(v[s][8 * j + 2], v[s][8 * j + 3]);
-                      const uint32_t w2 = pack_bf16x2(v[s][8 * j + 4], v[s][8 * j + 5]);
-                      const uint32_t w3 = pack_bf16x2(v[s][8 * j + 6], v[s][8 * j + 7]);
-                      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1),
-                                   "r"(w2), "r"(w3)
+                      const uint32_t a = base + ((((uint32_t)(2 * sb + j)) ^ row_xor) << 4);
+                      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                                   "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                                   "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
                                    : "memory");
                     }
                   }
                 }
+              }
             }
             fence_proxy_async_smem();
-            epi_bar_sync();
+            epi_bar_sync(group);
             if (issuer) {
               tma_store_5d(&tmC, buf, t.n0 + c0, t.w0, t.h0, t.i0, pl);
               tma_store_commit();
             }
             cbuf ^= 1;
-            if (pl + 1 < p.out_planes) {  // bf16x3: peel the next plane off the remainder
-#pragma unroll
-              for (int s = 0; s < 4; ++s)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[s][j] -= __bfloat162float(__float2bfloat16_rn(v[s][j]));
-            }
           }
         }
       } else {
@@ -517,11 +573,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      mbar_arrive(&tempty[group]);
+      acc_phase ^= 1;
     }
-    if (issuer && p.tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -586,7 +641,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // output staging: 128-byte rows -> 64 bf16 or 32 fp32 columns per TMA-stored chunk
   const int esz = (d->y_dtype == YV6_DT_F32) ? 4 : 2;
   k.c_chunk = 128 / esz;
-  k.tma_store = (d->force_direct == 0) && ((d->y_w_stride * esz) % 16 == 0) && ((d->y_h_stride * esz) % 16 == 0) &&
+  k.tma_store = (d->force_direct != 1) && ((d->y_w_stride * esz) % 16 == 0) && ((d->y_h_stride * esz) % 16 == 0) &&
                 ((d->y_img_stride * esz) % 16 == 0) && ((d->y_plane_stride * esz) % 16 == 0) &&
                 ((reinterpret_cast<uintptr_t>(d->y) & 15) == 0);
   // N tiling is chosen together with the M tiling below
@@ -599,8 +654,8 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     YV6_REQUIRE(k.BW * k.BH * k.BI <= kTileRows && k.BW * d->stride <= 256 && k.BH * d->stride <= 256,
                 "conv: forced tile %dx%dx%d invalid", k.BW, k.BH, k.BI);
   } else {
-    long best_tiles = -1;
-    int bestw = 1, besth = 1, besti = 1;
+    long best_tiles = -1, best_box_tiles = -1;
+    int bestw = 1, besth = 1, besti = 1, boxw = 0, boxh = 0;
     const int maxbw = std::min(std::min(k.Wo, kTileRows), 256 / d->stride);
     for (int bw = 1; bw <= maxbw; ++bw) {
       const int maxbh = std::min(std::min(k.Ho, kTileRows / bw), 256 / d->stride);
@@ -615,6 +670,23 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
           besti = bi;
         }
       }
+    }
+    // "warp-box" tiles: 128 rows whose 32-row quarters are boxes of the output (BW | 32 or 32 | BW), which
+    // lets every epilogue warp TMA-store its own rows without a block barrier; preferred within 8 % of the best
+    for (int bw = 1; bw <= std::min(kTileRows, 256 / d->stride); bw <<= 1) {
+      const int bh = kTileRows / bw;
+      if (bh * d->stride > 256) continue;
+      long tiles = (long)ceil_div(k.Wo, bw) * ceil_div(k.Ho, bh) * d->N;
+      if (best_box_tiles < 0 || tiles < best_box_tiles || (tiles == best_box_tiles && bw > boxw)) {
+        best_box_tiles = tiles;
+        boxw = bw;
+        boxh = bh;
+      }
+    }
+    if (best_box_tiles > 0 && best_box_tiles * 100 <= best_tiles * 108 && d->force_bi == 0) {
+      bestw = boxw;
+      besth = boxh;
+      besti = 1;
     }
     k.BW = bestw;
     k.BH = besth;
@@ -661,6 +733,8 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   k.tiles_n = ceil_div(d->Cout, k.BN);
   if (k.tiles_n > 1 && k.tma_store && (k.BN % bn_align) != 0) k.tma_store = 0;
   k.rows = k.BW * k.BH * k.BI;
+  if (k.tma_store && k.rows == kTileRows && k.BI == 1 && (32 % k.BW == 0 || k.BW % 32 == 0) && d->force_direct != 2)
+    k.tma_store = 2;  // per-warp stores
   k.tiles_w = ceil_div(k.Wo, k.BW);
   k.tiles_h = ceil_div(k.Ho, k.BH);
   k.tiles_i = ceil_div(d->N, k.BI);
@@ -671,7 +745,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // smem ring(s)
   k.a_stage_bytes = kTileRows * k.kb_bytes;
   k.b_stage_bytes = ((k.BN * k.kb_bytes + 1023) / 1024) * 1024;
-  const int budget = h->max_smem_optin - 1024 - 1024 - 2 * kCBufBytes;
+  const int budget = h->max_smem_optin - 1024 - 1024 - kCBufCount * kCBufBytes;
   if (k.halo) {
     const int b_tiles = k.npairs * k.cin_blocks * 9;   // B tiles one output tile consumes
     k.b_resident = (k.tiles_n == 1 && b_tiles <= kMaxBStages && d->force_stages == 0 &&
@@ -697,7 +771,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     k.a_region_bytes = stages * k.a_stage_bytes;
     k.b_region_bytes = stages * k.b_stage_bytes;
   }
-  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + 2 * kCBufBytes + 1024 + 1024;
+  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + 1024 + 1024;
 
   int cols = 32;
   while (cols < 2 * k.BN) cols *= 2;
@@ -809,6 +883,10 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
     cuuint64_t strides[4] = {(uint64_t)d->y_w_stride * esz, (uint64_t)d->y_h_stride * esz,
                              (uint64_t)d->y_img_stride * esz, plane_stride};
     cuuint32_t box[5] = {(cuuint32_t)k.c_chunk, (cuuint32_t)k.BW, (cuuint32_t)k.BH, (cuuint32_t)k.BI, 1};
+    if (k.tma_store == 2) {  // one warp = 32 consecutive rows of the tile
+      box[1] = (cuuint32_t)std::min(k.BW, 32);
+      box[2] = (cuuint32_t)std::max(1, 32 / k.BW);
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult cr = h->encode_tiled(&tmC, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                                   5, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
