@@ -3,8 +3,8 @@
 
 Bars: integer outputs (fg mask, labels, nonzero pattern of target_scores) exact; float64 target
 scores rtol 1e-9 (pow() may differ by an ulp); loss / loss_items rtol 1e-6 (the kernel evaluates a
-few f32 sub-expressions of the reference in f64; BASELINE.json's bar is 1e-4); fp32 gradients
-rtol 1e-4 + atol 1e-7."""
+few f32 sub-expressions of the reference in f64; 2e-5 for DFL models; BASELINE.json's bar is 1e-4);
+fp32 gradients rtol 1e-4 + atol 1e-7."""
 import numpy as np
 import pytest
 import torch
@@ -49,13 +49,17 @@ def test_compute_loss_matches_reference_golden(case):
     assert np.array_equal(labels.cpu().numpy()[fg], ref_labels[fg])
     nz = scores.cpu().nonzero().numpy().astype(np.int32)
     assert np.array_equal(nz, g[f"{name}_scores_idx"])
-    np.testing.assert_allclose(scores.cpu()[scores.cpu() != 0].numpy(), g[f"{name}_scores_val"], rtol=1e-9 if epoch >= warm else 1e-6)
+    # with DFL the predicted boxes come from an fp32 softmax expectation (expf vs torch's softmax differ by an
+    # ulp or two); IoU^6 amplifies that to ~3e-6 in the target scores.  Plain-ltrb models match to 1e-9.
+    s_tol = 2e-5 if use_dfl else (1e-9 if epoch >= warm else 1e-6)
+    np.testing.assert_allclose(scores.cpu()[scores.cpu() != 0].numpy(), g[f"{name}_scores_val"], rtol=s_tol)
     # the golden boxes were captured after the reference's in-place `target_bboxes /= stride_tensor` (loss.py:158)
     stride_col = torch.cat([torch.full((h * w,), float(s), dtype=torch.float64) for (h, w), s in zip(sizes, strides)])
     got_boxes = (bboxes.cpu() / stride_col.view(1, -1, 1)).numpy()[fg]
     np.testing.assert_allclose(got_boxes, g[f"{name}_bboxes_fg"], rtol=1e-12)
-    assert abs(loss.item() - float(g[f"{name}_loss"])) <= 1e-6 * abs(float(g[f"{name}_loss"]))
-    np.testing.assert_allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=1e-6, atol=1e-9)
+    l_tol = 2e-5 if use_dfl else 1e-6
+    assert abs(loss.item() - float(g[f"{name}_loss"])) <= l_tol * abs(float(g[f"{name}_loss"]))
+    np.testing.assert_allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=l_tol, atol=1e-9)
     gs = psd.grad.cpu()
     np.testing.assert_allclose(gs[torch.from_numpy(fg)].double().numpy(), g[f"{name}_grad_scores_fg"], rtol=1e-4, atol=1e-7)
     np.testing.assert_allclose(gs.flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=1e-4, atol=1e-7)
