@@ -33,6 +33,7 @@ enum {
 
 enum { YV6_ACT_NONE = 0, YV6_ACT_RELU = 1, YV6_ACT_SILU = 2, YV6_ACT_SIGMOID = 3 };
 enum { YV6_DT_BF16 = 0, YV6_DT_F32 = 1, YV6_DT_U8 = 2 };
+#define YV6_PAD_SAME (-1000000)
 
 typedef struct yv6_handle yv6_handle;
 
@@ -89,6 +90,11 @@ typedef struct yv6_conv_desc {
   int32_t force_bw, force_bh, force_bi, force_bn, force_stages, force_grid;
   int32_t force_direct;     /* epilogue store path: 0 auto, 1 direct global stores, 2 block-level (not per-warp) TMA store */
   int32_t force_halo;       /* 3x3 s1 halo-reuse mainloop: 0 = auto, 1 = force on (if eligible), -1 = off */
+  /* generalisations used by the backward pass (dgrad of stride-2 convs = four parity sub-convolutions with
+   * 1- or 2-tap kernels): kh, kw in 1..3 independently; `pad` pads rows, pad_w columns (YV6_PAD_SAME = pad);
+   * out_h / out_w > 0 override the output size (far-side reads are zero filled). */
+  int32_t pad_w, out_h, out_w;
+  int32_t force_groups;     /* epilogue warp groups: 0 auto (4 when BN <= 128, else 2), 2 = force two */
 } yv6_conv_desc;
 
 int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);
@@ -101,16 +107,16 @@ int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out10);
  * (reference yolov6/models/efficientrep.py:28-33), fused with the input conversion of
  * Trainer.prepro_data / Inferer.process_image (core/engine.py:407-410, core/inferer.py:162-171):
  * x is NCHW fp32 in [0,1] or NCHW uint8 (then scaled by in_scale = 1/255 on the fly).
- * Output NHWC bf16 (1 or 3 planes).  w / bias are HOST pointers (27*Cout + Cout floats travel as
- * kernel parameters): w is fp32 KRSC [Cout][3][3][3].
+ * Output NHWC bf16 (1 or 3 planes).  w / bias are DEVICE pointers: w is fp32 [3][3][3][Cout]
+ * (tap-major, Cout innermost), bias fp32 [Cout] or NULL.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct yv6_stem_desc {
   const void* x;            /* device, [N,3,H,W] fp32 or uint8                                  */
   int32_t x_dtype;          /* YV6_DT_F32 or YV6_DT_U8                                          */
   float in_scale;           /* multiplier for uint8 input (1/255)                               */
   int32_t N, H, W;
-  const float* w;           /* HOST fp32 [Cout][3][3][3]                                        */
-  const float* bias;        /* HOST fp32 [Cout] or NULL                                         */
+  const float* w;           /* device fp32 [kh=3][kw=3][cin=3][Cout]                            */
+  const float* bias;        /* device fp32 [Cout] or NULL                                       */
   int32_t Cout, act;        /* Cout in {16,32,48,64}                                            */
   void* y;                  /* device bf16 [planes][N,H/2,W/2,Cout]                             */
   int64_t y_plane_stride;
@@ -221,6 +227,60 @@ typedef struct yv6_loss_desc {
 } yv6_loss_desc;
 int64_t yv6_det_loss_workspace_bytes(int32_t B, int32_t A);
 int yv6_det_loss(yv6_handle* h, const yv6_loss_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training of the conv stack (train form): what autograd + cuDNN do for the reference's
+ * Trainer.train_in_steps (yolov6/core/engine.py:142-176) under ConvModule.forward (conv -> BN(batch
+ * stats) -> act, layers/common.py:46-49) and RepVGGBlock.forward (three BN-ed branches, common.py:245-255).
+ * Forward = yv6_conv_fwd (no bias / act) + yv6_bn_stats + yv6_bn_finalize + yv6_bn_apply_fwd;
+ * backward = yv6_bn_bwd -> yv6_conv_fwd with transposed / rotated weights (dgrad) + yv6_conv_wgrad.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dW[co][r][s][ci] (fp32 KRSC, ACCUMULATED into -- zero it first) from x [N,H,W,Cin] and dy [N,Ho,Wo,Cout]. */
+typedef struct yv6_wgrad_desc {
+  const void* x;  int32_t N, H, W, Cin, x_c_total;      /* bf16 NHWC (channel slice of a wider buffer allowed) */
+  const void* dy; int32_t Cout, dy_c_total;             /* bf16 NHWC gradient of the conv output               */
+  int32_t kh, kw, stride, pad;
+  float* dw;                                            /* fp32 [Cout][kh][kw][Cin]                            */
+  int32_t force_ksplit;                                 /* 0 = auto                                            */
+} yv6_wgrad_desc;
+int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stream);
+
+/* Per-channel sum and sum of squares (float64) of an NHWC bf16 tensor slice with channel pitch `pitch`. */
+int yv6_bn_stats(yv6_handle* h, const void* x, int64_t pixels, int32_t C, int64_t pitch, double* sum, double* sumsq,
+                 void* stream);
+/* mean / invstd (biased var + eps), scale = gamma*invstd, shift = beta - mean*scale, and the running-stat
+ * update of nn.BatchNorm2d (momentum, unbiased var); running_* may be NULL. */
+int yv6_bn_finalize(yv6_handle* h, const double* sum, const double* sumsq, double count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* mean_out, float* invstd_out, float* scale, float* shift, int32_t C, void* stream);
+
+/* Up to three BN-ed branches summed and activated (RepVGG: conv3x3, conv1x1, identity; ConvModule: one). */
+typedef struct yv6_bn_desc {
+  int32_t nb, act, C;
+  int64_t pixels;
+  const void* x[3];  int64_t x_pitch[3];                /* branch inputs (bf16 NHWC slices)                    */
+  const float* mean[3]; const float* invstd[3]; const float* scale[3]; const float* shift[3];
+  void* y; int64_t y_pitch;                             /* block output (fwd: written; bwd: relu mask)         */
+  /* backward only */
+  const void* dy; int64_t dy_pitch;                     /* gradient w.r.t. the block output                    */
+  double* s1; double* s2[3];                            /* [C] out: sum dz (= dbeta of every branch), sum dz*xhat_b (= dgamma_b) */
+  void* dx[3]; int64_t dx_pitch[3]; int32_t accumulate[3];  /* gradient w.r.t. each branch input              */
+} yv6_bn_desc;
+int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);
+int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);
+
+/* Head gradients: level slice [off, off+hw) of the [B,A,ch] fp32 tensors -> dense NHWC bf16 [B,hw,ch_pad];
+ * with `scores` the sigmoid backward dlogit = dscore * s * (1 - s) of effidehead.py:85 is applied. */
+int yv6_head_grad_prep(yv6_handle* h, const float* grad, const float* scores_or_null, int32_t B, int32_t A, int32_t ch,
+                       int32_t level_off, int32_t level_hw, int32_t ch_pad, void* out_bf16, void* stream);
+/* Backward of one MaxPool2d(5,1,2) of SPPF (common.py:104-112): dx (+)= scatter of dy to the window arg-max. */
+int yv6_maxpool5_bwd(yv6_handle* h, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, int32_t N,
+                     int32_t H, int32_t W, int32_t C, float* dx_scratch, void* dx, int64_t dx_pitch, int32_t accumulate,
+                     void* stream);
+/* Weight gradient of the 3-channel stem conv (3x3 stride 2): dw fp32 [Cout][3][3][3] (overwritten). */
+int yv6_stem_wgrad(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy, int64_t dy_pitch,
+                   int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libyolov6_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
 DT_BF16, DT_F32, DT_U8 = 0, 1, 2
+PAD_SAME = -1000000
 ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU, "sigmoid": ACT_SIGMOID}
 
 
@@ -32,6 +33,7 @@ class ConvDesc(C.Structure):
         ("nsplit", C.c_int32),
         ("force_bw", C.c_int32), ("force_bh", C.c_int32), ("force_bi", C.c_int32), ("force_bn", C.c_int32),
         ("force_stages", C.c_int32), ("force_grid", C.c_int32), ("force_direct", C.c_int32), ("force_halo", C.c_int32),
+        ("pad_w", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32), ("force_groups", C.c_int32),
     ]
 
 
@@ -40,7 +42,7 @@ class StemDesc(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_dtype", C.c_int32), ("in_scale", C.c_float),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-        ("w", C.POINTER(C.c_float)), ("bias", C.POINTER(C.c_float)),
+        ("w", C.c_void_p), ("bias", C.c_void_p),
         ("Cout", C.c_int32), ("act", C.c_int32),
         ("y", C.c_void_p), ("y_plane_stride", C.c_int64), ("nsplit", C.c_int32),
     ]

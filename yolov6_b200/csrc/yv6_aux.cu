@@ -16,8 +16,8 @@ namespace yv6 {
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemMaxCout = 64;
 struct StemParams {
-  float w[27 * kStemMaxCout];  // [tap(r,s)][cin][cout]
-  float b[kStemMaxCout];
+  const float* w;      // device fp32 [tap(r,s)][cin][cout] (27 x Cout)
+  const float* b;      // device fp32 [Cout] or null
   const void* x;
   __nv_bfloat16* y;
   int64_t y_plane_stride;
@@ -26,20 +26,25 @@ struct StemParams {
   float in_scale;
 };
 
+// One thread = one output pixel x all COUT channels; the 27 x COUT weights sit in shared memory and are
+// read as float4 broadcasts (every lane reads the same address).  Outputs are staged so that the global
+// stores are full 16-byte vectors of consecutive pixels.
 template <int COUT>
-__global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemParams p) {
-  __shared__ __align__(16) __nv_bfloat16 tile[128 * COUT];
+__global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
+  __shared__ __align__(16) float sw[27 * COUT];
+  __shared__ __align__(16) __nv_bfloat16 tile[256 * COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += 256) sw[i] = p.w[i];
+  __syncthreads();
   const int64_t total = (int64_t)p.N * p.Ho * p.Wo;
-  const int64_t pix0 = (int64_t)blockIdx.x * 128;
+  const int64_t pix0 = (int64_t)blockIdx.x * 256;
   const int64_t pix = pix0 + threadIdx.x;
   float acc[COUT];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = p.b[c];
+  for (int c = 0; c < COUT; ++c) acc[c] = p.b ? p.b[c] : 0.f;
   if (pix < total) {
     const int wo = (int)(pix % p.Wo);
     const int ho = (int)((pix / p.Wo) % p.Ho);
     const int n = (int)(pix / ((int64_t)p.Wo * p.Ho));
-    float in[27];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int hi = 2 * ho - 1 + r;
@@ -55,22 +60,24 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemP
             v = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + idx) * p.in_scale
                        : __ldg(reinterpret_cast<const float*>(p.x) + idx);
           }
-          in[(r * 3 + s) * 3 + c] = v;
+          const float4* wk = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + c) * COUT]);
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 w4 = wk[c4];
+            acc[4 * c4 + 0] = fmaf(v, w4.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(v, w4.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(v, w4.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(v, w4.w, acc[4 * c4 + 3]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(in[k], p.w[k * COUT + c], acc[c]);
-    }
-#pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = act_apply(acc[c], p.act);
   }
-  // stage the 128 x COUT tile so that global stores are full, coalesced 16-byte vectors
-  const int nvec = 128 * COUT / 8;
+  const int nvec = 256 * COUT / 8;
   const int64_t left = total - pix0;
-  const int64_t valid_elems = (left < 128 ? left : (int64_t)128) * COUT;
+  const int64_t valid_elems = (left < 256 ? left : (int64_t)256) * COUT;
   for (int pl = 0; pl < p.planes; ++pl) {
     if (pl) __syncthreads();
 #pragma unroll
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemP
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(p.y + pl * p.y_plane_stride + pix0 * COUT);
     const uint4* src = reinterpret_cast<const uint4*>(tile);
-    for (int i = threadIdx.x; i < nvec; i += 128)
+    for (int i = threadIdx.x; i < nvec; i += 256)
       if ((int64_t)i * 8 < valid_elems) dst[i] = src[i];
   }
 }
@@ -93,9 +100,9 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemP
 // ------------------------------------------------------------------------------------------------
 // SPPF pooling: reference SPPFModule / CSPSPPFModule (common.py:106-112, 150-158):
 //   y1 = pool5(x), y2 = pool5(y1), y3 = pool5(y2), cat([x, y1, y2, y3]).
-// With -inf padding the chained pools equal 5x5 / 9x9 / 13x13 windows clipped to the image, so one
-// pass computes all three.  x lives in channel slice 0 of the 4C-wide concat buffer; the results
-// are written to slices 1..3 of the same buffer.  One thread = one pixel x 8 channels.
+// With -inf padding the chained pools equal 5x5 / 9x9 / 13x13 windows clipped to the image.  One block
+// = one image x 8 channels: the HxW plane is loaded into shared memory once, row maxima of the three
+// window sizes are formed separably, then column maxima; results go to slices 1..3 of the concat buffer.
 // ------------------------------------------------------------------------------------------------
 struct PoolParams {
   __nv_bfloat16* buf;  // [planes][N,H,W,c_total]
@@ -115,33 +122,38 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
 }
 
 __global__ void __launch_bounds__(256) sppf_pool_kernel(const PoolParams p) {
+  extern __shared__ float sp[];                 // [4][H*W][8]: x, rowmax5, rowmax9, rowmax13
   const int cgs = p.C / 8;
-  const int64_t total = (int64_t)p.N * p.H * p.W * cgs;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cg = (int)(idx % cgs);
-  const int w = (int)((idx / cgs) % p.W);
-  const int h = (int)((idx / ((int64_t)cgs * p.W)) % p.H);
-  const int n = (int)(idx / ((int64_t)cgs * p.W * p.H));
-  float m5[8], m9[8], m13[8];
+  const int n = blockIdx.x / cgs, cg = blockIdx.x % cgs;
+  const int HW = p.H * p.W;
+  float* sx = sp;
+  float* r5 = sp + (size_t)HW * 8;
+  float* r9 = r5 + (size_t)HW * 8;
+  float* r13 = r9 + (size_t)HW * 8;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int64_t off = ((int64_t)n * HW + i) * p.c_total + cg * 8;
+    float v[8];
+    load8(p.buf + off, v);
+    for (int pl = 1; pl < p.planes; ++pl) {
+      float t[8];
+      load8(p.buf + pl * p.plane_stride + off, t);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m5[j] = m9[j] = m13[j] = -INFINITY;
-  for (int dy = -6; dy <= 6; ++dy) {
-    const int hh = h + dy;
-    if (hh < 0 || hh >= p.H) continue;
+      for (int j = 0; j < 8; ++j) v[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sx[i * 8 + j] = v[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {   // horizontal maxima
+    const int h = i / p.W, w = i % p.W;
+    float m5[8], m9[8], m13[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m5[j] = m9[j] = m13[j] = -INFINITY;
     for (int dx = -6; dx <= 6; ++dx) {
       const int ww = w + dx;
       if (ww < 0 || ww >= p.W) continue;
-      const int64_t off = (((int64_t)n * p.H + hh) * p.W + ww) * p.c_total + cg * 8;
-      float v[8];
-      load8(p.buf + off, v);
-      for (int pl = 1; pl < p.planes; ++pl) {
-        float t[8];
-        load8(p.buf + pl * p.plane_stride + off, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += t[j];
-      }
-      const int ad = max(abs(dy), abs(dx));
+      const float* v = &sx[(h * p.W + ww) * 8];
+      const int ad = abs(dx);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         m13[j] = fmaxf(m13[j], v[j]);
@@ -149,23 +161,42 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(const PoolParams p) {
         if (ad <= 2) m5[j] = fmaxf(m5[j], v[j]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { r5[i * 8 + j] = m5[j]; r9[i * 8 + j] = m9[j]; r13[i * 8 + j] = m13[j]; }
   }
-  const int64_t o = (((int64_t)n * p.H + h) * p.W + w) * p.c_total + cg * 8;
-  float* res[3] = {m5, m9, m13};
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {   // vertical maxima of the row maxima, then store
+    const int h = i / p.W, w = i % p.W;
+    float m[3][8];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    float* m = res[k];
-    for (int pl = 0; pl < p.planes; ++pl) {
-      uint32_t wds[4];
+    for (int j = 0; j < 8; ++j) m[0][j] = m[1][j] = m[2][j] = -INFINITY;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int hh = h + dy;
+      if (hh < 0 || hh >= p.H) continue;
+      const int o = (hh * p.W + w) * 8;
+      const int ad = abs(dy);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
-        wds[j] = *reinterpret_cast<uint32_t*>(&b2);
-        m[2 * j] -= __low2float(b2);
-        m[2 * j + 1] -= __high2float(b2);
+      for (int j = 0; j < 8; ++j) {
+        m[2][j] = fmaxf(m[2][j], r13[o + j]);
+        if (ad <= 4) m[1][j] = fmaxf(m[1][j], r9[o + j]);
+        if (ad <= 2) m[0][j] = fmaxf(m[0][j], r5[o + j]);
       }
-      *reinterpret_cast<uint4*>(p.buf + pl * p.plane_stride + o + (int64_t)(k + 1) * p.C) =
-          make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    }
+    const int64_t o = ((int64_t)n * HW + i) * p.c_total + cg * 8;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      for (int pl = 0; pl < p.planes; ++pl) {
+        uint32_t wds[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(m[k][2 * j], m[k][2 * j + 1]);
+          wds[j] = *reinterpret_cast<uint32_t*>(&b2);
+          m[k][2 * j] -= __low2float(b2);
+          m[k][2 * j + 1] -= __high2float(b2);
+        }
+        *reinterpret_cast<uint4*>(p.buf + pl * p.plane_stride + o + (int64_t)(k + 1) * p.C) =
+            make_uint4(wds[0], wds[1], wds[2], wds[3]);
+      }
     }
   }
 }
@@ -243,10 +274,8 @@ extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream)
   YV6_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "stem: nsplit must be 1 or 3");
   YV6_REQUIRE(d->x_dtype == YV6_DT_F32 || d->x_dtype == YV6_DT_U8, "stem: image must be fp32 or uint8");
   StemParams p;
-  // weights arrive as host fp32 KRSC [Cout][3][3][3]; re-order to [tap][cin][cout]
-  for (int co = 0; co < d->Cout; ++co)
-    for (int k = 0; k < 27; ++k) p.w[k * d->Cout + co] = d->w[co * 27 + k];
-  for (int co = 0; co < d->Cout; ++co) p.b[co] = d->bias ? d->bias[co] : 0.f;
+  p.w = d->w;
+  p.b = d->bias;
   p.x = d->x;
   p.y = reinterpret_cast<__nv_bfloat16*>(d->y);
   p.y_plane_stride = d->y_plane_stride;
@@ -260,13 +289,13 @@ extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream)
   p.act = d->act;
   p.planes = d->nsplit;
   const int64_t total = (int64_t)p.N * p.Ho * p.Wo;
-  const unsigned grid = (unsigned)((total + 127) / 128);
+  const unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t s = (cudaStream_t)stream;
   switch (d->Cout) {
-    case 16: stem_kernel<16><<<grid, 128, 0, s>>>(p); break;
-    case 32: stem_kernel<32><<<grid, 128, 0, s>>>(p); break;
-    case 48: stem_kernel<48><<<grid, 128, 0, s>>>(p); break;
-    default: stem_kernel<64><<<grid, 128, 0, s>>>(p); break;
+    case 16: stem_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    case 32: stem_kernel<32><<<grid, 256, 0, s>>>(p); break;
+    case 48: stem_kernel<48><<<grid, 256, 0, s>>>(p); break;
+    default: stem_kernel<64><<<grid, 256, 0, s>>>(p); break;
   }
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
@@ -276,9 +305,15 @@ extern "C" int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int
                              int32_t nsplit, int64_t plane_stride, void* stream) {
   YV6_REQUIRE(h && buf, "sppf_pool: null argument");
   YV6_REQUIRE(C % 8 == 0 && c_total >= 4 * C && c_total % 8 == 0, "sppf_pool: bad channels C=%d c_total=%d", C, c_total);
+  const size_t smem = (size_t)4 * H * W * 8 * sizeof(float);
+  YV6_REQUIRE(smem <= (size_t)h->max_smem_optin, "sppf_pool: %dx%d plane does not fit in shared memory", H, W);
   PoolParams p{reinterpret_cast<__nv_bfloat16*>(buf), plane_stride, N, H, W, C, c_total, nsplit == 3 ? 3 : 1};
-  const int64_t total = (int64_t)N * H * W * (C / 8);
-  sppf_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  static size_t configured = 0;
+  if (smem > configured) {
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
+    configured = h->max_smem_optin;
+  }
+  sppf_pool_kernel<<<(unsigned)(N * (C / 8)), 256, smem, (cudaStream_t)stream>>>(p);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }

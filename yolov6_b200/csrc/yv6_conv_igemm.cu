@@ -31,7 +31,10 @@
 
 namespace yv6 {
 
-constexpr int kConvThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups (TMEM acc 0 / 1)
+// warp 0 producer, warp 1 MMA, then G epilogue groups of four warps, one per TMEM accumulator:
+// G = 2 (320 threads) in general, G = 4 (576 threads) when 4 accumulators fit (BN <= 128): small-K tiles are
+// bound by the instruction latency of the epilogue, which more resident warps hide.
+constexpr int kMaxGroups = 4;
 constexpr int kMaxStages = 12;
 constexpr int kTileRows = 128;
 
@@ -39,12 +42,12 @@ struct ConvKParams {
   int32_t BW, BH, BI, rows;
   int32_t tiles_w, tiles_h, tiles_i, tiles_n, num_tiles;
   int32_t N, Ho, Wo, Cout, BN;
-  int32_t taps, kw, stride, pad, Cin;
+  int32_t taps, kw, stride, pad, pad_w, Cin;   // pad = rows (h), pad_w = columns
   int32_t cin_blocks, kb_elems, kb_bytes, ksteps;
   int32_t sbo_bytes, layout_type;
   int32_t npairs;
   int32_t stages, a_stage_bytes, b_stage_bytes;
-  int32_t tmem_cols;
+  int32_t tmem_cols, groups;
   int32_t act, y_dtype, out_planes, res_planes;
   void* y;
   int64_t y_img_stride, y_h_stride, y_w_stride, y_plane_stride;
@@ -211,7 +214,8 @@ __device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32
   }
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -224,9 +228,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint64_t* a_full = tempty + 4;            // halo mode rings
+  uint64_t* tempty = tfull + kMaxGroups;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + kMaxGroups);
+  uint64_t* a_full = tempty + kMaxGroups + 2;            // halo mode rings
   uint64_t* a_empty = a_full + kMaxAStages;
   uint64_t* b_full = a_empty + kMaxAStages;
   uint64_t* b_empty = b_full + kMaxBStages;
@@ -239,7 +243,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < G; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 128);
     }
@@ -312,7 +316,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = tap / p.kw, s = tap - r * p.kw;
-          const int cx = t.w0 * p.stride + s - p.pad;
+          const int cx = t.w0 * p.stride + s - p.pad_w;
           const int cy = t.h0 * p.stride + r - p.pad;
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -387,8 +391,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (elect_one()) umma_commit(&tfull[acc]);
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == G) { acc = 0; acc_phase ^= 1; }
       }
     } else
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -417,8 +420,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == G) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ================================ epilogue ================================
@@ -431,11 +433,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tq = row / p.BW;
     const int bh = tq % p.BH;
     const int bi = tq / p.BH;
-    uint8_t* gC = sC + group * 2 * kCBufBytes;  // this group's two staging buffers
+    constexpr int NBUF = kCBufCount / G;          // staging buffers per group (2 when G = 2, 1 when G = 4)
+    uint8_t* gC = sC + group * NBUF * kCBufBytes;
     const bool f32 = (p.y_dtype == YV6_DT_F32);
     uint32_t acc_phase = 0;
     int cbuf = 0;
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += G * gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int img = t.i0 + bi, ho = t.h0 + bh, wo = t.w0 + bw;
       const bool valid = (row < p.rows) && (img < p.N) && (ho < p.Ho) && (wo < p.Wo);
@@ -456,7 +459,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int nsub = min(p.c_chunk, p.BN - c0) >> 4;
           for (int pl = 0; pl < p.out_planes; ++pl) {
             uint8_t* buf = gC + cbuf * kCBufBytes + q * 4096;
-            if (lane == 0) tma_store_wait_read<1>();  // this warp's store from two chunks ago has read its buffer
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last read this buffer is done
             __syncwarp();
             const uint32_t base = smem_u32(buf) + lrow;
             uint32_t r[2][16];
@@ -499,19 +502,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_store_5d(&tmC, buf, t.n0 + c0, sw0, sh0, t.i0, pl);
               tma_store_commit();
             }
-            cbuf ^= 1;
+            if (++cbuf == NBUF) cbuf = 0;
           }
         }
       } else if (p.tma_store == 1) {
         // ---- block-level store: tiles whose warps do not map to boxes (e.g. 20x5): the group stages the
         //      whole 128-row chunk, synchronises on its named barrier, one thread issues the TMA store.
-        const bool issuer = (q == 2 && lane == 0);  // first thread of the group
+        const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);  // first thread of the group
         const uint32_t row_smem = (uint32_t)row * 128u, row_xor = (uint32_t)(row & 7);
         for (int c0 = 0; c0 < p.BN; c0 += p.c_chunk) {
           const int nsub = min(p.c_chunk, p.BN - c0) >> 4;
           for (int pl = 0; pl < p.out_planes; ++pl) {
             uint8_t* buf = gC + cbuf * kCBufBytes;
-            if (issuer) tma_store_wait_read<1>();
+            if (issuer) tma_store_wait_read<NBUF - 1>();
             epi_bar_sync(group);
             const uint32_t base = smem_u32(buf) + row_smem;
             uint32_t r[2][16];
@@ -556,7 +559,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_store_5d(&tmC, buf, t.n0 + c0, t.w0, t.h0, t.i0, pl);
               tma_store_commit();
             }
-            cbuf ^= 1;
+            if (++cbuf == NBUF) cbuf = 0;
           }
         }
       } else {
@@ -606,7 +609,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   YV6_REQUIRE(d->Cin > 0 && d->Cin % 16 == 0, "conv: Cin=%d must be a positive multiple of 16", d->Cin);
   YV6_REQUIRE(d->x_c_total >= d->Cin && d->x_c_total % 8 == 0, "conv: bad x_c_total=%d", d->x_c_total);
   YV6_REQUIRE(d->Cout > 0, "conv: Cout=%d", d->Cout);
-  YV6_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "conv: kernel %dx%d unsupported", d->kh, d->kw);
+  YV6_REQUIRE(d->kh >= 1 && d->kh <= 3 && d->kw >= 1 && d->kw <= 3, "conv: kernel %dx%d unsupported", d->kh, d->kw);
   YV6_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
   YV6_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "conv: nsplit must be 1 or 3");
   YV6_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0,
@@ -616,8 +619,11 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   ConvKParams& k = plan->k;
   memset(&k, 0, sizeof(k));
   k.N = d->N;
-  k.Ho = (d->H + 2 * d->pad - d->kh) / d->stride + 1;
-  k.Wo = (d->W + 2 * d->pad - d->kw) / d->stride + 1;
+  // pad_w < 0 means "same as pad" (square padding); out_h/out_w > 0 override the conv arithmetic (used by
+  // the parity sub-problems of a stride-2 dgrad, whose far-side reads rely on TMA zero fill)
+  const int pad_w = (d->pad_w == YV6_PAD_SAME) ? d->pad : d->pad_w;
+  k.Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->kh) / d->stride + 1;
+  k.Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * pad_w - d->kw) / d->stride + 1;
   YV6_REQUIRE(k.Ho > 0 && k.Wo > 0, "conv: empty output");
   k.Cout = d->Cout;
   k.Cin = d->Cin;
@@ -625,6 +631,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   k.kw = d->kw;
   k.stride = d->stride;
   k.pad = d->pad;
+  k.pad_w = pad_w;
 
   // K block = largest of 64/32/16 channels dividing Cin -> 128/64/32-byte swizzle
   k.kb_elems = (d->Cin % 64 == 0) ? 64 : (d->Cin % 32 == 0) ? 32 : 16;
@@ -695,7 +702,8 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // halo mode: 3x3 stride-1 with 64-channel K blocks and an 8x16 output tile; taken when its fixed tile
   // shape costs at most 25% more tiles than the best free-form box (it moves ~6x fewer A bytes)
   k.halo = 0;
-  if (d->kh == 3 && d->stride == 1 && d->pad == 1 && d->Cin % 64 == 0 && d->force_bw == 0 && d->force_halo >= 0) {
+  if (d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && pad_w == 1 && d->out_h == 0 && d->out_w == 0 &&
+      d->Cin % 64 == 0 && d->force_bw == 0 && d->force_halo >= 0) {
     const long generic = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
     const long halo_tiles = (long)ceil_div(k.Wo, 8) * ceil_div(k.Ho, 16) * d->N;
     if (d->force_halo > 0 || halo_tiles * 4 <= generic * 5) {
@@ -773,8 +781,9 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   }
   plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + 1024 + 1024;
 
+  k.groups = (4 * k.BN <= 512 && d->force_groups != 2) ? 4 : 2;
   int cols = 32;
-  while (cols < 2 * k.BN) cols *= 2;
+  while (cols < k.groups * k.BN) cols *= 2;
   k.tmem_cols = cols;
 
   k.act = d->act;
@@ -904,11 +913,16 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
 
   static bool configured = false;
   if (!configured) {
-    YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->max_smem_optin));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)h->max_smem_optin));
     configured = true;
   }
-  conv_igemm_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
+  if (k.groups == 4)
+    conv_igemm_kernel<4><<<plan.grid, 64 + 128 * 4, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
+  else
+    conv_igemm_kernel<2><<<plan.grid, 64 + 128 * 2, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }

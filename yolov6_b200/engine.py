@@ -54,8 +54,8 @@ class InferEngine:
             w, b = fold_op(sd, op)
             ent = {}
             if op.kind == "stem":
-                ent["w_host"] = np.ascontiguousarray(w.float().numpy().reshape(-1))      # [Cout][3][3][3]
-                ent["b_host"] = np.ascontiguousarray(b.float().numpy())
+                ent["w_dev"] = w.float().permute(1, 2, 3, 0).contiguous().to(dev)       # [3][3][3][Cout]
+                ent["b_dev"] = b.float().contiguous().to(dev)
             else:
                 ws = w if isinstance(w, list) else [w]
                 packed = []
@@ -110,8 +110,8 @@ class InferEngine:
                 d.x_dtype = DT_U8 if in_dtype == torch.uint8 else DT_F32
                 d.in_scale = 1.0 / 255.0
                 d.N, d.H, d.W = N, H, W
-                d.w = ent["w_host"].ctypes.data_as(C.POINTER(C.c_float))
-                d.bias = ent["b_host"].ctypes.data_as(C.POINTER(C.c_float))
+                d.w = ent["w_dev"].data_ptr()
+                d.bias = ent["b_dev"].data_ptr()
                 d.Cout, d.act = op.cout, ACT_CODES[op.act]
                 d.y = buf.data_ptr()
                 d.y_plane_stride = buf.stride(0) if P == 3 else 0
@@ -133,6 +133,7 @@ class InferEngine:
                     d.kh = d.kw = 1 if op.kind == "convT" else op.k
                     d.stride = 1 if op.kind == "convT" else op.s
                     d.pad = d.kh // 2
+                    d.pad_w = _lib.PAD_SAME
                     d.act = ACT_CODES[op.act]
                     d.nsplit = P
                     if op.kind == "pred":

@@ -36,7 +36,7 @@ def split3(t):
 
 def conv_fwd(x, w, bias, y, *, cin=None, x_c_offset=0, stride=1, act=None, y_c_offset=0,
              y_img_stride=None, y_h_stride=None, y_w_stride=None, y_elem_offset=0,
-             res=None, res_c_offset=0, alpha=1.0, nsplit=1, force=None, stream=None):
+             res=None, res_c_offset=0, alpha=1.0, nsplit=1, force=None, stream=None, pad=None, out_hw=None):
     """y[..., y_c_offset:+Cout] = act(conv(x[..., x_c_offset:+Cin], w) + bias) (+ alpha*res).
 
     x: [N,H,W,Ct] bf16 (nsplit=1) or [3,N,H,W,Ct] (nsplit=3); w: [Cout,kh,kw,Cin] bf16 (or [3,...]);
@@ -58,7 +58,10 @@ def conv_fwd(x, w, bias, y, *, cin=None, x_c_offset=0, stride=1, act=None, y_c_o
     d.w = w.data_ptr()
     d.w_plane_stride = w.stride(0) if planes else 0
     d.bias = bias.data_ptr() if bias is not None else 0
-    d.Cout, d.kh, d.kw, d.stride, d.pad = Cout, kh, kw, stride, kh // 2
+    d.Cout, d.kh, d.kw, d.stride, d.pad = Cout, kh, kw, stride, (kh // 2 if pad is None else pad[0])
+    d.pad_w = _lib.PAD_SAME if pad is None else pad[1]
+    if out_hw is not None:
+        d.out_h, d.out_w = out_hw
     d.act = ACT_CODES[act]
     y_planes = planes and y.dtype == torch.bfloat16
     ysh = y.shape[1:] if y_planes else y.shape
@@ -92,6 +95,7 @@ def conv_plan(x_shape, w_shape, stride=1, nsplit=1, force=None, device=0):
     d.x = d.w = d.y = 16  # plan only: non-null, aligned
     d.N, d.H, d.W, d.Cin, d.x_c_total = N, H, W, Cin, Ct
     d.Cout, d.kh, d.kw, d.stride, d.pad = Cout, kh, kw, stride, kh // 2
+    d.pad_w = _lib.PAD_SAME
     d.nsplit = nsplit
     if force:
         for k, v in force.items():
