@@ -58,9 +58,29 @@ def scaled_lists(cfg):
 # ---------------------------------------------------------------------------------------------
 # layer restatements
 # ---------------------------------------------------------------------------------------------
+_BN_TRAIN = [False]
+
+
+class train_mode:
+    """Context manager: BatchNorm uses batch statistics (nn.BatchNorm2d.train(), biased variance in the
+    normalisation) so that the train-form forward/backward of the reference can be re-stated for the
+    gradient parity tests.  Running statistics are not updated (the oracle is stateless)."""
+
+    def __enter__(self):
+        _BN_TRAIN.append(True)
+
+    def __exit__(self, *a):
+        _BN_TRAIN.pop()
+
+
 def _bn(sd, p, x):
-    """Eval-mode BatchNorm2d with running stats, eps=1e-3."""
+    """BatchNorm2d, eps=1e-3: running stats in eval mode, batch stats inside `train_mode()`."""
     w, b = sd[p + ".weight"].to(x.dtype), sd[p + ".bias"].to(x.dtype)
+    if _BN_TRAIN[-1]:
+        m = x.mean(dim=(0, 2, 3))
+        v = x.var(dim=(0, 2, 3), unbiased=False)
+        scale = w / torch.sqrt(v + BN_EPS)
+        return x * scale.view(1, -1, 1, 1) + (b - m * scale).view(1, -1, 1, 1)
     m, v = sd[p + ".running_mean"].to(x.dtype), sd[p + ".running_var"].to(x.dtype)
     scale = w / torch.sqrt(v + BN_EPS)
     return x * scale.view(1, -1, 1, 1) + (b - m * scale).view(1, -1, 1, 1)

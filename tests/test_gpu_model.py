@@ -82,7 +82,7 @@ def test_uint8_input_is_scaled_on_device():
     assert rel_err(out, ref) < 1e-4
 
 
-def test_load_state_dict_refreshes_engine_and_training_raises():
+def test_load_state_dict_refreshes_engine():
     m, sd = load("yolov6n", "bf16")
     x = fab.synthetic_images(1, 64, 64, seed=0).cuda()
     with torch.no_grad():
@@ -91,6 +91,3 @@ def test_load_state_dict_refreshes_engine_and_training_raises():
         m.load_state_dict(sd2)
         b = m(x)[0].clone()
     assert not torch.allclose(a, b)
-    m.train()
-    with pytest.raises(RuntimeError):
-        m(x)

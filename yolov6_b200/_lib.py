@@ -61,6 +61,29 @@ class LossDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    """Mirror of `yv6_wgrad_desc` (include/yv6.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("x_c_total", C.c_int32),
+        ("dy", C.c_void_p), ("Cout", C.c_int32), ("dy_c_total", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("dw", C.c_void_p), ("force_ksplit", C.c_int32),
+    ]
+
+
+class BnDesc(C.Structure):
+    """Mirror of `yv6_bn_desc` (include/yv6.h)."""
+    _fields_ = [
+        ("nb", C.c_int32), ("act", C.c_int32), ("C", C.c_int32), ("pixels", C.c_int64),
+        ("x", C.c_void_p * 3), ("x_pitch", C.c_int64 * 3),
+        ("mean", C.c_void_p * 3), ("invstd", C.c_void_p * 3), ("scale", C.c_void_p * 3), ("shift", C.c_void_p * 3),
+        ("y", C.c_void_p), ("y_pitch", C.c_int64),
+        ("dy", C.c_void_p), ("dy_pitch", C.c_int64),
+        ("s1", C.c_void_p), ("s2", C.c_void_p * 3),
+        ("dx", C.c_void_p * 3), ("dx_pitch", C.c_int64 * 3), ("accumulate", C.c_int32 * 3),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 _handles = {}
@@ -94,6 +117,18 @@ _SIGNATURES = {
                                  C.c_int32, C.c_void_p, C.c_void_p]),
     "yv6_det_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "yv6_det_loss": (C.c_int, [C.c_void_p, C.POINTER(LossDesc), C.c_void_p]),
+    "yv6_conv_wgrad": (C.c_int, [C.c_void_p, C.POINTER(WgradDesc), C.c_void_p]),
+    "yv6_bn_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yv6_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "yv6_bn_apply_fwd": (C.c_int, [C.c_void_p, C.POINTER(BnDesc), C.c_void_p]),
+    "yv6_bn_bwd": (C.c_int, [C.c_void_p, C.POINTER(BnDesc), C.c_void_p]),
+    "yv6_head_grad_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_void_p, C.c_void_p]),
+    "yv6_maxpool5_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "yv6_stem_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "yv6_nms_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "yv6_nms_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -781,7 +781,10 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   }
   plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + 1024 + 1024;
 
-  k.groups = (4 * k.BN <= 512 && d->force_groups != 2) ? 4 : 2;
+  // four groups only pay off when the tile's mainloop is shorter than its epilogue (1x1 / small-K layers)
+  const int kblocks_per_tile = k.npairs * k.taps * k.cin_blocks;
+  k.groups = (4 * k.BN <= 512 && kblocks_per_tile <= 8 && d->force_groups != 2) ? 4 : 2;
+  if (d->force_groups == 4 && 4 * k.BN <= 512) k.groups = 4;
   int cols = 32;
   while (cols < k.groups * k.BN) cols *= 2;
   k.tmem_cols = cols;

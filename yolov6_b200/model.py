@@ -115,7 +115,7 @@ class Model(nn.Module):
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        for k in ("_graph", "_engine", "_engine_key"):
+        for k in ("_graph", "_engine", "_engine_key", "_train_engine"):
             st.pop(k, None)
         st["_engine"], st["_engine_key"] = None, None
         return st
@@ -174,10 +174,24 @@ class Model(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def train_engine(self):
+        eng = self.__dict__.get("_train_engine")
+        if eng is None or eng.dev != next(self.parameters()).device:
+            from .train import TrainEngine
+            eng = TrainEngine(self)
+            self.__dict__["_train_engine"] = eng
+        return eng
+
     def forward(self, x):
         if self.training:
-            raise RuntimeError("yolov6_b200: the training forward/backward of the conv stack is not built yet "
-                               "(round 1 ships the inference path, NMS, TAL and the loss kernels); call .eval()")
+            # train form (batch-stat BatchNorm, three-branch RepVGG) through the sm_100a training engine;
+            # returns the reference's train-mode structure [(feats, cls, reg), featmaps] (yolo.py:33-41,
+            # effidehead.py:72-92); `feats` carry only the level shapes ComputeLoss needs (loss.py:63-68)
+            from .train import train_forward
+            eng = self.train_engine()
+            cls, reg = train_forward(eng, x)
+            feats = [torch.empty(x.shape[0], 1, h, w, device=x.device) for h, w in eng.sizes]
+            return [(feats, cls, reg), feats]
         export_mode = torch.onnx.is_in_onnx_export() or self.export
         eng = self.engine()
         pred = eng.forward(x)
