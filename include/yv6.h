@@ -261,11 +261,15 @@ typedef struct yv6_bn_desc {
   int64_t pixels;
   const void* x[3];  int64_t x_pitch[3];                /* branch inputs (bf16 NHWC slices)                    */
   const float* mean[3]; const float* invstd[3]; const float* scale[3]; const float* shift[3];
-  void* y; int64_t y_pitch;                             /* block output (fwd: written; bwd: relu mask)         */
+  void* y; int64_t y_pitch;                             /* block output (fwd: written; bwd: unused)            */
   /* backward only */
   const void* dy; int64_t dy_pitch;                     /* gradient w.r.t. the block output                    */
   double* s1; double* s2[3];                            /* [C] out: sum dz (= dbeta of every branch), sum dz*xhat_b (= dgamma_b) */
   void* dx[3]; int64_t dx_pitch[3]; int32_t accumulate[3];  /* gradient w.r.t. each branch input              */
+  /* optional BottleRep shortcut (common.py:600-617): y = act(z) + res_alpha * res; backward adds
+   * res_alpha * dy into dres and writes sum(dy * res) to dalpha[0] */
+  const void* res; int64_t res_pitch; float res_alpha;
+  void* dres; int64_t dres_pitch; double* dalpha;
 } yv6_bn_desc;
 int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);
 int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);

@@ -73,6 +73,30 @@ class train_mode:
         _BN_TRAIN.pop()
 
 
+_QUANT = [False]
+
+
+class bf16_storage:
+    """Context manager: emulate the storage precision of the CUDA training path -- conv weights (except
+    the fp32 stem) and every tensor the kernels write to HBM (raw conv outputs, block outputs) are rounded
+    to bf16, arithmetic stays in the tensor's dtype.  Lets the gradient parity test compare like with
+    like instead of measuring how bf16 rounding compounds through ~50 batch-normalised layers."""
+
+    def __enter__(self):
+        _QUANT.append(True)
+
+    def __exit__(self, *a):
+        _QUANT.pop()
+
+
+def _q(t):
+    return t.to(torch.bfloat16).to(t.dtype) if _QUANT[-1] else t
+
+
+def _wq(w, name=""):
+    return w if (not _QUANT[-1] or name.startswith("backbone.stem")) else w.to(torch.bfloat16).to(w.dtype)
+
+
 def _bn(sd, p, x):
     """BatchNorm2d, eps=1e-3: running stats in eval mode, batch stats inside `train_mode()`."""
     w, b = sd[p + ".weight"].to(x.dtype), sd[p + ".bias"].to(x.dtype)
@@ -97,9 +121,10 @@ def _act(x, act):
 
 def conv_module(sd, p, x, stride, act):
     """ConvModule.forward, reference yolov6/layers/common.py:26-49: conv(no bias, pad=k//2) -> BN -> act."""
-    w = sd[p + ".conv.weight"].to(x.dtype)
+    w = _wq(sd[p + ".conv.weight"].to(x.dtype), p)
     k = w.shape[-1]
-    return _act(_bn(sd, p + ".bn", F.conv2d(x, w, None, stride=stride, padding=k // 2)), act)
+    y = _act(_bn(sd, p + ".bn", _q(F.conv2d(x, w, None, stride=stride, padding=k // 2))), act)
+    return _q(y) if act is not None or not p.endswith(("rbr_dense", "rbr_1x1")) else y
 
 
 def conv_bn_act(sd, p, x, stride, act):
@@ -110,11 +135,11 @@ def conv_bn_act(sd, p, x, stride, act):
 def repvgg(sd, p, x, stride):
     """RepVGGBlock.forward in train form, common.py:245-255: relu(BN(3x3) + BN(1x1, pad 0) + BN(x))."""
     y = conv_module(sd, p + ".rbr_dense", x, stride, None)
-    w1 = sd[p + ".rbr_1x1.conv.weight"].to(x.dtype)
-    y = y + _bn(sd, p + ".rbr_1x1.bn", F.conv2d(x, w1, None, stride=stride, padding=0))
+    w1 = _wq(sd[p + ".rbr_1x1.conv.weight"].to(x.dtype), p)
+    y = y + _bn(sd, p + ".rbr_1x1.bn", _q(F.conv2d(x, w1, None, stride=stride, padding=0)))
     if p + ".rbr_identity.weight" in sd:
         y = y + _bn(sd, p + ".rbr_identity", x)
-    return torch.relu(y)
+    return _q(torch.relu(y))
 
 
 def basic_block(sd, p, x, stride, mode):
@@ -182,8 +207,8 @@ def cspsppf(sd, p, x, act):
 
 def bifusion(sd, p, xs):
     """BiFusion.forward, common.py:695-718 (always ReLU): cv3(cat(up(x0), cv1(x1), down(cv2(x2))))."""
-    x0 = F.conv_transpose2d(xs[0], sd[p + ".upsample.upsample_transpose.weight"].to(xs[0].dtype),
-                            sd[p + ".upsample.upsample_transpose.bias"].to(xs[0].dtype), stride=2)
+    x0 = _q(F.conv_transpose2d(xs[0], _wq(sd[p + ".upsample.upsample_transpose.weight"].to(xs[0].dtype)),
+                               sd[p + ".upsample.upsample_transpose.bias"].to(xs[0].dtype), stride=2))
     x1 = conv_bn_act(sd, p + ".cv1", xs[1], 1, "relu")
     x2 = conv_bn_act(sd, p + ".downsample", conv_bn_act(sd, p + ".cv2", xs[2], 1, "relu"), 2, "relu")
     return conv_bn_act(sd, p + ".cv3", torch.cat((x0, x1, x2), 1), 1, "relu")
@@ -257,8 +282,8 @@ def head_raw(sd, cfg, feats):
         x = conv_bn_act(sd, f"detect.stems.{i}", x, 1, "silu")
         cf = conv_bn_act(sd, f"detect.cls_convs.{i}", x, 1, "silu")
         rf = conv_bn_act(sd, f"detect.reg_convs.{i}", x, 1, "silu")
-        c = F.conv2d(cf, sd[f"detect.cls_preds.{i}.weight"].to(x.dtype), sd[f"detect.cls_preds.{i}.bias"].to(x.dtype))
-        r = F.conv2d(rf, sd[f"detect.reg_preds.{i}.weight"].to(x.dtype), sd[f"detect.reg_preds.{i}.bias"].to(x.dtype))
+        c = F.conv2d(cf, _wq(sd[f"detect.cls_preds.{i}.weight"].to(x.dtype)), sd[f"detect.cls_preds.{i}.bias"].to(x.dtype))
+        r = F.conv2d(rf, _wq(sd[f"detect.reg_preds.{i}.weight"].to(x.dtype)), sd[f"detect.reg_preds.{i}.bias"].to(x.dtype))
         cls_all.append(torch.sigmoid(c).flatten(2).permute(0, 2, 1))
         reg_all.append(r.flatten(2).permute(0, 2, 1))
     return torch.cat(cls_all, 1), torch.cat(reg_all, 1)

@@ -1,10 +1,10 @@
-"""GPU parity of the training engine (train-form forward + backward through conv / wgrad / BN kernels)
-against the oracle's train-mode network differentiated by torch autograd on CPU (float64).
+"""GPU parity of the training engine (train-form forward + backward through conv / wgrad / BN kernels).
 
 The kernels compute in bf16 (operands and stored activations) with fp32 accumulation, like the
-reference's own GPU training which runs convs under fp16 autocast (core/engine.py:150).  Bars, per
-parameter tensor: cosine similarity of the gradient >= 0.99 and relative L2 error <= 8e-2 against the
-float64 oracle; forward head outputs within 3e-2.  Measured values are printed."""
+reference's own GPU training which runs convs under fp16 autocast (core/engine.py:150).  The forward
+is compared with the oracle's train-mode network (bf16 storage, float64 arithmetic; head outputs
+within 5e-2); the backward is compared op by op with torch autograd in float64 (1e-2 relative L2),
+see the test's docstring for why.  Measured values are printed."""
 import numpy as np
 import pytest
 import torch
@@ -16,54 +16,194 @@ from oracle import model as om
 pytestmark = pytest.mark.gpu
 
 
-def oracle_grads(name, sd, x, wc, wr):
-    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
-    with om.train_mode():
+def oracle_forward(name, sd, x):
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    with torch.no_grad(), om.train_mode(), om.bf16_storage():   # same storage precision as the kernels (bf16 in HBM)
         cls, reg, _ = om.forward(sd64, om.CONFIGS[name], x.double(), train_outputs=True)
-    loss = (cls * wc.double()).sum() + (reg * wr.double()).sum()
-    loss.backward()
-    return cls.detach(), reg.detach(), {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.grad is not None}
+    return cls, reg
 
 
-@pytest.mark.parametrize("name,size,batch", [("yolov6n", 128, 4), ("yolov6s", 96, 2)])
-def test_train_step_gradients_match_oracle(name, size, batch):
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).double()
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _bn_train(t, gamma, beta):
+    mu, var = t.mean(dim=(0, 2, 3)), t.var(dim=(0, 2, 3), unbiased=False)
+    sc = gamma / torch.sqrt(var + 1e-3)
+    return t * sc.view(1, -1, 1, 1) + (beta - mu * sc).view(1, -1, 1, 1)
+
+
+def _q(t):
+    """bf16 storage of an intermediate with a straight-through gradient (what the kernels write to HBM)."""
+    return t + (t.to(torch.bfloat16).double() - t).detach()
+
+
+@pytest.mark.parametrize("name,size,batch", [("yolov6n", 128, 4), ("yolov6s", 96, 2), ("yolov6m", 96, 2), ("yolov6l6", 128, 2)])
+def test_train_step_matches_reference_op_by_op(name, size, batch):
+    """Forward against the oracle's train-mode network; backward op by op.
+
+    Train-mode BatchNorm over randomly initialised weights is chaotic: the float64 oracle and the same oracle
+    with bf16 storage already disagree on parameter gradients with cosine ~0.3 (measured), so an
+    end-to-end gradient comparison measures rounding noise, not the kernels.  Instead every op of the
+    engine's backward pass is checked against torch autograd (float64, on the engine's own forward
+    tensors and incoming gradient): parameter gradients, the forward value, and -- summed over all
+    consumers of a tensor -- the input gradients.  Bars: 1e-2 relative L2 (bf16 gradient storage), 3e-2 for
+    the per-channel BatchNorm sums."""
+    import torch.nn.functional as F
     from yolov6_b200.model import build_model
     dev = torch.device("cuda:0")
     sd = fab.fabricate_state_dict(golden_keys(name), seed=0)
+    for k in sd:      # batch-stat BN makes the features unit-variance; keep the head logits O(1)
+        if (".cls_preds." in k or ".reg_preds." in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+        if k.endswith(".alpha"):
+            sd[k] = sd[k] * 0.75
     m = build_model(name, 80, dev)
     m.load_state_dict(sd)
     m.train()
+    eng = m.train_engine()
+    eng.debug = True
     x = fab.synthetic_images(batch, size, size, seed=11)
-    (feats, cls, reg), _ = m(x.to(dev))
+    xd = x.to(dev)
+    (feats, cls, reg), _ = m(xd)
     g = torch.Generator().manual_seed(5)
-    wc, wr = torch.randn(cls.shape, generator=g), torch.randn(reg.shape, generator=g)
-    loss = (cls * wc.to(dev)).sum() + (reg * wr.to(dev)).sum()
-    loss.backward()
-    ocls, oreg, ograds = oracle_grads(name, sd, x, wc, wr)
-    e_cls = float((cls.detach().cpu().double() - ocls).abs().max())
-    e_reg = float((reg.detach().cpu().double() - oreg).abs().max() / (1 + oreg.abs().max()))
-    print(f"{name}: forward |dcls| {e_cls:.2e}  rel |dreg| {e_reg:.2e}")
-    assert e_cls < 3e-2 and e_reg < 3e-2
+    wc, wr = torch.randn(cls.shape, generator=g).to(dev), torch.randn(reg.shape, generator=g).to(dev)
+    ((cls * wc).sum() + (reg * wr).sum()).backward()
+    torch.cuda.synchronize()
     assert [tuple(f.shape[2:]) for f in feats] == [(size // s, size // s) for s in om.CONFIGS[name]["strides"]]
-    worst_cos, worst_rel, nchecked = 1.0, 0.0, 0
-    for k, p in m.named_parameters():
-        if k not in ograds:
+
+    # ---- forward vs the oracle (bf16-storage train-mode network, float64 arithmetic)
+    ocls, oreg = oracle_forward(name, sd, x)
+    # (rounding differences between fp32 and float64 accumulation are amplified layer by layer by the
+    # batch-statistics BatchNorm, so this end-to-end bar is an RMS one; each op is checked tightly below)
+    e_cls = float((cls.detach().cpu().double() - ocls).pow(2).mean().sqrt())
+    e_reg = _rel(reg.detach().cpu(), oreg)
+    m_cls = float((cls.detach().cpu().double() - ocls).abs().max())
+    print(f"{name}: forward vs oracle: cls rms {e_cls:.2e} (max {m_cls:.2e}), reg rel L2 {e_reg:.2e}")
+    assert e_cls < 2e-2 and e_reg < 5e-2
+
+    # ---- backward, op by op
+    P = dict(m.named_parameters())
+    gr = m.graph
+    ref_g = [torch.zeros(t.shape, dtype=torch.float64, device=dev) for t in eng.bufs]
+    worst = dict(fwd=0.0, dparam=0.0)
+    nparam = 0
+
+    def check_param(pname, ref, tol=1e-2):
+        nonlocal nparam
+        got = P[pname].grad
+        assert got is not None, f"no gradient for {pname}"
+        if float(ref.norm()) < 1e-9:
+            return
+        e = _rel(got.reshape(ref.shape), ref)
+        worst["dparam"] = max(worst["dparam"], e)
+        nparam += 1
+        assert e < tol, f"{pname}: gradient rel err {e:.3e}"
+
+    def sl(bufs, t, c=None):
+        return bufs[t.buf][..., t.c_off:t.c_off + (c if c is not None else t.c)]
+
+    for i, op in enumerate(gr.ops):
+        ctx, dbg = eng.ctx[i], eng.dbg.get(i)
+        if op.kind == "pool":                                   # SPPF / SimSPPF max-pool chain (common.py:104-112)
+            c = op.cin
+            buf = eng.bufs[op.dst.buf]
+            y0 = _nchw(buf[..., :c]).requires_grad_(True)
+            ys = [y0]
+            for _ in range(3):
+                ys.append(F.max_pool2d(ys[-1], 5, 1, 2))
+                ys[-1].retain_grad()
+            gd = _nchw(dbg["gdst"])
+            for j in range(1, 4):
+                assert torch.equal(_nchw(buf[..., j * c:(j + 1) * c]), ys[j].detach()), f"{op.name}: pool {j}"
+            (torch.cat(ys, 1) * gd).sum().backward()
+            for j in range(3):                                   # chain contribution = total - what the consumers sent
+                ref_g[op.dst.buf][..., j * c:(j + 1) * c] += (ys[j].grad - gd[:, j * c:(j + 1) * c]).permute(0, 2, 3, 1)
             continue
-        assert p.grad is not None, f"no gradient for {k}"
-        a, b = p.grad.detach().cpu().double().flatten(), ograds[k].flatten()
-        if b.norm() < 1e-12:
+        src = None
+        if op.kind != "stem":
+            src = _nchw(sl(eng.bufs, op.src, op.cin)).requires_grad_(True)
+        if op.kind == "pred":                                   # effidehead.py:79-92 (train branch)
+            which, lvl = op.head
+            w = _nchw(ctx["w"]).requires_grad_(True)
+            b = P[op.name + ".bias"].detach().double().requires_grad_(True)
+            y = F.conv2d(src, w, b)
+            y = torch.sigmoid(y) if which == "cls" else y
+            out, wt = (eng.cls, wc) if which == "cls" else (eng.reg, wr)
+            lo, hi = eng.offs[lvl], eng.offs[lvl + 1]
+            yf = y.flatten(2).permute(0, 2, 1)
+            worst["fwd"] = max(worst["fwd"], _rel(out[:, lo:hi], yf.detach()))
+            assert _rel(out[:, lo:hi], yf.detach()) < 1e-3, op.name
+            (yf * wt[:, lo:hi].double()).sum().backward()
+            check_param(op.name + ".weight", w.grad)
+            check_param(op.name + ".bias", b.grad)
+        elif op.kind == "convT":                                # Transpose, common.py:149-163
+            w = P[op.name + ".upsample_transpose.weight"].detach().to(torch.bfloat16).double().requires_grad_(True)
+            b = P[op.name + ".upsample_transpose.bias"].detach().double().requires_grad_(True)
+            y = F.conv_transpose2d(src, w, b, stride=2)
+            e = _rel(_nchw(sl(eng.bufs, op.dst, op.cout)), y.detach())
+            worst["fwd"] = max(worst["fwd"], e)
+            assert e < 1e-2, op.name
+            (y * _nchw(dbg["gdst"])).sum().backward()
+            check_param(op.name + ".upsample_transpose.weight", w.grad)
+            check_param(op.name + ".upsample_transpose.bias", b.grad)
+        else:                                                   # ConvModule / RepVGGBlock, common.py:46-49,245-255
+            z, leaves = 0, []
+            for br in ctx["branches"]:
+                if br["k"] == 0:
+                    t, pfx = src, br["prefix"]
+                else:
+                    pfx = br["prefix"] + ".bn"
+                    if op.kind == "stem":                       # fp32 weights, fp32 image
+                        w = P[br["prefix"] + ".conv.weight"].detach().double().requires_grad_(True)
+                        t = F.conv2d(xd.double(), w, stride=2, padding=br["k"] // 2)
+                    else:
+                        w = _nchw(br["w"]).requires_grad_(True)  # the engine's bf16 KRSC weights
+                        t = F.conv2d(src, w, stride=op.s, padding=br["k"] // 2)
+                    t = _q(t)
+                    assert _rel(_nchw(br["x"]), t.detach()) < 2e-3, f"{br['prefix']}: raw conv"
+                    leaves.append((br["prefix"] + ".conv.weight", w))
+                gam = P[pfx + ".weight"].detach().double().requires_grad_(True)
+                bet = P[pfx + ".bias"].detach().double().requires_grad_(True)
+                leaves += [(pfx + ".weight", gam), (pfx + ".bias", bet)]
+                z = z + _bn_train(t, gam, bet)
+            y = torch.relu(z) if op.act == "relu" else (z * torch.sigmoid(z) if op.act == "silu" else z)
+            if op.res is not None:                              # BottleRep shortcut, common.py:600-617
+                res = _nchw(sl(eng.bufs, op.res, op.cout)).requires_grad_(True)
+                al = P[op.alpha].detach().double().requires_grad_(True)
+                y = y + al * res
+                leaves.append((op.alpha, al))
+            e = _rel(_nchw(sl(eng.bufs, op.dst, op.cout)), y.detach())
+            worst["fwd"] = max(worst["fwd"], e)
+            assert e < 1e-2, f"{op.name}: forward rel err {e:.3e}"
+            (y * _nchw(dbg["gdst"])).sum().backward()
+            for pname, leaf in leaves:   # per-channel BN sums over few pixels feel single relu-mask flips (z ~ 0 in fp32 vs float64)
+                check_param(pname, leaf.grad, 1e-2 if leaf.dim() == 4 else 3e-2)
+            if op.res is not None:
+                sl(ref_g, op.res, op.cout).add_(res.grad.permute(0, 2, 3, 1))
+        if src is not None:
+            sl(ref_g, op.src, op.cin).add_(src.grad.permute(0, 2, 3, 1))
+    # input gradients: every tensor's gradient is the sum over its consumers
+    worst_g = 0.0
+    for bi, (got, ref) in enumerate(zip(eng.gbufs, ref_g)):
+        if float(ref.norm()) == 0:
             continue
-        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300))
-        rel = float((a - b).norm() / b.norm())
-        if cos < worst_cos or rel > worst_rel:
-            print(f"  {k}: cos {cos:.4f} rel {rel:.3e}")
-        worst_cos, worst_rel, nchecked = min(worst_cos, cos), max(worst_rel, rel), nchecked + 1
-        assert cos >= 0.99 and rel <= 8e-2, f"{k}: cos {cos:.4f} rel {rel:.3e}"
-    print(f"{name}: {nchecked} parameter gradients checked, worst cos {worst_cos:.4f}, worst rel {worst_rel:.3e}")
-    assert nchecked > 300
-    # running statistics follow nn.BatchNorm2d (momentum 0.03, unbiased variance)
-    rm = dict(m.named_buffers())["backbone.ERBlock_2.0.rbr_dense.bn.running_mean"].cpu()
-    assert not torch.allclose(rm, sd["backbone.ERBlock_2.0.rbr_dense.bn.running_mean"])
+        e = _rel(got.float(), ref)
+        worst_g = max(worst_g, e)
+        assert e < 1e-2, f"buffer {bi} ({gr.bufs[bi].name}): input-gradient rel err {e:.3e}"
+    print(f"{name}: {len(gr.ops)} ops, {nparam} parameter gradients; worst rel err: forward {worst['fwd']:.2e}, "
+          f"d(param) {worst['dparam']:.2e}, d(input) {worst_g:.2e}")
+    assert nparam > 300
+    # every trainable parameter received a gradient; running statistics follow nn.BatchNorm2d (momentum 0.03)
+    missing = [k for k, p in P.items() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:5]
+    rm = dict(m.named_buffers())["backbone.ERBlock_2.0.rbr_dense.bn.running_mean"].cpu() if name != "yolov6m" and name != "yolov6l6" else None
+    if rm is not None:
+        assert not torch.allclose(rm, sd["backbone.ERBlock_2.0.rbr_dense.bn.running_mean"])
 
 
 def test_wgrad_kernel_matches_torch():
@@ -91,3 +231,61 @@ def test_wgrad_kernel_matches_torch():
         _lib.check(_lib.lib().yv6_conv_wgrad(_lib.handle(0), C.byref(d), _lib.stream_ptr()))
         err = float((dw.cpu().double() - ref).abs().max() / (ref.abs().max() + 1e-9))
         assert err < 1e-4, f"wgrad {(N, H, W, Cin, Cout, k, s)}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("nb,act", [(1, "silu"), (1, "relu"), (3, "relu"), (2, "relu")])
+def test_bn_forward_backward_kernels_match_torch(nb, act):
+    """yv6_bn_stats/finalize/apply_fwd and yv6_bn_bwd against torch autograd on the same bf16 inputs."""
+    import ctypes as C
+    from yolov6_b200 import _lib
+    dev = torch.device("cuda:0")
+    lib, h, sp = _lib.lib(), _lib.handle(0), _lib.stream_ptr()
+    g = torch.Generator().manual_seed(nb)
+    N, H, W, Cc = 3, 10, 12, 32
+    xs = [(torch.randn(N, H, W, Cc, generator=g) * (1 + b) + 0.3 * b).to(torch.bfloat16) for b in range(nb)]
+    gam = [torch.rand(Cc, generator=g) + 0.5 for _ in range(nb)]
+    bet = [torch.randn(Cc, generator=g) * 0.1 for _ in range(nb)]
+    dy = torch.randn(N, H, W, Cc, generator=g).to(torch.bfloat16)
+    # torch reference (float64)
+    xr = [x.double().requires_grad_(True) for x in xs]
+    gr = [t.double().requires_grad_(True) for t in gam]
+    br = [t.double().requires_grad_(True) for t in bet]
+    z = 0
+    for b in range(nb):
+        mu, var = xr[b].mean(dim=(0, 1, 2)), xr[b].var(dim=(0, 1, 2), unbiased=False)
+        z = z + (xr[b] - mu) / torch.sqrt(var + 1e-3) * gr[b] + br[b]
+    y = torch.relu(z) if act == "relu" else z * torch.sigmoid(z)
+    (y * dy.double()).sum().backward()
+    # kernels
+    xd = [x.to(dev) for x in xs]
+    gd_, bd_ = [t.to(dev) for t in gam], [t.to(dev) for t in bet]      # keep alive: raw pointers go to the kernels
+    sts = []
+    for b in range(nb):
+        s = torch.empty(2, Cc, dtype=torch.float64, device=dev)
+        _lib.check(lib.yv6_bn_stats(h, xd[b].data_ptr(), N * H * W, Cc, Cc, s[0].data_ptr(), s[1].data_ptr(), sp))
+        out = torch.empty(4, Cc, dtype=torch.float32, device=dev)
+        _lib.check(lib.yv6_bn_finalize(h, s[0].data_ptr(), s[1].data_ptr(), float(N * H * W), gd_[b].data_ptr(),
+                                       bd_[b].data_ptr(), 1e-3, 0.03, 0, 0, out[0].data_ptr(), out[1].data_ptr(),
+                                       out[2].data_ptr(), out[3].data_ptr(), Cc, sp))
+        sts.append((out, s))
+    yk = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device=dev)
+    d = _lib.BnDesc()
+    d.nb, d.act, d.C, d.pixels = nb, _lib.ACT_CODES[act], Cc, N * H * W
+    dxs = [torch.zeros(N, H, W, Cc, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+    sums = torch.empty(4, Cc, dtype=torch.float64, device=dev)
+    dyd = dy.to(dev)
+    for b in range(nb):
+        d.x[b], d.x_pitch[b] = xd[b].data_ptr(), Cc
+        d.mean[b], d.invstd[b], d.scale[b], d.shift[b] = (sts[b][0][i].data_ptr() for i in range(4))
+        d.s2[b] = sums[1 + b].data_ptr()
+        d.dx[b], d.dx_pitch[b], d.accumulate[b] = dxs[b].data_ptr(), Cc, 0
+    d.y, d.y_pitch, d.dy, d.dy_pitch, d.s1 = yk.data_ptr(), Cc, dyd.data_ptr(), Cc, sums[0].data_ptr()
+    _lib.check(lib.yv6_bn_apply_fwd(h, C.byref(d), sp))
+    _lib.check(lib.yv6_bn_bwd(h, C.byref(d), sp))
+    assert float((yk.float().cpu().double() - y.detach()).abs().max() / (1 + y.detach().abs().max())) < 1e-2
+    for b in range(nb):
+        ref = xr[b].grad
+        got = dxs[b].float().cpu().double()
+        assert float((got - ref).norm() / ref.norm()) < 1e-2, f"dx[{b}]"
+        assert float((sums[1 + b].cpu() - gr[b].grad).norm() / gr[b].grad.norm()) < 1e-2, f"dgamma[{b}]"
+        assert float((sums[0].cpu() - br[b].grad).norm() / br[b].grad.norm()) < 1e-2, f"dbeta[{b}]"

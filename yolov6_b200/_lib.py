@@ -81,6 +81,8 @@ class BnDesc(C.Structure):
         ("dy", C.c_void_p), ("dy_pitch", C.c_int64),
         ("s1", C.c_void_p), ("s2", C.c_void_p * 3),
         ("dx", C.c_void_p * 3), ("dx_pitch", C.c_int64 * 3), ("accumulate", C.c_int32 * 3),
+        ("res", C.c_void_p), ("res_pitch", C.c_int64), ("res_alpha", C.c_float),
+        ("dres", C.c_void_p), ("dres_pitch", C.c_int64), ("dalpha", C.c_void_p),
     ]
 
 

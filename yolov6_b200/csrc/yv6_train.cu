@@ -99,6 +99,8 @@ struct ApplyParams {
   int64_t pixels;
   __nv_bfloat16* y;
   int64_t y_pitch;
+  View res;                  // optional shortcut: y = act(z) + alpha * res (BottleRep, common.py:600-617)
+  float alpha;
 };
 __device__ __forceinline__ float act_fwd(float z, int act) {
   if (act == YV6_ACT_RELU) return fmaxf(z, 0.f);
@@ -126,6 +128,12 @@ __global__ void __launch_bounds__(kTrThreads) bn_apply_fwd_kernel(const ApplyPar
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = act_fwd(z[j], p.act);
+    if (p.res.p != nullptr) {
+      float r[8];
+      ld8(p.res.p + px * p.res.pitch + cg * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] += p.alpha * r[j];
+    }
     st8(p.y + px * p.y_pitch + cg * 8, z);
   }
 }
@@ -138,7 +146,11 @@ struct BwdParams {
   const float* scale[3];     // gamma * invstd
   const float* shift[3];
   View dy;                   // gradient w.r.t. the block output
-  View y;                    // block output (relu mask); unused for silu / none
+  View res;                  // optional shortcut input (y = act(z) + alpha * res)
+  float alpha;
+  __nv_bfloat16* dres;       // g(res) += alpha * dy
+  int64_t dres_pitch;
+  double* dalpha;            // += sum dy * res
   int nb, act, C;
   int64_t pixels;
   double* s1;                // [C]      sum dz            (shared by the branches)
@@ -152,12 +164,7 @@ struct BwdParams {
 
 __device__ __forceinline__ void bwd_dz(const BwdParams& p, int64_t px, int cg, float (&dz)[8]) {
   ld8(p.dy.p + px * p.dy.pitch + cg * 8, dz);
-  if (p.act == YV6_ACT_RELU) {
-    float yv[8];
-    ld8(p.y.p + px * p.y.pitch + cg * 8, yv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dz[j] = (yv[j] > 0.f) ? dz[j] : 0.f;
-  } else if (p.act == YV6_ACT_SILU) {
+  if (p.act != YV6_ACT_NONE) {   // the pre-activation is recomputed from the branch inputs (same fp32 arithmetic as the forward)
     float z[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = 0.f;
@@ -167,10 +174,15 @@ __device__ __forceinline__ void bwd_dz(const BwdParams& p, int64_t px, int cg, f
 #pragma unroll
       for (int j = 0; j < 8; ++j) z[j] += v[j] * p.scale[b][cg * 8 + j] + p.shift[b][cg * 8 + j];
     }
+    if (p.act == YV6_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sg = 1.f / (1.f + __expf(-z[j]));
-      dz[j] *= sg * (1.f + z[j] * (1.f - sg));
+      for (int j = 0; j < 8; ++j) dz[j] = (z[j] > 0.f) ? dz[j] : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sg = 1.f / (1.f + __expf(-z[j]));
+        dz[j] *= sg * (1.f + z[j] * (1.f - sg));
+      }
     }
   }
 }
@@ -180,10 +192,18 @@ __global__ void __launch_bounds__(kTrThreads) bn_bwd_reduce_kernel(const BwdPara
   const int cg = threadIdx.x % cgs;
   const int prow = threadIdx.x / cgs, prows = blockDim.x / cgs;
   float a1[8], a2[3][8];
+  float da = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[0][j] = a2[1][j] = a2[2][j] = 0.f; }
   for (int64_t px = (int64_t)blockIdx.x * prows + prow; px < p.pixels; px += (int64_t)gridDim.x * prows) {
     float dz[8];
+    if (p.dalpha != nullptr) {
+      float g[8], r[8];
+      ld8(p.dy.p + px * p.dy.pitch + cg * 8, g);
+      ld8(p.res.p + px * p.res.pitch + cg * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) da += g[j] * r[j];
+    }
     bwd_dz(p, px, cg, dz);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a1[j] += dz[j];
@@ -199,6 +219,11 @@ __global__ void __launch_bounds__(kTrThreads) bn_bwd_reduce_kernel(const BwdPara
     atomicAdd(&p.s1[cg * 8 + j], (double)a1[j]);
     for (int b = 0; b < p.nb; ++b) atomicAdd(&p.s2[b][cg * 8 + j], (double)a2[b][j]);
   }
+  if (p.dalpha != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(p.dalpha, (double)da);
+  }
 }
 
 __global__ void __launch_bounds__(kTrThreads) bn_bwd_apply_kernel(const BwdParams p) {
@@ -208,6 +233,15 @@ __global__ void __launch_bounds__(kTrThreads) bn_bwd_apply_kernel(const BwdParam
     const int cg = (int)(i % cgs);
     const int64_t px = i / cgs;
     float dz[8];
+    if (p.dres != nullptr) {
+      float g[8], old[8];
+      ld8(p.dy.p + px * p.dy.pitch + cg * 8, g);
+      __nv_bfloat16* dst = p.dres + px * p.dres_pitch + cg * 8;
+      ld8(dst, old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) old[j] += p.alpha * g[j];
+      st8(dst, old);
+    }
     bwd_dz(p, px, cg, dz);
     for (int b = 0; b < p.nb; ++b) {
       float v[8], o[8];
@@ -366,6 +400,8 @@ extern "C" int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* strea
   }
   p.nb = d->nb; p.act = d->act; p.C = d->C; p.pixels = d->pixels;
   p.y = reinterpret_cast<__nv_bfloat16*>(d->y); p.y_pitch = d->y_pitch;
+  p.res = View{reinterpret_cast<const __nv_bfloat16*>(d->res), d->res_pitch};
+  p.alpha = d->res_alpha;
   bn_apply_fwd_kernel<<<grid_for(d->pixels * (d->C / 8), kTrThreads, h->num_sms), kTrThreads, 0, (cudaStream_t)stream>>>(p);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
@@ -382,13 +418,19 @@ extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
     p.dx[b] = reinterpret_cast<__nv_bfloat16*>(d->dx[b]); p.dx_pitch[b] = d->dx_pitch[b]; p.accumulate[b] = d->accumulate[b];
   }
   p.dy = View{reinterpret_cast<const __nv_bfloat16*>(d->dy), d->dy_pitch};
-  p.y = View{reinterpret_cast<const __nv_bfloat16*>(d->y), d->y_pitch};
+  p.res = View{reinterpret_cast<const __nv_bfloat16*>(d->res), d->res_pitch};
+  p.alpha = d->res_alpha;
+  p.dres = d->res ? reinterpret_cast<__nv_bfloat16*>(d->dres) : nullptr;
+  p.dres_pitch = d->dres_pitch;
+  p.dalpha = d->res ? d->dalpha : nullptr;
+  YV6_REQUIRE(!d->res || (d->dres && d->dalpha), "bn_bwd: shortcut without dres / dalpha");
   p.nb = d->nb; p.act = d->act; p.C = d->C; p.pixels = d->pixels;
   p.s1 = d->s1;
   p.inv_count = 1.0 / (double)d->pixels;
   cudaStream_t s = (cudaStream_t)stream;
   YV6_CHECK_CUDA(cudaMemsetAsync(d->s1, 0, sizeof(double) * d->C, s));
   for (int b = 0; b < d->nb; ++b) YV6_CHECK_CUDA(cudaMemsetAsync(d->s2[b], 0, sizeof(double) * d->C, s));
+  if (p.dalpha) YV6_CHECK_CUDA(cudaMemsetAsync(p.dalpha, 0, sizeof(double), s));
   const int cgs = d->C / 8;
   const int rows = std::max(1, kTrThreads / cgs);
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((d->pixels + rows - 1) / rows, (int64_t)h->num_sms * 8));

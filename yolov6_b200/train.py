@@ -17,8 +17,8 @@ engine (arch.py):
 
 Parameters stay fp32 `nn.Parameter`s of the Model (master weights); every step they are cast to bf16
 KRSC for the kernels, and gradients are written to `.grad` in the reference's tensor layouts so that the
-reference's optimizer / EMA / DDP all-reduce apply unchanged.  BottleRep shortcuts (M / L6) are not
-wired for training yet (raises).
+reference's optimizer / EMA / DDP all-reduce apply unchanged.  BottleRep shortcuts (M / L6,
+common.py:600-617) ride in the BN apply / backward kernels (y = act(z) + alpha * x).
 """
 import ctypes as C
 
@@ -41,14 +41,13 @@ class TrainEngine:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("yolov6_b200 training runs on sm_100a CUDA kernels only (no CPU fallback)")
-        for op in self.g.ops:
-            if op.res is not None:
-                raise NotImplementedError("training of BottleRep shortcuts (YOLOv6-M/L6) is not wired yet")
         self.lib = _lib.lib()
         self.h = _lib.handle(self.dev.index or 0)
         self.params = dict(model.named_parameters())
         self.buffers_ = dict(model.named_buffers())
         self._shape = None
+        self.debug = False      # tests: snapshot the incoming gradient of every op into self.dbg[op index]
+        self.dbg = {}
 
     # ------------------------------------------------------------------ helpers
     def _conv(self, x, x_off, cin, w, y, y_off, cout, k, stride, *, pad=None, out_hw=None, bias=None, act=None,
@@ -219,8 +218,13 @@ class TrainEngine:
                 d.x_pitch[b] = br["x"].shape[3]
                 d.scale[b], d.shift[b] = br["st"][2].data_ptr(), br["st"][3].data_ptr()
             d.y, d.y_pitch = dst.data_ptr() + op.dst.c_off * 2, dst.shape[3]
+            alpha = 1.0
+            if op.res is not None:
+                rbuf, _ = self._view(op.res)
+                alpha = float(P[op.alpha].detach()) if op.alpha in P else 1.0
+                d.res, d.res_pitch, d.res_alpha = rbuf.data_ptr() + op.res.c_off * 2, rbuf.shape[3], alpha
             _lib.check(self.lib.yv6_bn_apply_fwd(self.h, C.byref(d), _lib.stream_ptr()))
-            self.ctx.append(dict(branches=branches, count=count))
+            self.ctx.append(dict(branches=branches, count=count, alpha=alpha))
         return self.cls, self.reg
 
     # ------------------------------------------------------------------ backward
@@ -265,6 +269,8 @@ class TrainEngine:
                 buf, gbuf = self._view(op.dst)
                 n, h, w, ct = buf.shape
                 c = op.cin
+                if self.debug:
+                    self.dbg[i] = dict(gdst=gbuf[..., :4 * c].clone())
                 scratch = torch.empty(n, h, w, c, dtype=torch.float32, device=dev)
                 for j in (3, 2, 1):   # y_j = pool(y_{j-1}); slice j of the concat
                     _lib.check(self.lib.yv6_maxpool5_bwd(self.h, buf.data_ptr() + (j - 1) * c * 2, ct, gbuf.data_ptr() + j * c * 2, ct,
@@ -293,6 +299,8 @@ class TrainEngine:
                 src, gsrc = self._view(op.src)
                 _, gdst = self._view(op.dst)
                 gd = gdst[..., op.dst.c_off:op.dst.c_off + op.cout]
+                if self.debug:
+                    self.dbg[i] = dict(gdst=gd.clone())
                 dwt = torch.zeros(op.cin, op.cout, 2, 2, dtype=torch.float32, device=dev)
                 db = torch.zeros(op.cout, dtype=torch.float64, device=dev)
                 for q in range(4):
@@ -330,7 +338,16 @@ class TrainEngine:
                     dcs.append(dc)
             d.y, d.y_pitch = dst.data_ptr() + op.dst.c_off * 2, dct
             d.dy, d.dy_pitch = gdst.data_ptr() + op.dst.c_off * 2, dct
+            if op.res is not None:
+                rbuf, grbuf = self._view(op.res)
+                dalpha = torch.empty(1, dtype=torch.float64, device=dev)
+                d.res, d.res_pitch, d.res_alpha = rbuf.data_ptr() + op.res.c_off * 2, rbuf.shape[3], ctx["alpha"]
+                d.dres, d.dres_pitch, d.dalpha = grbuf.data_ptr() + op.res.c_off * 2, grbuf.shape[3], dalpha.data_ptr()
             _lib.check(self.lib.yv6_bn_bwd(self.h, C.byref(d), _lib.stream_ptr()))
+            if op.res is not None and op.alpha in P and P[op.alpha].requires_grad:
+                self._add_grad(op.alpha, dalpha)
+            if self.debug:
+                self.dbg[i] = dict(gdst=gdst[..., op.dst.c_off:op.dst.c_off + op.cout].clone(), dcs=dcs)
             for b, br in enumerate(brs):
                 bnp = br["prefix"] + (".bn" if br["k"] else "")
                 self._add_grad(bnp + ".weight", sums[1 + b])        # dgamma = sum dz * xhat
