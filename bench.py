@@ -70,6 +70,48 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_cores():
+    """Host threads this process can really use: CPU affinity, capped by the cgroup CPU quota (a container
+    that sees 128 logical CPUs but is throttled to a few would otherwise be timed oversubscribed)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:                                                            # cgroup v1
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = int(f.read())
+            if quota > 0:
+                n = max(1, min(n, quota // period))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
+def pick_threads(step_one_image):
+    """The thread count (<= host_cores()) at which the CPU path runs fastest on a 1-image probe -- the CPU arm
+    gets its best configuration, not an oversubscribed one."""
+    best, best_t = None, float("inf")
+    cores = host_cores()
+    for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        torch.set_num_threads(n)
+        step_one_image()
+        t0 = time.perf_counter()
+        step_one_image()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_step(sd, cfg, images, nms_kw):
     """The reference path restated on CPU (oracle): eval forward + NMS on `images` (NCHW fp32)."""
     from oracle import model as om
@@ -87,12 +129,13 @@ def run_reference(args):
         return
     from oracle import fabricate as fab
     from oracle import model as om
-    sd = fab.fabricate_state_dict(load_keys(args.model), seed=0)
+    from yolov6_b200.model import build_model          # only as the container of the seeded synthetic checkpoint
+    from yolov6_b200.synth import randomize_            # (same weights as the GPU arm); nothing of it is timed
+    sd = {k: v.detach() for k, v in randomize_(build_model(args.model, 80, torch.device("cpu")), seed=0).state_dict().items()}
     cfg = om.CONFIGS[args.model]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sample = args.ref_batch
     x = fab.synthetic_images(sample, args.size, args.size, seed=0)
+    cores = pick_threads(lambda: cpu_reference_step(sd, cfg, x[:1], NMS_KW))
     for _ in range(args.warmup_ref):
         cpu_reference_step(sd, cfg, x, NMS_KW)
     t0 = time.perf_counter()
@@ -200,8 +243,8 @@ def main():
         sampler = ClockSampler(local_rank)
         sampler.start()
         ms_dev = timed(step_device, args.steps, max(args.warmup, 3))
-        sampler.stop_flag = True
         ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+        sampler.stop_flag = True                # sampled across both timed regions
         # roofline of the dominant kernel (conv_igemm): CUDA events around every conv launch of 5 steps
         conv_ms, conv_flop, n_conv = eng.profile_convs(dev_f32[0], steps=5)
     sampler.join(timeout=2)
@@ -221,7 +264,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-equivalent)", "data": "synthetic",
         "config": {"workload": f"{args.model} {S}x{S} bs{B}/GPU inference: forward + decode + batched NMS",
-                   "nms": NMS_KW, "weights": "seeded random (oracle/fabricate.py)", "parallelism": f"dp{world} image-sharded, no collective",
+                   "nms": NMS_KW, "weights": "seeded random (yolov6_b200/synth.py)", "parallelism": f"dp{world} image-sharded, no collective",
                    "l2": "inputs (157 MB fp32 per batch, two alternating buffers) exceed the 126 MB L2",
                    "launch": "one CUDA graph per batch (DetectPipeline)" if use_graph else "eager ctypes launches"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
@@ -237,10 +280,8 @@ def main():
     if not args.no_cpu_baseline:
         from oracle import model as om        # CPU-baseline leg: the checker, timed on the host cores
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
         xs = torch.rand(args.ref_batch, 3, S, S, generator=torch.Generator().manual_seed(0))
-        cpu_reference_step(sd, om.CONFIGS[args.model], xs[:1], NMS_KW)
+        cores = pick_threads(lambda: cpu_reference_step(sd, om.CONFIGS[args.model], xs[:1], NMS_KW))
         t0 = time.perf_counter()
         for _ in range(args.steps_ref):
             cpu_reference_step(sd, om.CONFIGS[args.model], xs, NMS_KW)
