@@ -95,6 +95,7 @@ typedef struct yv6_conv_desc {
    * out_h / out_w > 0 override the output size (far-side reads are zero filled). */
   int32_t pad_w, out_h, out_w;
   int32_t force_groups;     /* epilogue warp groups: 0 auto (4 when BN <= 128, else 2), 2 = force two */
+  void* trace;              /* debug: device uint64[16] receiving clock64 stamps of CTA 0's phases, or NULL */
 } yv6_conv_desc;
 
 int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);

@@ -146,6 +146,8 @@ BENCH_SHAPES = {
     "s2_64_128@80": (160, 160, 64, 128, 3, 2), "s2_128_256@40": (80, 80, 128, 256, 3, 2),
     "s2_256_512@20": (40, 40, 256, 512, 3, 2), "1x1_512_256@20": (20, 20, 512, 256, 1, 1),
     "1x1_384_128@40": (40, 40, 384, 128, 1, 1), "1x1_128_128@80": (80, 80, 128, 128, 1, 1),
+    "1x1_256_256@20": (20, 20, 256, 256, 1, 1), "1x1_64_64@160": (160, 160, 64, 64, 1, 1),
+    "1x1_128_128@20": (20, 20, 128, 128, 1, 1),
 }
 
 if __name__ == "__main__":
@@ -158,7 +160,7 @@ if __name__ == "__main__":
         Ho, Wo = (H + 2 * (k // 2) - k) // st + 1, (W + 2 * (k // 2) - k) // st + 1
         y = torch.empty(32, Ho, Wo, Cout, dtype=torch.bfloat16, device=dev)
         for _ in range(3):
-            ops.conv_fwd(xb, wb, bias, y, stride=st, act="relu")
+            ops.conv_fwd(xb, wb, bias, y, stride=st, act=sys.argv[3] if len(sys.argv) > 3 else "relu")
         torch.cuda.synchronize()
         sys.exit(0)
     # --- correctness ---

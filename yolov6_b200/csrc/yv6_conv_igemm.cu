@@ -61,7 +61,12 @@ struct ConvKParams {
   // nine taps through UMMA descriptors offset into it; B tiles ride their own ring (or stay resident).
   int32_t halo, a_stages, b_stages, b_resident;
   int32_t a_region_bytes, b_region_bytes;  // smem carve: [A ring][B ring][2 C buffers][barriers]
+  int32_t bias_smem;                       // bias[0 .. tiles_n*BN) is staged in shared memory by the epilogue warps
+  int32_t res_aligned;                     // residual rows are 16-byte aligned (channel offset / pitches % 8 == 0)
+  int32_t fast_act;                        // bf16 outputs: SiLU through tanh.approx (rel. error 2^-11 < bf16 ulp)
+  unsigned long long* trace;               // debug: clock64 stamps of CTA 0 (16 slots) or null
 };
+#define YV6_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[slot] = (unsigned long long)clock64(); } while (0)
 
 constexpr int kHaloW = 10, kHaloH = 18;                   // BW = 8, BH = 16 output tile + 1-pixel border
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;         // 23040
@@ -165,14 +170,33 @@ __device__ __forceinline__ void store_chunk(const ConvKParams& p, int64_t off, i
 constexpr int kCBufBytes = kTileRows * 128;  // one staged output chunk: 128 rows x 128 B
 constexpr int kCBufCount = 4;               // two per epilogue group
 
+constexpr int kBiasSmemFloats = 1024;        // bias staged in shared memory when the layer's channels fit
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // bias + activation (+ residual) for 16 consecutive output channels of one pixel
-__device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32_t (&r)[16], int n, int ncol,
+__device__ __forceinline__ void epilogue_math(const ConvKParams& p, const float* sbias, const uint32_t (&r)[16], int n, int ncol,
                                               bool valid, int64_t roff, float (&v)[16]) {
   if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 b = __ldg(b4 + j);
+      // shared-memory copy (broadcast LDS) when staged; the global path costs an exposed L2 round trip per chunk
+      const float4 b = sbias ? *reinterpret_cast<const float4*>(sbias + n + 4 * j)
+                             : __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
       v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
       v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
       v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
@@ -185,12 +209,20 @@ __device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32
   if (p.act == YV6_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else if (p.act == YV6_ACT_SILU) {       // x * sigmoid(x); ex2/rcp approximations are ~1e-7 relative
+  } else if (p.act == YV6_ACT_SILU) {
+    if (p.fast_act) {                       // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU per element
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+      for (int j = 0; j < 16; ++j) {
+        const float h = 0.5f * v[j];
+        v[j] = fmaf(h, tanh_fast(h), h);
+      }
+    } else {                                // ex2 / rcp approximations are ~1e-7 relative
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] * rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * v[j]));
+    }
   } else if (p.act == YV6_ACT_SIGMOID) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
+    for (int j = 0; j < 16; ++j) v[j] = rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * v[j]));
   }
   if (p.res != nullptr && valid && ncol > 0) {
     for (int pl = 0; pl < p.res_planes; ++pl) {
@@ -214,6 +246,86 @@ __device__ __forceinline__ void epilogue_math(const ConvKParams& p, const uint32
   }
 }
 
+// Fast epilogue step: 32 accumulator columns of this thread's row -> bias, activation, optional residual ->
+// one staged (swizzled) row segment.  Straight-line code: a single TMEM load, bias from shared memory,
+// the activation chosen once per call, 128-bit shared stores.  `base` = shared address of the row,
+// `rxor` = row & 7 (128-byte swizzle), `unit0` = first 16-byte unit of the segment within the row.
+template <bool F32>
+__device__ __forceinline__ void epi_cols32(const ConvKParams& p, const float* sbias, uint32_t taddr, int n,
+                                           const __nv_bfloat16* res_row, uint32_t base, uint32_t rxor, int unit0) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  uint4 rq[4];
+  if (res_row != nullptr) {               // issued before the TMEM wait: the L2 round trip overlaps it
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n) + j);
+  }
+  tmem_ld_wait();
+  float v[32];
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = sbias ? *reinterpret_cast<const float4*>(sbias + n + 4 * j)
+                             : __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+      v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+      v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+      v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+      v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  }
+  if (p.act == YV6_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (p.act == YV6_ACT_SILU) {
+    if (p.fast_act) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float h = 0.5f * v[j];
+        v[j] = fmaf(h, tanh_fast(h), h);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] * rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * v[j]));
+    }
+  } else if (p.act == YV6_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * v[j]));
+  }
+  if (res_row != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[8 * j + 2 * k] = fmaf(p.alpha, __low2float(b2), v[8 * j + 2 * k]);
+        v[8 * j + 2 * k + 1] = fmaf(p.alpha, __high2float(b2), v[8 * j + 2 * k + 1]);
+      }
+    }
+  }
+  if (F32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = base + ((((uint32_t)(unit0 + j)) ^ rxor) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
+                   "f"(v[4 * j + 3])
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = base + ((((uint32_t)(unit0 + j)) ^ rxor) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])),
+                   "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                   "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                   : "memory");
+    }
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -224,7 +336,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.a_region_bytes;
   uint8_t* sC = sB + (size_t)p.b_region_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kCBufCount * kCBufBytes);
+  float* sBiasBuf = reinterpret_cast<float*>(sC + kCBufCount * kCBufBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kCBufCount * kCBufBytes + kBiasSmemFloats * sizeof(float));
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -237,6 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) YV6_TRACE(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -261,6 +375,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) YV6_TRACE(1);
 
   const int kblocks = p.npairs * p.taps * p.cin_blocks;
 
@@ -326,6 +441,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                           t.i0, pa);
               tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage],
                           tap * p.Cin + cb * p.kb_elems, t.n0, pb);
+              if (tile == (int)blockIdx.x && pi == 0 && tap == 0 && cb == 0) YV6_TRACE(2);
             }
             __syncwarp();
             if (++stage == p.stages) {
@@ -401,6 +517,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (kb == 0 && tile == (int)blockIdx.x && lane == 0) YV6_TRACE(3);
         const uint64_t ad = desc_const | (uint64_t)(a_base + (uint32_t)stage * a_step);
         const uint64_t bd = desc_const | (uint64_t)(b_base + (uint32_t)stage * b_step);
         if (elect_one()) {
@@ -420,6 +537,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (elect_one()) umma_commit(&tfull[acc]);
       __syncwarp();
+      if (tile == (int)blockIdx.x && lane == 0) YV6_TRACE(4);
       if (++acc == G) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -436,6 +554,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int NBUF = kCBufCount / G;          // staging buffers per group (2 when G = 2, 1 when G = 4)
     uint8_t* gC = sC + group * NBUF * kCBufBytes;
     const bool f32 = (p.y_dtype == YV6_DT_F32);
+    const float* sbias = nullptr;
+    if (p.bias_smem) {   // the epilogue warps are idle until the first accumulator is ready: stage the bias now
+      for (int i = (int)threadIdx.x - 64; i < p.tiles_n * p.BN; i += 128 * G) sBiasBuf[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 7, %0;" ::"r"(128 * G) : "memory");
+      sbias = sBiasBuf;
+    }
     uint32_t acc_phase = 0;
     int cbuf = 0;
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += G * gridDim.x) {
@@ -446,8 +570,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                           (int64_t)wo * p.y_w_stride;
       const int64_t roff = (int64_t)img * p.res_img_stride + (int64_t)ho * p.res_h_stride +
                            (int64_t)wo * p.res_w_stride;
+      // straight-line path: single output plane, no residual or a 16-byte aligned bf16 one
+      const __nv_bfloat16* res_row = (p.res != nullptr && valid) ? p.res + roff : nullptr;
+      const bool fast_tile = (p.out_planes == 1) && (p.res == nullptr || (p.res_planes == 1 && p.res_aligned));
       mbar_wait(&tfull[group], acc_phase);
       tc_fence_after();
+      if (tile == (int)blockIdx.x && q == 0 && lane == 0) YV6_TRACE(5);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * p.BN);
       if (p.tma_store == 2) {
         // ---- per-warp stores: the 32 rows of this warp form a box of the output, so each warp stages
@@ -462,16 +590,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last read this buffer is done
             __syncwarp();
             const uint32_t base = smem_u32(buf) + lrow;
+            if (fast_tile && nsub * 16 == p.c_chunk) {
+              if (f32) {
+                epi_cols32<true>(p, sbias, taddr + (uint32_t)c0, t.n0 + c0, res_row, base, lxor, 0);
+              } else {
+                epi_cols32<false>(p, sbias, taddr + (uint32_t)c0, t.n0 + c0, res_row, base, lxor, 0);
+                epi_cols32<false>(p, sbias, taddr + (uint32_t)(c0 + 32), t.n0 + c0 + 32, res_row, base, lxor, 4);
+              }
+            } else {
             uint32_t r[2][16];
             tmem_ld16(taddr + (uint32_t)c0, r[0]);
-#pragma unroll
+#pragma unroll 1
             for (int sb = 0; sb < 4; ++sb) {
               if (sb < nsub) {
                 tmem_ld_wait();
                 if (sb + 1 < nsub) tmem_ld16(taddr + (uint32_t)(c0 + 16 * (sb + 1)), r[(sb + 1) & 1]);
                 const int n = t.n0 + c0 + 16 * sb;
                 float v[16];
-                epilogue_math(p, r[sb & 1], n, min(16, p.Cout - n), valid, roff, v);
+                epilogue_math(p, sbias, r[sb & 1], n, min(16, p.Cout - n), valid, roff, v);
                 for (int k = 0; k < pl; ++k) {  // bf16x3: peel the planes already written
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
@@ -496,6 +632,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
             }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -517,16 +654,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (issuer) tma_store_wait_read<NBUF - 1>();
             epi_bar_sync(group);
             const uint32_t base = smem_u32(buf) + row_smem;
+            if (fast_tile && nsub * 16 == p.c_chunk) {
+              if (f32) {
+                epi_cols32<true>(p, sbias, taddr + (uint32_t)c0, t.n0 + c0, res_row, base, row_xor, 0);
+              } else {
+                epi_cols32<false>(p, sbias, taddr + (uint32_t)c0, t.n0 + c0, res_row, base, row_xor, 0);
+                epi_cols32<false>(p, sbias, taddr + (uint32_t)(c0 + 32), t.n0 + c0 + 32, res_row, base, row_xor, 4);
+              }
+            } else {
             uint32_t r[2][16];
             tmem_ld16(taddr + (uint32_t)c0, r[0]);
-#pragma unroll
+#pragma unroll 1
             for (int sb = 0; sb < 4; ++sb) {
               if (sb < nsub) {
                 tmem_ld_wait();
                 if (sb + 1 < nsub) tmem_ld16(taddr + (uint32_t)(c0 + 16 * (sb + 1)), r[(sb + 1) & 1]);
                 const int n = t.n0 + c0 + 16 * sb;
                 float v[16];
-                epilogue_math(p, r[sb & 1], n, min(16, p.Cout - n), valid, roff, v);
+                epilogue_math(p, sbias, r[sb & 1], n, min(16, p.Cout - n), valid, roff, v);
                 for (int k = 0; k < pl; ++k) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
@@ -553,6 +698,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               }
             }
+            }
             fence_proxy_async_smem();
             epi_bar_sync(group);
             if (issuer) {
@@ -571,15 +717,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int n = t.n0 + c0;
           const int ncol = min(16, p.Cout - n);
           float v[16];
-          epilogue_math(p, r, n, ncol, valid, roff, v);
+          epilogue_math(p, sbias, r, n, ncol, valid, roff, v);
           if (valid && ncol > 0) store_chunk(p, off, n, ncol, v);
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[group]);
+      if (tile == (int)blockIdx.x && q == 0 && lane == 0) YV6_TRACE(6);
       acc_phase ^= 1;
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (group == 0 && q == 0 && lane == 0) YV6_TRACE(7);
   }
 
   tc_fence_before();
@@ -587,6 +735,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (lane == 0) YV6_TRACE(8);
   }
 }
 
@@ -753,7 +902,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // smem ring(s)
   k.a_stage_bytes = kTileRows * k.kb_bytes;
   k.b_stage_bytes = ((k.BN * k.kb_bytes + 1023) / 1024) * 1024;
-  const int budget = h->max_smem_optin - 1024 - 1024 - kCBufCount * kCBufBytes;
+  const int budget = h->max_smem_optin - 1024 - 1024 - kCBufCount * kCBufBytes - kBiasSmemFloats * (int)sizeof(float);
   if (k.halo) {
     const int b_tiles = k.npairs * k.cin_blocks * 9;   // B tiles one output tile consumes
     k.b_resident = (k.tiles_n == 1 && b_tiles <= kMaxBStages && d->force_stages == 0 &&
@@ -779,7 +928,8 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     k.a_region_bytes = stages * k.a_stage_bytes;
     k.b_region_bytes = stages * k.b_stage_bytes;
   }
-  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + 1024 + 1024;
+  k.trace = reinterpret_cast<unsigned long long*>(d->trace);
+  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + kBiasSmemFloats * sizeof(float) + 1024 + 1024;
 
   // four groups only pay off when the tile's mainloop is shorter than its epilogue (1x1 / small-K layers)
   const int kblocks_per_tile = k.npairs * k.taps * k.cin_blocks;
@@ -791,6 +941,10 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
 
   k.act = d->act;
   k.y_dtype = d->y_dtype;
+  k.bias_smem = (d->bias != nullptr && k.tiles_n * k.BN <= kBiasSmemFloats) ? 1 : 0;
+  k.fast_act = (d->y_dtype == YV6_DT_BF16 && d->nsplit != 3) ? 1 : 0;
+  k.res_aligned = (d->res != nullptr && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0 && d->res_img_stride % 8 == 0 &&
+                   d->res_h_stride % 8 == 0 && d->res_w_stride % 8 == 0) ? 1 : 0;
   k.out_planes = (d->nsplit == 3 && d->y_dtype == YV6_DT_BF16) ? 3 : 1;
   k.res_planes = (d->nsplit == 3) ? 3 : 1;
   k.y = d->y;

@@ -81,7 +81,10 @@ def conv_fwd(x, w, bias, y, *, cin=None, x_c_offset=0, stride=1, act=None, y_c_o
     d.nsplit = nsplit
     if force:
         for k, v in force.items():
-            setattr(d, "force_" + k, int(v))
+            if k == "trace":                      # debug: uint64[16] device tensor for the kernel's phase stamps
+                d.trace = v.data_ptr()
+            else:
+                setattr(d, "force_" + k, int(v))
     dev = x.device.index or 0
     _lib.check(_lib.lib().yv6_conv_fwd(_lib.handle(dev), C.byref(d), _lib.stream_ptr(stream)))
     return y
