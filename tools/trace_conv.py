@@ -22,6 +22,8 @@ SHAPES = [  # name, N, H, W, Cin, Cout, k, stride, act, out_f32
     ("3x3 64->64 @80 relu", 32, 80, 80, 64, 64, 3, 1, "relu", False),
     ("1x1 64->64 @160 relu", 32, 160, 160, 64, 64, 1, 1, "relu", False),
     ("3x3 256->256 @40 relu", 32, 40, 40, 256, 256, 3, 1, "relu", False),
+    ("3x3 64->64 @160 relu", 32, 160, 160, 64, 64, 3, 1, "relu", False),
+    ("3x3 128->128 @80 relu", 32, 80, 80, 128, 128, 3, 1, "relu", False),
 ]
 LABELS = ["prologue", "first TMA issue", "operands landed", "tile0 MMAs issued", "acc visible", "epilogue tile0",
           "stores drained", "dealloc"]
@@ -50,6 +52,10 @@ for name, N, H, W, Cin, Cout, k, st, act, f32 in SHAPES:
     d = [(t[i + 1] - t[i]) / clk if t[i + 1] and t[i] else float("nan") for i in range(8)]
     # slots: 0 entry,1 prologue,2 first tma,3 landed,4 mma issued,5 acc visible,6 epi done,7 drained,8 dealloc
     rel = [(t[i] - t[0]) / clk if t[i] else float("nan") for i in range(1, 9)]
+    def rel1(i):
+        return (t[i] - t[0]) / clk if t[i] else float("nan")
+    print(f"    local tile 4 / 8 (halo kernels): A-load issued {rel1(12):.2f} / {rel1(13):.2f}, MMAs committed {rel1(14):.2f} / {rel1(15):.2f}, "
+          f"epilogue done {rel1(9):.2f} / {rel1(10):.2f}")
     plan = ops.conv_plan((N, H, W, Cin), (Cout, k, k, Cin), st)
-    print(f"| {name} | {sorted(ts)[2]:.1f} | " + " | ".join(f"{v:.2f}" for v in rel) + f" | {list(plan)} |", flush=True)
+    print(f"| {name} | {sorted(ts)[2]:.1f} | " + " | ".join(f"{v:.2f}" for v in rel) + f" | {plan} |", flush=True)
 print("\n(columns = microseconds since kernel entry of CTA 0, at ~1.9 GHz)")

@@ -92,9 +92,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin with a watchdog: a mis-programmed pipeline must trap (-> cudaErrorLaunchFailure on the
-// host, surfaced as RuntimeError) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// host, surfaced as RuntimeError) instead of hanging the GPU.  The spin loop lives out of line so that
+// the many call sites stay a single try_wait + branch (instruction-cache footprint of the hot loops).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -103,11 +103,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000ull) {  // 4 s
-        printf("yv6: mbarrier wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+        if ((threadIdx.x & 31) == 0) printf("yv6: mbarrier wait timeout block %d warp %d\n", blockIdx.x, threadIdx.x >> 5);
         __trap();
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ---- TMA ----

@@ -394,6 +394,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&a_empty[sa], pha ^ 1);
+            if (pi == 0 && cb == 0 && lane == 0) {
+              if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(12);
+              if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(13);
+            }
             if (elect_one()) {
               mbar_expect_tx(&a_full[sa], (uint32_t)kHaloBytes);
               tma_load_5d(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 - 1, t.i0, pa);
@@ -465,6 +469,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // Loop-invariant parameters live in registers: the asm statements below clobber "memory", which would
+    // otherwise force a constant-bank reload (and its latency) in front of every tcgen05.mma group.
+    const int num_tiles = p.num_tiles, BN = p.BN, ksteps = p.ksteps, nstages = p.stages;
+    const int a_stages = p.a_stages, b_stages = p.b_stages, b_resident = p.b_resident;
+    const int pcs = p.npairs * p.cin_blocks;
     if (p.halo) {
       // A descriptors walk the halo tile: 8-row groups are the 8 pixels of one output row, one halo row
       // (10 pixels = 1280 bytes) apart; tap (r,s) just shifts the start address by (10 r + s) pixels.
@@ -473,47 +482,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t halo_step = (uint32_t)kHaloStageBytes >> 4;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         int slot = 0;
         uint32_t started = 0;
-        for (int pc = 0; pc < p.npairs * p.cin_blocks; ++pc) {
+        for (int pc = 0; pc < pcs; ++pc) {
           mbar_wait(&a_full[sa], pha);
           tc_fence_after();
           const uint32_t a0 = a_base + (uint32_t)sa * halo_step;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap, ++slot) {
-            const int bs = p.b_resident ? slot : sb;
-            mbar_wait(&b_full[bs], p.b_resident ? 0u : phb);
-            tc_fence_after();
-            const int r = tap / 3, sx = tap - 3 * r;
-            const uint64_t ad = desc_a | (uint64_t)(a0 + (uint32_t)(r * kHaloW + sx) * 8u);
+            const int bs = b_resident ? slot : sb;
+            // resident weights were loaded (and waited for) during this CTA's first tile
+            if (!b_resident || first) {
+              mbar_wait(&b_full[bs], b_resident ? 0u : phb);
+              tc_fence_after();
+            }
+            const uint64_t ad = desc_a | (uint64_t)(a0 + (uint32_t)((tap / 3) * kHaloW + (tap % 3)) * 8u);
             const uint64_t bd = desc_b | (uint64_t)(b_base + (uint32_t)bs * b_step);
             if (elect_one()) {
               umma_bf16(d_tmem, ad, bd, idesc, started);
               umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
               umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
               umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-              if (!p.b_resident) umma_commit(&b_empty[sb]);
+              if (!b_resident) umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             started = 1u;
-            if (!p.b_resident && ++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            if (!b_resident && ++sb == b_stages) { sb = 0; phb ^= 1; }
           }
           if (elect_one()) umma_commit(&a_empty[sa]);
           __syncwarp();
-          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+          if (++sa == a_stages) { sa = 0; pha ^= 1; }
         }
         if (elect_one()) umma_commit(&tfull[acc]);
         __syncwarp();
+        if (lane == 0) {
+          if (tile == (int)blockIdx.x) YV6_TRACE(4);
+          if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(14);
+          if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(15);
+        }
+        first = false;
         if (++acc == G) { acc = 0; acc_phase ^= 1; }
       }
     } else
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -522,15 +541,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint64_t bd = desc_const | (uint64_t)(b_base + (uint32_t)stage * b_step);
         if (elect_one()) {
           umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(kb != 0));
-          if (p.ksteps > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-          if (p.ksteps > 2) {
+          if (ksteps > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          if (ksteps > 2) {
             umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
             umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
           }
           umma_commit(&empty[stage]);
         }
         __syncwarp();
-        if (++stage == p.stages) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
         }
@@ -723,7 +742,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(&tempty[group]);
-      if (tile == (int)blockIdx.x && q == 0 && lane == 0) YV6_TRACE(6);
+      if (q == 0 && lane == 0) {
+        if (tile == (int)blockIdx.x) YV6_TRACE(6);
+        if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(9);
+        if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(10);
+      }
       acc_phase ^= 1;
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
