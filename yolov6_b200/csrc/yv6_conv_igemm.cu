@@ -326,7 +326,10 @@ __device__ __forceinline__ void epi_cols32(const ConvKParams& p, const float* sb
   }
 }
 
-template <int G>
+// MODE: 0 = one TMA box per (tap, channel block); 1 = halo input tiles, weights streamed through a ring;
+//       2 = halo input tiles, the layer's weights resident in shared memory.  Compile-time so that each
+//       variant carries only its own producer / issue loops (instruction-cache footprint, issue-slot count).
+template <int G, int MODE>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
@@ -350,6 +353,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool HALO = (MODE != 0);
+  constexpr bool BRES = (MODE == 2);
   if (threadIdx.x == 0) YV6_TRACE(0);
 
   if (threadIdx.x == 0) {
@@ -361,7 +366,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 128);
     }
-    if (p.halo) {
+    if (HALO) {
       for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     }
@@ -383,7 +388,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ================================ TMA producer ================================
     // The whole warp walks the schedule (keeps control flow convergent so addresses / coordinates
     // live in uniform registers); one elected lane arms the barrier and issues the two TMA loads.
-    if (p.halo) {
+    if constexpr (HALO) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       bool first = true;
@@ -405,7 +410,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
             for (int tap = 0; tap < 9; ++tap, ++slot) {
-              if (p.b_resident) {
+              if constexpr (BRES) {
                 if (first && elect_one()) {
                   mbar_expect_tx(&b_full[slot], (uint32_t)(p.BN * 128));
                   tma_load_3d(sB + (size_t)slot * p.b_stage_bytes, &tmB, &b_full[slot], tap * p.Cin + cb * 64, t.n0, pb);
@@ -472,9 +477,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Loop-invariant parameters live in registers: the asm statements below clobber "memory", which would
     // otherwise force a constant-bank reload (and its latency) in front of every tcgen05.mma group.
     const int num_tiles = p.num_tiles, BN = p.BN, ksteps = p.ksteps, nstages = p.stages;
-    const int a_stages = p.a_stages, b_stages = p.b_stages, b_resident = p.b_resident;
+    const int a_stages = p.a_stages, b_stages = p.b_stages;
+    constexpr bool b_resident = BRES;
     const int pcs = p.npairs * p.cin_blocks;
-    if (p.halo) {
+    if constexpr (HALO) {
       // A descriptors walk the halo tile: 8-row groups are the 8 pixels of one output row, one halo row
       // (10 pixels = 1280 bytes) apart; tap (r,s) just shifts the start address by (10 r + s) pixels.
       const uint64_t desc_a = umma_smem_desc(0, (uint32_t)(kHaloW * 128), 2u);
@@ -1091,18 +1097,19 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
     tmC = tmA;  // unused by the kernel
   }
 
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
+  static const KernelFn kernels[2][3] = {
+      {conv_igemm_kernel<2, 0>, conv_igemm_kernel<2, 1>, conv_igemm_kernel<2, 2>},
+      {conv_igemm_kernel<4, 0>, conv_igemm_kernel<4, 1>, conv_igemm_kernel<4, 2>}};
   static bool configured = false;
   if (!configured) {
-    YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)h->max_smem_optin));
-    YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)h->max_smem_optin));
+    for (int g = 0; g < 2; ++g)
+      for (int m = 0; m < 3; ++m)
+        YV6_CHECK_CUDA(cudaFuncSetAttribute(kernels[g][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
     configured = true;
   }
-  if (k.groups == 4)
-    conv_igemm_kernel<4><<<plan.grid, 64 + 128 * 4, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
-  else
-    conv_igemm_kernel<2><<<plan.grid, 64 + 128 * 2, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
+  const int mode = k.halo ? (k.b_resident ? 2 : 1) : 0;
+  kernels[k.groups == 4 ? 1 : 0][mode]<<<plan.grid, 64 + 128 * k.groups, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }
