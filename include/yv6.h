@@ -122,6 +122,8 @@ typedef struct yv6_stem_desc {
   void* y;                  /* device bf16 [planes][N,H/2,W/2,Cout]                             */
   int64_t y_plane_stride;
   int32_t nsplit;           /* 1 or 3                                                           */
+  int32_t fp32_math;        /* nsplit == 1 only: 1 = fp32 image / weights on CUDA cores (training), 0 = bf16
+                               image / weights on tensor cores (inference)                          */
 } yv6_stem_desc;
 int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream);
 

@@ -87,3 +87,39 @@ def test_conv_rejects_bad_arguments():
     y = torch.zeros(1, 8, 8, 16, dtype=torch.bfloat16, device=dev)
     with pytest.raises(RuntimeError):
         ops.conv_fwd(x, w, None, y)
+
+
+@pytest.mark.parametrize("N,H,W,Cout,act,u8,fp32_math", [
+    (2, 64, 64, 32, "relu", False, 0), (1, 70, 50, 16, "relu", False, 0), (2, 33, 65, 64, "silu", True, 0),
+    (1, 128, 96, 48, None, False, 0), (2, 64, 64, 32, None, False, 1), (1, 37, 41, 16, "relu", True, 1)])
+def test_stem_kernels_match_torch(N, H, W, Cout, act, u8, fp32_math):
+    """yv6_stem_fwd (3x3 stride-2 conv over the 3-channel image, common.py:197-255 deploy form of the first
+    RepVGGBlock / ConvBNSiLU): tensor-core path on bf16-rounded image / weights, and the fp32 CUDA-core path."""
+    import ctypes as C
+    from yolov6_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(H * 131 + W)
+    x = (torch.rand(N, 3, H, W, generator=g) * 255).to(torch.uint8) if u8 else torch.rand(N, 3, H, W, generator=g)
+    w = torch.randn(Cout, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(Cout, generator=g) * 0.1
+    xf = x.float() / 255 if u8 else x
+    if fp32_math:
+        ref = F.conv2d(xf.double(), w.double(), b.double(), stride=2, padding=1)
+    else:   # the kernel rounds image and weights to bf16, accumulates in fp32
+        ref = F.conv2d(xf.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), b.double(), stride=2, padding=1)
+    ref = torch.relu(ref) if act == "relu" else (ref * torch.sigmoid(ref) if act == "silu" else ref)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    xd = x.to(dev).contiguous()
+    wd = w.permute(2, 3, 1, 0).contiguous().to(dev)        # [3][3][3][Cout]
+    bd = b.to(dev)
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    d = _lib.StemDesc()
+    d.x, d.x_dtype, d.in_scale = xd.data_ptr(), (_lib.DT_U8 if u8 else _lib.DT_F32), 1.0 / 255.0
+    d.N, d.H, d.W = N, H, W
+    d.w, d.bias, d.Cout, d.act = wd.data_ptr(), bd.data_ptr(), Cout, _lib.ACT_CODES[act]
+    d.y, d.y_plane_stride, d.nsplit, d.fp32_math = y.data_ptr(), 0, 1, fp32_math
+    _lib.check(_lib.lib().yv6_stem_fwd(_lib.handle(0), C.byref(d), _lib.stream_ptr()))
+    got = y.float().permute(0, 3, 1, 2).double().cpu()
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max() / (1 + ref.abs().max()))
+    assert err < 6e-3, err          # bf16 output rounding (2^-9 relative)

@@ -45,7 +45,7 @@ class StemDesc(C.Structure):
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("w", C.c_void_p), ("bias", C.c_void_p),
         ("Cout", C.c_int32), ("act", C.c_int32),
-        ("y", C.c_void_p), ("y_plane_stride", C.c_int64), ("nsplit", C.c_int32),
+        ("y", C.c_void_p), ("y_plane_stride", C.c_int64), ("nsplit", C.c_int32), ("fp32_math", C.c_int32),
     ]
 
 

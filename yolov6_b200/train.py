@@ -198,7 +198,7 @@ class TrainEngine:
                     d.x, d.x_dtype, d.in_scale = self.x.data_ptr(), (DT_U8 if self.x.dtype == torch.uint8 else DT_F32), 1.0 / 255.0
                     d.N, d.H, d.W = N, H, W
                     d.w, d.bias, d.Cout, d.act = wdev.data_ptr(), 0, op.cout, 0
-                    d.y, d.y_plane_stride, d.nsplit = raw.data_ptr(), 0, 1
+                    d.y, d.y_plane_stride, d.nsplit, d.fp32_math = raw.data_ptr(), 0, 1, 1
                     _lib.check(self.lib.yv6_stem_fwd(self.h, C.byref(d), _lib.stream_ptr()))
                     wk = wdev
                 else:
