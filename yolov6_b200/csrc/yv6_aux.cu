@@ -98,23 +98,24 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 }
 
 // Tensor-core stem for bf16 activations: the 3x3 stride-2 conv over 3 input channels is a GEMM with K = 27
-// (padded to 32).  One CTA = 8 output rows x 32 output columns; the 17 x 65 x 3 input patch is staged once in
-// shared memory as bf16, each warp owns one output row (two 16-pixel m-tiles) and gathers its mma.sync A
-// fragments straight from the patch; the weights live in registers as B fragments for the whole kernel.
-// The work is bound by HBM (read the image once, write N*Ho*Wo*Cout bf16 once), so legacy mma.sync is ample.
+// (padded to 32).  Persistent CTAs walk tiles of 8 output rows x 32 output columns; the 17 x 65 x 3 input
+// patch is staged in shared memory as bf16 with 16-byte global loads, each warp owns one output row (two
+// 16-pixel m-tiles) and gathers its mma.sync A fragments straight from the patch; the weights live in
+// registers as B fragments for the whole kernel.  The work is bound by HBM (read the image once, write
+// N*Ho*Wo*Cout bf16 once), so legacy mma.sync is ample; what matters is the instruction count per pixel.
 template <int COUT>
 __global__ void __launch_bounds__(256) stem_mma_kernel(const StemParams p) {
-  constexpr int TH = 8, TW = 32, PH = 2 * TH + 1, PW = 2 * TW + 1, PWP = PW + 1, NT = COUT / 8;
+  constexpr int TH = 8, TW = 32, PH = 2 * TH + 1, PW = 2 * TW + 1, NT = COUT / 8;
+  constexpr int PWP = 68;                                  // patch row pitch; element j of a row = input column wi0 + j - 1
+  static_assert(PW + 1 <= PWP, "patch pitch");
   constexpr int PITCH = COUT * 2 + 16;                     // staged output row pitch (bytes): conflict-free
   __shared__ __align__(16) __nv_bfloat16 patch[3 * PH * PWP];
   __shared__ __align__(16) uint8_t stage[8 * 32 * PITCH];
   const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
-  const int tile = blockIdx.x;
-  const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
-  const int px0 = tw * TW, py0 = th * TH;
+  const int num_tiles = tiles_w * tiles_h * p.N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 
-  // ---- weights -> B fragments (bf16), bias -> registers ----
+  // ---- weights -> B fragments (bf16), bias -> registers; once per CTA ----
   uint32_t bfrag[NT][2][2];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
@@ -134,23 +135,8 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemParams p) {
     bias[nt][0] = p.b ? __ldg(p.b + nt * 8 + 2 * t) : 0.f;
     bias[nt][1] = p.b ? __ldg(p.b + nt * 8 + 2 * t + 1) : 0.f;
   }
-  // ---- input patch -> shared (bf16, zero outside the image) ----
-  const int hi0 = 2 * py0 - 1, wi0 = 2 * px0 - 1;
-  for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
-    const int col = i % PW, row = (i / PW) % PH, c = i / (PW * PH);
-    const int hi = hi0 + row, wi = wi0 + col;
-    float v = 0.f;
-    if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
-      const int64_t idx = (((int64_t)n * 3 + c) * p.H + hi) * p.W + wi;
-      v = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + idx) * p.in_scale
-                 : __ldg(reinterpret_cast<const float*>(p.x) + idx);
-    }
-    patch[(c * PH + row) * PWP + col] = __float2bfloat16_rn(v);
-  }
-  __syncthreads();
   // ---- A-fragment gather offsets of this thread: k -> (channel, tap row, tap column) ----
   int koff[2][2][2];
-  bool kok[2][2][2];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -159,60 +145,109 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemParams p) {
       for (int e = 0; e < 2; ++e) {
         const int k = ks * 16 + h2 * 8 + 2 * t + e;
         const int tap = k / 3, c = k - 3 * tap, r = tap / 3, sx = tap - 3 * r;
-        kok[ks][h2][e] = (k < 27);
-        koff[ks][h2][e] = (k < 27) ? (c * PH + r) * PWP + sx : 0;
+        koff[ks][h2][e] = (k < 27) ? (c * PH + r) * PWP + sx + 1 : -1;
       }
-  float acc[2][NT][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+  const bool vec_ok = (p.W % 4 == 0);
   const unsigned short* P = reinterpret_cast<const unsigned short*>(patch);
+  uint8_t* wstage = stage + warp * 32 * PITCH;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int px0 = tw * TW, py0 = th * TH;
+    const int hi0 = 2 * py0 - 1, wi0 = 2 * px0 - 1;        // wi0 + 1 is a multiple of 64: 16-byte aligned groups
+    __syncthreads();                                       // previous tile's gathers are done with `patch`
+    // ---- input patch -> shared: per (channel, row) one leading element + 16 groups of four ----
+    for (int item = threadIdx.x; item < 3 * PH * 17; item += 256) {
+      const int rc = item / 17, q = item - rc * 17;
+      const int row = rc % PH, c = rc / PH;
+      const int hi = hi0 + row;
+      __nv_bfloat16* dst = patch + rc * PWP;
+      const bool row_ok = (hi >= 0 && hi < p.H);
+      const int64_t rbase = (((int64_t)n * 3 + c) * p.H + hi) * p.W;
+      if (q == 0) {
+        float v = 0.f;
+        if (row_ok && wi0 >= 0)
+          v = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi0) * p.in_scale
+                     : __ldg(reinterpret_cast<const float*>(p.x) + rbase + wi0);
+        dst[1] = __float2bfloat16_rn(v);
+      } else {
+        const int wi = wi0 + 1 + 4 * (q - 1);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_ok) {
+          if (vec_ok && wi + 3 < p.W) {
+            if (p.x_u8) {
+              const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi));
+              v[0] = u.x * p.in_scale; v[1] = u.y * p.in_scale; v[2] = u.z * p.in_scale; v[3] = u.w * p.in_scale;
+            } else {
+              const float4 f = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + rbase + wi));
+              v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+            }
+          } else {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const int base0 = (2 * warp) * PWP + 2 * (mt * 16 + g), base1 = base0 + 16;   // pixels g and g + 8
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      uint32_t a[4];
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const uint32_t lo0 = kok[ks][h2][0] ? P[base0 + koff[ks][h2][0]] : 0u, hi0v = kok[ks][h2][1] ? P[base0 + koff[ks][h2][1]] : 0u;
-        const uint32_t lo1 = kok[ks][h2][0] ? P[base1 + koff[ks][h2][0]] : 0u, hi1v = kok[ks][h2][1] ? P[base1 + koff[ks][h2][1]] : 0u;
-        a[2 * h2 + 0] = lo0 | (hi0v << 16);
-        a[2 * h2 + 1] = lo1 | (hi1v << 16);
+            for (int j = 0; j < 4; ++j)
+              if (wi + j < p.W)
+                v[j] = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi + j) * p.in_scale
+                              : __ldg(reinterpret_cast<const float*>(p.x) + rbase + wi + j);
+          }
+        }
+        __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + 2 + 4 * (q - 1));
+        d2[0] = __floats2bfloat162_rn(v[0], v[1]);
+        d2[1] = __floats2bfloat162_rn(v[2], v[3]);
       }
+    }
+    __syncthreads();
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int base0 = (2 * warp) * PWP + 2 * (mt * 16 + g), base1 = base0 + 16;   // pixels g and g + 8
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int o0 = koff[ks][h2][0], o1 = koff[ks][h2][1];
+          const uint32_t lo0 = o0 >= 0 ? P[base0 + o0] : 0u, hi0v = o1 >= 0 ? P[base0 + o1] : 0u;
+          const uint32_t lo1 = o0 >= 0 ? P[base1 + o0] : 0u, hi1v = o1 >= 0 ? P[base1 + o1] : 0u;
+          a[2 * h2 + 0] = lo0 | (hi0v << 16);
+          a[2 * h2 + 1] = lo1 | (hi1v << 16);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+              : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[nt][ks][0]), "r"(bfrag[nt][ks][1]));
+        }
+      }
+    }
+    // ---- bias + activation -> staged row of this warp -> coalesced 16-byte stores ----
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        asm volatile(
-            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-            : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
-            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[nt][ks][0]), "r"(bfrag[nt][ks][1]));
+        const float v0 = act_apply(acc[mt][nt][0] + bias[nt][0], p.act), v1 = act_apply(acc[mt][nt][1] + bias[nt][1], p.act);
+        const float v2 = act_apply(acc[mt][nt][2] + bias[nt][0], p.act), v3 = act_apply(acc[mt][nt][3] + bias[nt][1], p.act);
+        *reinterpret_cast<__nv_bfloat162*>(wstage + (mt * 16 + g) * PITCH + (nt * 8 + 2 * t) * 2) = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<__nv_bfloat162*>(wstage + (mt * 16 + g + 8) * PITCH + (nt * 8 + 2 * t) * 2) = __floats2bfloat162_rn(v2, v3);
+      }
+    __syncwarp();
+    const int py = py0 + warp;
+    if (py < p.Ho) {
+      const int valid = min(TW, p.Wo - px0);
+      __nv_bfloat16* dst = p.y + (((int64_t)n * p.Ho + py) * p.Wo + px0) * COUT;
+      constexpr int CPP = COUT / 8;                          // 16-byte chunks per pixel
+      for (int i = lane; i < valid * CPP; i += 32) {
+        const int px = i / CPP, part = i - px * CPP;
+        reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(wstage + px * PITCH + part * 16);
       }
     }
-  }
-  // ---- bias + activation -> staged row of this warp -> coalesced 16-byte stores ----
-  uint8_t* wstage = stage + warp * 32 * PITCH;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const float v0 = act_apply(acc[mt][nt][0] + bias[nt][0], p.act), v1 = act_apply(acc[mt][nt][1] + bias[nt][1], p.act);
-      const float v2 = act_apply(acc[mt][nt][2] + bias[nt][0], p.act), v3 = act_apply(acc[mt][nt][3] + bias[nt][1], p.act);
-      *reinterpret_cast<__nv_bfloat162*>(wstage + (mt * 16 + g) * PITCH + (nt * 8 + 2 * t) * 2) = __floats2bfloat162_rn(v0, v1);
-      *reinterpret_cast<__nv_bfloat162*>(wstage + (mt * 16 + g + 8) * PITCH + (nt * 8 + 2 * t) * 2) = __floats2bfloat162_rn(v2, v3);
-    }
-  __syncwarp();
-  const int py = py0 + warp;
-  if (py < p.Ho) {
-    const int valid = min(TW, p.Wo - px0);
-    __nv_bfloat16* dst = p.y + (((int64_t)n * p.Ho + py) * p.Wo + px0) * COUT;
-    constexpr int CPP = COUT / 8;                            // 16-byte chunks per pixel
-    for (int i = lane; i < valid * CPP; i += 32) {
-      const int px = i / CPP, part = i - px * CPP;
-      reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(wstage + px * PITCH + part * 16);
-    }
+    __syncwarp();
   }
 }
 
@@ -412,7 +447,8 @@ extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream)
   cudaStream_t s = (cudaStream_t)stream;
   if (d->nsplit == 1 && !d->fp32_math) {
     // bf16 activations: tensor-core path (bf16 image / weights, fp32 accumulate)
-    const unsigned tiles = (unsigned)(((p.Wo + 31) / 32) * ((p.Ho + 7) / 8) * p.N);
+    const unsigned ntile = (unsigned)(((p.Wo + 31) / 32) * ((p.Ho + 7) / 8) * p.N);
+    const unsigned tiles = std::min<unsigned>(ntile, (unsigned)h->num_sms * 6);   // persistent CTAs
     switch (d->Cout) {
       case 16: stem_mma_kernel<16><<<tiles, 256, 0, s>>>(p); break;
       case 32: stem_mma_kernel<32><<<tiles, 256, 0, s>>>(p); break;
