@@ -27,6 +27,10 @@ CASES = [
     ("1x1_x3_f32out", 2, 20, 20, 64, 80, 1, 1, "sigmoid", True, 3, False, 0, 0, None),
     ("3x3_x3_residual", 2, 20, 20, 64, 64, 3, 1, "relu", False, 3, True, 0, 0, None),
     ("3x3_bi_batch5", 5, 10, 10, 64, 64, 3, 1, "relu", False, 1, False, 0, 0, None),
+    # many tiles per CTA (persistent loop over tiles), small weight tensors
+    ("3x3_s2_cin32_many_tiles", 8, 160, 160, 32, 64, 3, 2, "relu", False, 1, False, 0, 0, None),
+    ("1x1_many_tiles_res", 8, 96, 96, 64, 64, 1, 1, "silu", False, 1, True, 0, 0, None),
+    ("3x3_s2_x3_many_tiles", 6, 96, 96, 32, 32, 3, 2, "relu", False, 3, False, 0, 0, None),
 ]
 
 

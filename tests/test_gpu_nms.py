@@ -56,3 +56,28 @@ def test_source_indices_and_empty_images():
     for b in range(3):
         assert count[b] == ref[b].shape[0]
         assert np.array_equal(src[b, :count[b]].cpu().numpy(), ref_idx[b].astype(np.int32))
+
+
+def test_detect_pipeline_matches_eager_model_plus_nms():
+    """DetectPipeline (one CUDA graph: H2D -> network -> decode -> NMS -> D2H) returns exactly what the eager
+    calls `model(x)` + `non_max_suppression` return (core/inferer.py:70-82)."""
+    from yolov6_b200.model import build_model
+    from yolov6_b200.nms import non_max_suppression
+    from yolov6_b200.pipeline import DetectPipeline
+    from yolov6_b200.synth import randomize_
+    dev = torch.device("cuda:0")
+    m = randomize_(build_model("yolov6n", 80, dev), seed=3).eval()
+    B, S = 3, 192
+    kw = dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)
+    pipe = DetectPipeline(m, B, S, S, host_input=True, **kw)
+    g = torch.Generator().manual_seed(9)
+    for _ in range(2):
+        img = (torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8)
+        dets = pipe(img)
+        with torch.no_grad():
+            pred = m(img.to(dev))[0]
+        ref = non_max_suppression(pred, **kw)
+        assert len(dets) == B
+        assert sum(len(d) for d in dets) > 0
+        for d, r in zip(dets, ref):
+            assert torch.equal(d, r.cpu())

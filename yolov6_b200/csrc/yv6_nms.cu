@@ -1,15 +1,16 @@
-// yv6_nms.cu -- batched non-maximum suppression for all images of a batch in four launches.
+// yv6_nms.cu -- batched non-maximum suppression for all images of a batch in three launches.
 //
 // Reference: `non_max_suppression` (yolov6/utils/nms.py:31-105) which loops over images in Python,
 // compacts with boolean masks and calls torchvision.ops.nms per image (nms.py:96).  Here:
-//   1. nms_scan   : warp-per-anchor-row pass over pred[B,A,5+nc] (coalesced class reads): candidate
-//                   rule of nms.py:48, obj*cls (nms.py:69), best class (nms.py:79-80) or per-class
-//                   count (nms.py:75-77); per-anchor entry counts + per-tile totals.
-//   2. nms_emit   : order-preserving compaction (anchor-major, class-minor = `nonzero` order): boxes
-//                   xywh->xyxy (nms.py:21-28), 64-bit sort keys.
-//   3. nms_sort   : one block per image, bitonic sort of (descending score, ascending position) keys
-//                   -- a total order equal to torchvision's stable descending sort.
-//   4. nms_greedy : one block per image, greedy suppression in chunks of 64 sorted candidates against
+//   1. nms_select : one warp-per-anchor-row pass over pred[B,A,5+nc] (coalesced class reads, pred is read
+//                   exactly once): candidate rule of nms.py:48, obj*cls (nms.py:69), best class
+//                   (nms.py:79-80) or every class above the threshold (nms.py:75-77); survivors take a
+//                   slot from a per-image atomic counter and write box (xywh->xyxy, nms.py:21-28),
+//                   score, class, anchor and a 64-bit key (descending score, ascending anchor*nc+class).
+//   2. nms_sort   : one block per image, bitonic key-value sort (value = slot).  The key order is a total
+//                   order equal to torchvision's stable descending sort over the reference's candidate
+//                   list, whose order is anchor-major / class-minor (`nonzero`, nms.py:76).
+//   3. nms_greedy : one block per image, greedy suppression in chunks of 64 sorted candidates against
 //                   the kept set; class offset boxes + cls*4096 (nms.py:94-95); float IoU promoted to
 //                   double against the double threshold exactly like torchvision's CPU kernel; stops
 //                   at max_det (nms.py:97-98); at most max_nms = 30000 candidates enter (nms.py:90-91).
@@ -28,17 +29,9 @@ constexpr int kMultiCap = 65536;    // candidate capacity per image in multi-lab
 constexpr int kSortSmemMax = 16384; // keys sorted in shared memory up to this many
 
 struct NmsWs {
-  int32_t* anchor_cnt;   // [B][A]
-  float* anchor_score;   // [B][A] best score (single-label)
-  int32_t* anchor_cls;   // [B][A] best class (single-label)
-  int32_t* tile_cnt;     // [B][T]
-  int32_t* cand_count;   // [B]
+  int32_t* cand_count;   // [B] slots taken (may exceed cap; clamped by the consumers)
   int32_t* overflow;     // [1]
   uint64_t* keys;        // [B][cap2]
-  float4* boxes;         // [B][cap]
-  float* scores;         // [B][cap]
-  int32_t* cls;          // [B][cap]
-  int32_t* anchors;      // [B][cap]
   int32_t cap, cap2, T;
 };
 
@@ -55,133 +48,159 @@ struct NmsParams {
   NmsWs ws;
 };
 
-__global__ void __launch_bounds__(kNmsTile) nms_scan_kernel(const NmsParams p) {
-  const int b = blockIdx.y, tile = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ int warp_tot[kNmsTile / 32];
-  int my_cnt = 0;
-  float my_score = 0.f;
-  int my_cls = 0;
-  for (int i = 0; i < 32; ++i) {
-    const int a = tile * kNmsTile + warp * 32 + i;
-    if (a >= p.A) break;  // warp-uniform
-    const float* row = p.pred + ((int64_t)b * p.A + a) * p.no;
-    const float obj = __ldg(row + 4);
-    float raw_max = -INFINITY, best = -INFINITY;
-    int best_c = 0x7fffffff, cnt = 0;
-    for (int c = lane; c < p.nc; c += 32) {
-      const float v = __ldg(row + 5 + c);
-      raw_max = fmaxf(raw_max, v);
-      const float s = __fmul_rn(v, obj);                                   // nms.py:69
-      const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[c] != 0);
-      if (s > best) { best = s; best_c = c; }                              // first max within the lane
-      if (s > p.conf && cls_ok) ++cnt;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      raw_max = fmaxf(raw_max, __shfl_xor_sync(0xffffffffu, raw_max, o));
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-      if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }  // first max overall
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
-    const bool cand = (obj > p.conf) && (raw_max > p.conf);                // nms.py:48
-    int entries;
-    if (p.multi_label) {
-      entries = cand ? cnt : 0;                                            // nms.py:75-77
-    } else {
-      const bool cls_ok = (p.class_mask == nullptr) || (best_c < p.nc && p.class_mask[best_c] != 0);
-      entries = (cand && best > p.conf && cls_ok) ? 1 : 0;                 // nms.py:79-84
-    }
-    if (lane == i) { my_cnt = entries; my_score = best; my_cls = best_c; }
-  }
-  const int a = tile * kNmsTile + threadIdx.x;
-  if (a < p.A) {
-    const int64_t o = (int64_t)b * p.A + a;
-    p.ws.anchor_cnt[o] = my_cnt;
-    p.ws.anchor_score[o] = my_score;
-    p.ws.anchor_cls[o] = my_cls;
-  }
-  int tot = my_cnt;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if (lane == 0) warp_tot[warp] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < kNmsTile / 32; ++w) s += warp_tot[w];
-    p.ws.tile_cnt[b * p.ws.T + tile] = s;
-  }
-}
-
 __device__ __forceinline__ float4 xywh2xyxy_rn(const float* r) {
   const float x = __ldg(r), y = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
   const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);               // nms.py:24-27
   return make_float4(__fsub_rn(x, hw), __fsub_rn(y, hh), __fadd_rn(x, hw), __fadd_rn(y, hh));
 }
 
-__device__ __forceinline__ uint64_t make_key(float score, int pos) {
-  return ((uint64_t)(0xffffffffu - __float_as_uint(score)) << 32) | (uint32_t)pos;  // score > 0
+__device__ __forceinline__ uint64_t make_key(float score, int order) {
+  return ((uint64_t)(0xffffffffu - __float_as_uint(score)) << 32) | (uint32_t)order;  // score > 0
 }
 
-__global__ void __launch_bounds__(kNmsTile) nms_emit_kernel(const NmsParams p) {
-  const int b = blockIdx.y, tile = blockIdx.x;
-  __shared__ int red[kNmsTile];
-  // offset of this tile = sum of the preceding tiles' counts
-  int part = 0;
-  for (int t = threadIdx.x; t < tile; t += kNmsTile) part += p.ws.tile_cnt[b * p.ws.T + t];
-  red[threadIdx.x] = part;
-  __syncthreads();
-  for (int s = kNmsTile / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
+// Hits of anchor rows; lanes own classes lane, lane+32, ...  R rows are scanned together so that their loads
+// and shuffle reductions overlap (the pass is latency-bound otherwise).  (nms.py:48,69,75-84)
+struct RowScan {
+  float obj, raw_max, best;
+  int best_c, cnt;        // cnt: warp total of (score > conf and class allowed)
+};
+template <int R>
+__device__ __forceinline__ void scan_rows(const NmsParams& p, const float* const (&row)[R], const bool (&ok)[R], int lane,
+                                          RowScan (&r)[R]) {
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    r[q].obj = ok[q] ? __ldg(row[q] + 4) : 0.f;
+    r[q].raw_max = -INFINITY;
+    r[q].best = -INFINITY;
+    r[q].best_c = 0x7fffffff;
+    r[q].cnt = 0;
   }
-  const int tile_off = red[0];
-  __syncthreads();
-  const int a = tile * kNmsTile + threadIdx.x;
-  const int cnt = (a < p.A) ? p.ws.anchor_cnt[(int64_t)b * p.A + a] : 0;
-  // exclusive scan of cnt over the block
-  red[threadIdx.x] = cnt;
-  __syncthreads();
-  for (int o = 1; o < kNmsTile; o <<= 1) {
-    const int v = (threadIdx.x >= o) ? red[threadIdx.x - o] : 0;
-    __syncthreads();
-    red[threadIdx.x] += v;
-    __syncthreads();
-  }
-  int pos = tile_off + red[threadIdx.x] - cnt;
-  if (tile == gridDim.x - 1 && threadIdx.x == kNmsTile - 1) {
-    const int total = tile_off + red[kNmsTile - 1];
-    p.ws.cand_count[b] = min(total, p.ws.cap);
-    if (total > p.ws.cap) atomicExch(p.ws.overflow, 1);
-  }
-  if (cnt == 0) return;
-  const float* row = p.pred + ((int64_t)b * p.A + a) * p.no;
-  const float4 box = xywh2xyxy_rn(row);
-  const int64_t base = (int64_t)b * p.ws.cap;
-  if (!p.multi_label) {
-    if (pos < p.ws.cap) {
-      const float s = p.ws.anchor_score[(int64_t)b * p.A + a];
-      p.ws.boxes[base + pos] = box;
-      p.ws.scores[base + pos] = s;
-      p.ws.cls[base + pos] = p.ws.anchor_cls[(int64_t)b * p.A + a];
-      p.ws.anchors[base + pos] = a;
-      p.ws.keys[(int64_t)b * p.ws.cap2 + pos] = make_key(s, pos);
+  for (int c = lane; c < p.nc; c += 32) {
+    const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[c] != 0);
+    float v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = ok[q] ? __ldg(row[q] + 5 + c) : -INFINITY;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      r[q].raw_max = fmaxf(r[q].raw_max, v[q]);
+      const float s = __fmul_rn(v[q], r[q].obj);                           // nms.py:69
+      if (s > r[q].best) { r[q].best = s; r[q].best_c = c; }               // first max within the lane
+      if (s > p.conf && cls_ok) ++r[q].cnt;
     }
-  } else {
-    const float obj = __ldg(row + 4);
-    for (int c = 0; c < p.nc; ++c) {
-      const float s = __fmul_rn(__ldg(row + 5 + c), obj);
-      const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[c] != 0);
-      if (s > p.conf && cls_ok) {
-        if (pos < p.ws.cap) {
-          p.ws.boxes[base + pos] = box;
-          p.ws.scores[base + pos] = s;
-          p.ws.cls[base + pos] = c;
-          p.ws.anchors[base + pos] = a;
-          p.ws.keys[(int64_t)b * p.ws.cap2 + pos] = make_key(s, pos);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      r[q].raw_max = fmaxf(r[q].raw_max, __shfl_xor_sync(0xffffffffu, r[q].raw_max, o));
+      const float ob = __shfl_xor_sync(0xffffffffu, r[q].best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, r[q].best_c, o);
+      if (ob > r[q].best || (ob == r[q].best && oc < r[q].best_c)) { r[q].best = ob; r[q].best_c = oc; }  // first max overall
+      r[q].cnt += __shfl_xor_sync(0xffffffffu, r[q].cnt, o);
+    }
+  }
+}
+
+__device__ __forceinline__ int row_entries(const NmsParams& p, const RowScan& r) {
+  const bool cand = (r.obj > p.conf) && (r.raw_max > p.conf);              // nms.py:48
+  if (p.multi_label) return cand ? r.cnt : 0;                              // nms.py:75-77
+  const bool cls_ok = (p.class_mask == nullptr) || (r.best_c < p.nc && p.class_mask[r.best_c] != 0);
+  return (cand && r.best > p.conf && cls_ok) ? 1 : 0;                      // nms.py:79-84
+}
+
+// One warp per 32 anchor rows.  Pass 1 counts the entries of each row (lane i keeps row i's count), one
+// atomicAdd per warp reserves the key slots, pass 2 revisits only the rows that have entries (L1/L2 hits)
+// and writes their keys.  Key = (descending score, ascending anchor*nc + class): everything the greedy
+// pass needs (anchor, class, exact score) is encoded in it, the box is re-read from `pred`.
+__global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p) {
+  constexpr int R = 4;
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* keys = p.ws.keys + (int64_t)b * p.ws.cap2;
+  const int a0 = blockIdx.x * kNmsTile + warp * 32;
+  if (a0 >= p.A) return;
+  const float* img = p.pred + (int64_t)b * p.A * p.no;
+  int my_entries = 0;                                                      // lane i: entries of row a0 + i
+  for (int i0 = 0; i0 < 32; i0 += R) {
+    const float* row[R];
+    bool ok[R];
+    RowScan r[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      ok[q] = (a0 + i0 + q < p.A);
+      row[q] = img + (int64_t)(a0 + i0 + q) * p.no;
+    }
+    scan_rows<R>(p, row, ok, lane, r);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int e = ok[q] ? row_entries(p, r[q]) : 0;
+      if (lane == i0 + q) my_entries = e;
+    }
+  }
+  int incl = my_entries;                                                   // inclusive prefix over the 32 rows
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(&p.ws.cand_count[b], total);
+  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  const int row_slot = slot0 + incl - my_entries;
+  if (!p.multi_label) {
+    for (int i0 = 0; i0 < 32; i0 += R) {
+      const float* row[R];
+      bool ok[R];
+      RowScan r[R];
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        ok[q] = __shfl_sync(0xffffffffu, my_entries, i0 + q) != 0;
+        row[q] = img + (int64_t)(a0 + i0 + q) * p.no;
+        any = any || ok[q];
+      }
+      if (!any) continue;  // warp-uniform
+      scan_rows<R>(p, row, ok, lane, r);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int slot = __shfl_sync(0xffffffffu, row_slot, i0 + q);
+        if (ok[q] && lane == 0 && slot < p.ws.cap) keys[slot] = make_key(r[q].best, a0 + i0 + q);
+      }
+    }
+    return;
+  }
+  for (int i0 = 0; i0 < 32; i0 += R) {
+    bool ok[R];
+    int slot[R];
+    float obj[R];
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      ok[q] = __shfl_sync(0xffffffffu, my_entries, i0 + q) != 0;
+      slot[q] = __shfl_sync(0xffffffffu, row_slot, i0 + q);
+      any = any || ok[q];
+    }
+    if (!any) continue;  // warp-uniform
+#pragma unroll
+    for (int q = 0; q < R; ++q) obj[q] = ok[q] ? __ldg(img + (int64_t)(a0 + i0 + q) * p.no + 4) : 0.f;
+    for (int c0 = 0; c0 < p.nc; c0 += 32) {                               // class-ascending within each row
+      const int c = c0 + lane;
+      const bool cls_ok = (c < p.nc) && ((p.class_mask == nullptr) || (p.class_mask[c] != 0));
+      float v[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[q] = (ok[q] && c < p.nc) ? __ldg(img + (int64_t)(a0 + i0 + q) * p.no + 5 + c) : 0.f;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const float sv = __fmul_rn(v[q], obj[q]);
+        const bool hit = ok[q] && cls_ok && (sv > p.conf);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int my = slot[q] + __popc(m & ((1u << lane) - 1u));
+          if (my < p.ws.cap) keys[my] = make_key(sv, (a0 + i0 + q) * p.nc + c);
         }
-        ++pos;
+        slot[q] += __popc(m);
       }
     }
   }
@@ -190,7 +209,9 @@ __global__ void __launch_bounds__(kNmsTile) nms_emit_kernel(const NmsParams p) {
 __global__ void __launch_bounds__(1024) nms_sort_kernel(const NmsParams p) {
   extern __shared__ uint64_t skeys[];
   const int b = blockIdx.x;
-  const int n = p.ws.cand_count[b];
+  const int taken = p.ws.cand_count[b];
+  if (taken > p.ws.cap && threadIdx.x == 0) atomicExch(p.ws.overflow, 1);
+  const int n = min(taken, p.ws.cap);
   if (n <= 1) return;
   int P = 2;
   while (P < n) P <<= 1;
@@ -202,8 +223,13 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const NmsParams p) {
     k[i] = v;
   }
   __syncthreads();
+  // Bitonic network.  Compare-exchange distances below CH stay inside one warp's chunk of CH keys, so those
+  // passes need only __syncwarp; block barriers are paid for the few long-distance passes alone.
+  const int CH = min(P, 256);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int size = 2; size <= P; size <<= 1) {
-    for (int j = size >> 1; j > 0; j >>= 1) {
+    int j = size >> 1;
+    for (; j >= CH; j >>= 1) {
       for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
         const int i = ((t / j) * 2 * j) + (t % j);
         const int l = i + j;
@@ -213,6 +239,20 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const NmsParams p) {
       }
       __syncthreads();
     }
+    for (; j > 0; j >>= 1) {
+      for (int chunk = warp; chunk * CH < P; chunk += nwarps) {
+        const int base = chunk * CH;
+        for (int t = lane; t < (CH >> 1); t += 32) {
+          const int i = base + ((t / j) * 2 * j) + (t % j);
+          const int l = i + j;
+          const uint64_t x = k[i], y = k[l];
+          const bool up = ((i & size) == 0);
+          if ((x > y) == up) { k[i] = y; k[l] = x; }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
   }
   if (in_smem)
     for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = k[i];
@@ -226,14 +266,17 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
   float* kept_area = reinterpret_cast<float*>(kept_box + p.max_det);   // [max_det]
   __shared__ float4 ch_box[64];
   __shared__ float ch_area[64];
-  __shared__ int ch_idx[64];
+  __shared__ float4 ch_raw[64];         // un-offset xyxy box (the output)
+  __shared__ int ch_cls[64], ch_anchor[64];
+  __shared__ float ch_score[64];
   __shared__ int ch_alive[64];
   __shared__ unsigned int ch_mask[64][2];
+  __shared__ int ch_out[64];            // output row of each chunk member, -1 when suppressed
   __shared__ int s_kept;
   const int b = blockIdx.x;
-  const int n = min(p.ws.cand_count[b], kMaxNms);
+  const int n = min(min(p.ws.cand_count[b], p.ws.cap), kMaxNms);
   const uint64_t* keys = p.ws.keys + (int64_t)b * p.ws.cap2;
-  const int64_t base = (int64_t)b * p.ws.cap;
+  const int div = p.multi_label ? p.nc : 1;                            // key order = anchor * div + class
   const double thr = p.iou;
   if (threadIdx.x == 0) s_kept = 0;
   __syncthreads();
@@ -246,15 +289,34 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
       ch_alive[c] = (c < m);
       ch_mask[c][0] = ch_mask[c][1] = 0u;
       if (c < m) {
-        const int idx = (int)(keys[c0 + c] & 0xffffffffu);
-        float4 bx = p.ws.boxes[base + idx];
+        const uint64_t key = keys[c0 + c];
+        const int order = (int)(key & 0xffffffffu);
+        const int anchor = order / div;
+        int cls;
+        if (p.multi_label) {
+          cls = order - anchor * div;
+        } else {                                                         // best class: recompute from the row (exact)
+          const float* row = p.pred + ((int64_t)b * p.A + anchor) * p.no;
+          const float obj = __ldg(row + 4);
+          float best = -INFINITY;
+          cls = 0;
+          for (int cc = 0; cc < p.nc; ++cc) {
+            const float sv = __fmul_rn(__ldg(row + 5 + cc), obj);
+            if (sv > best) { best = sv; cls = cc; }
+          }
+        }
+        const float4 raw = xywh2xyxy_rn(p.pred + ((int64_t)b * p.A + anchor) * p.no);
+        float4 bx = raw;
         if (!p.agnostic) {
-          const float off = __fmul_rn((float)p.ws.cls[base + idx], 4096.f);  // nms.py:94
+          const float off = __fmul_rn((float)cls, 4096.f);                // nms.py:94
           bx = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
         }
+        ch_raw[c] = raw;
+        ch_cls[c] = cls;
+        ch_anchor[c] = anchor;
+        ch_score[c] = __uint_as_float(0xffffffffu - (uint32_t)(key >> 32));
         ch_box[c] = bx;
         ch_area[c] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-        ch_idx[c] = idx;
       }
     }
     __syncthreads();
@@ -287,29 +349,36 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
       }
     }
     __syncthreads();
-    // (c) sequential resolve of the chunk, append survivors
+    // (c) sequential resolve of the chunk (bit masks only), then the survivors are appended in parallel
     if (threadIdx.x == 0) {
       unsigned int rem0 = 0u, rem1 = 0u;
       int k = kept;
-      for (int c = 0; c < m && k < p.max_det; ++c) {
+      for (int c = 0; c < 64; ++c) {
         const bool removed = (c < 32) ? ((rem0 >> c) & 1u) : ((rem1 >> (c - 32)) & 1u);
-        if (ch_alive[c] && !removed) {
+        int o = -1;
+        if (c < m && k < p.max_det && ch_alive[c] && !removed) {
           rem0 |= ch_mask[c][0];
           rem1 |= ch_mask[c][1];
-          kept_box[k] = ch_box[c];
-          kept_area[k] = ch_area[c];
-          const int idx = ch_idx[c];
-          const float4 bx = p.ws.boxes[base + idx];
-          float* o = p.out + ((int64_t)b * p.max_det + k) * 6;
-          o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-          o[4] = p.ws.scores[base + idx];
-          o[5] = (float)p.ws.cls[base + idx];
-          p.out_src[((int64_t)b * p.max_det + k) * 2] = p.ws.anchors[base + idx];
-          p.out_src[((int64_t)b * p.max_det + k) * 2 + 1] = p.ws.cls[base + idx];
-          ++k;
+          o = k++;
         }
+        ch_out[c] = o;
       }
       s_kept = k;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int c = threadIdx.x, k = ch_out[c];
+      if (k >= 0) {
+        kept_box[k] = ch_box[c];
+        kept_area[k] = ch_area[c];
+        const float4 bx = ch_raw[c];
+        float* o = p.out + ((int64_t)b * p.max_det + k) * 6;
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = ch_score[c];
+        o[5] = (float)ch_cls[c];
+        p.out_src[((int64_t)b * p.max_det + k) * 2] = ch_anchor[c];
+        p.out_src[((int64_t)b * p.max_det + k) * 2 + 1] = ch_cls[c];
+      }
     }
     __syncthreads();
   }
@@ -326,17 +395,9 @@ static void nms_layout(int32_t B, int32_t A, int32_t nc, int32_t multi_label, Nm
   const int T = (A + kNmsTile - 1) / kNmsTile;
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += align256(bytes); return base ? base + o : (char*)nullptr; };
-  ws->anchor_cnt = (int32_t*)take((int64_t)B * A * 4);
-  ws->anchor_score = (float*)take((int64_t)B * A * 4);
-  ws->anchor_cls = (int32_t*)take((int64_t)B * A * 4);
-  ws->tile_cnt = (int32_t*)take((int64_t)B * T * 4);
   ws->cand_count = (int32_t*)take((int64_t)B * 4);
   ws->overflow = (int32_t*)take(4);
   ws->keys = (uint64_t*)take((int64_t)B * cap2 * 8);
-  ws->boxes = (float4*)take((int64_t)B * cap * 16);
-  ws->scores = (float*)take((int64_t)B * cap * 4);
-  ws->cls = (int32_t*)take((int64_t)B * cap * 4);
-  ws->anchors = (int32_t*)take((int64_t)B * cap * 4);
   ws->cap = (int32_t)cap;
   ws->cap2 = (int32_t)cap2;
   ws->T = T;
@@ -385,9 +446,9 @@ extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int3
   if (overflow != nullptr) p.ws.overflow = overflow;
   cudaStream_t s = (cudaStream_t)stream;
   YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.overflow, 0, 4, s));
+  YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.cand_count, 0, sizeof(int32_t) * B, s));
   dim3 grid(p.ws.T, B);
-  nms_scan_kernel<<<grid, kNmsTile, 0, s>>>(p);
-  nms_emit_kernel<<<grid, kNmsTile, 0, s>>>(p);
+  nms_select_kernel<<<grid, kNmsTile, 0, s>>>(p);
   static bool configured = false;
   if (!configured) {
     YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemMax * 8));
