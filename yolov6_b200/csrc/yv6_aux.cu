@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 // registers as B fragments for the whole kernel.  The work is bound by HBM (read the image once, write
 // N*Ho*Wo*Cout bf16 once), so legacy mma.sync is ample; what matters is the instruction count per pixel.
 template <int COUT>
-__global__ void __launch_bounds__(256) stem_mma_kernel(const StemParams p) {
+__global__ void __launch_bounds__(256, 2) stem_mma_kernel(const StemParams p) {
   constexpr int TH = 8, TW = 32, PH = 2 * TH + 1, PW = 2 * TW + 1, NT = COUT / 8;
   constexpr int PWP = 68;                                  // patch row pitch; element j of a row = input column wi0 + j - 1
   static_assert(PW + 1 <= PWP, "patch pitch");
@@ -151,51 +151,75 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemParams p) {
   const unsigned short* P = reinterpret_cast<const unsigned short*>(patch);
   uint8_t* wstage = stage + warp * 32 * PITCH;
 
+  // Input patch items of this thread: item = (channel-row rc, group q); q == 0 is the single leading
+  // column, q >= 1 a 16-byte group of four.  The next tile's items are fetched into registers before the
+  // current tile is computed, so the global-load latency overlaps the gather / MMA / store of this tile.
+  constexpr int NITEM = (3 * PH * 17 + 255) / 256;
+  float4 pre[NITEM];
+  auto fetch = [&](int tile) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int hi0 = 2 * th * TH - 1, wi0 = 2 * tw * TW - 1;  // wi0 + 1 is a multiple of 64: 16-byte aligned groups
+#pragma unroll
+    for (int it = 0; it < NITEM; ++it) {
+      const int item = threadIdx.x + it * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (item < 3 * PH * 17) {
+        const int rc = item / 17, q = item - rc * 17;
+        const int row = rc % PH, c = rc / PH;
+        const int hi = hi0 + row;
+        if (hi >= 0 && hi < p.H) {
+          const int64_t rbase = (((int64_t)n * 3 + c) * p.H + hi) * p.W;
+          if (q == 0) {
+            if (wi0 >= 0)
+              v.x = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi0) * p.in_scale
+                           : __ldg(reinterpret_cast<const float*>(p.x) + rbase + wi0);
+          } else {
+            const int wi = wi0 + 1 + 4 * (q - 1);
+            if (vec_ok && wi + 3 < p.W) {
+              if (p.x_u8) {
+                const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi));
+                v = make_float4(u.x * p.in_scale, u.y * p.in_scale, u.z * p.in_scale, u.w * p.in_scale);
+              } else {
+                v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + rbase + wi));
+              }
+            } else {
+              float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (wi + j < p.W)
+                  e[j] = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi + j) * p.in_scale
+                                : __ldg(reinterpret_cast<const float*>(p.x) + rbase + wi + j);
+              v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+          }
+        }
+      }
+      pre[it] = v;
+    }
+  };
+  if ((int)blockIdx.x < num_tiles) fetch(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
     const int px0 = tw * TW, py0 = th * TH;
-    const int hi0 = 2 * py0 - 1, wi0 = 2 * px0 - 1;        // wi0 + 1 is a multiple of 64: 16-byte aligned groups
     __syncthreads();                                       // previous tile's gathers are done with `patch`
-    // ---- input patch -> shared: per (channel, row) one leading element + 16 groups of four ----
-    for (int item = threadIdx.x; item < 3 * PH * 17; item += 256) {
-      const int rc = item / 17, q = item - rc * 17;
-      const int row = rc % PH, c = rc / PH;
-      const int hi = hi0 + row;
-      __nv_bfloat16* dst = patch + rc * PWP;
-      const bool row_ok = (hi >= 0 && hi < p.H);
-      const int64_t rbase = (((int64_t)n * 3 + c) * p.H + hi) * p.W;
-      if (q == 0) {
-        float v = 0.f;
-        if (row_ok && wi0 >= 0)
-          v = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi0) * p.in_scale
-                     : __ldg(reinterpret_cast<const float*>(p.x) + rbase + wi0);
-        dst[1] = __float2bfloat16_rn(v);
-      } else {
-        const int wi = wi0 + 1 + 4 * (q - 1);
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (row_ok) {
-          if (vec_ok && wi + 3 < p.W) {
-            if (p.x_u8) {
-              const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi));
-              v[0] = u.x * p.in_scale; v[1] = u.y * p.in_scale; v[2] = u.z * p.in_scale; v[3] = u.w * p.in_scale;
-            } else {
-              const float4 f = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + rbase + wi));
-              v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-            }
-          } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (wi + j < p.W)
-                v[j] = p.x_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + rbase + wi + j) * p.in_scale
-                              : __ldg(reinterpret_cast<const float*>(p.x) + rbase + wi + j);
-          }
+    for (int it = 0; it < NITEM; ++it) {
+      const int item = threadIdx.x + it * 256;
+      if (item < 3 * PH * 17) {
+        const int rc = item / 17, q = item - rc * 17;
+        __nv_bfloat16* dst = patch + rc * PWP;
+        if (q == 0) {
+          dst[1] = __float2bfloat16_rn(pre[it].x);
+        } else {
+          __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + 2 + 4 * (q - 1));
+          d2[0] = __floats2bfloat162_rn(pre[it].x, pre[it].y);
+          d2[1] = __floats2bfloat162_rn(pre[it].z, pre[it].w);
         }
-        __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + 2 + 4 * (q - 1));
-        d2[0] = __floats2bfloat162_rn(v[0], v[1]);
-        d2[1] = __floats2bfloat162_rn(v[2], v[3]);
       }
     }
     __syncthreads();
+    if (tile + (int)gridDim.x < num_tiles) fetch(tile + gridDim.x);   // in flight during this tile's math
     float acc[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -448,7 +472,7 @@ extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream)
   if (d->nsplit == 1 && !d->fp32_math) {
     // bf16 activations: tensor-core path (bf16 image / weights, fp32 accumulate)
     const unsigned ntile = (unsigned)(((p.Wo + 31) / 32) * ((p.Ho + 7) / 8) * p.N);
-    const unsigned tiles = std::min<unsigned>(ntile, (unsigned)h->num_sms * 6);   // persistent CTAs
+    const unsigned tiles = std::min<unsigned>(ntile, (unsigned)h->num_sms * 2);   // persistent CTAs, two resident per SM (register budget)
     switch (d->Cout) {
       case 16: stem_mma_kernel<16><<<tiles, 256, 0, s>>>(p); break;
       case 32: stem_mma_kernel<32><<<tiles, 256, 0, s>>>(p); break;
