@@ -258,7 +258,12 @@ def main():
             peaks = json.load(f)
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = conv_flop / (conv_ms * 1e-3) / 1e12
-    nms_launches = 5
+    nms_launches = 3              # nms_select, nms_sort, nms_greedy
+    traffic = None                # DRAM bytes per conv launch from the committed ncu capture (profiles/)
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,7 +276,10 @@ def main():
                 "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * NMS_KW["max_det"] * 6 * 4 + B * 4},
         "gpu_launches": (eng.launch_count(B, S, S) + nms_launches) * args.steps,
         "roofline": {"bound": "tensor", "kernel": "yv6::conv_igemm_kernel", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                     "traffic_note": "bytes per conv_igemm launch, ncu dram__bytes_read+write averaged over the step's launches "
+                                     "(profiles/r01_conv_traffic.json); algorithmic activation bytes per launch = "
+                                     f"{eng.conv_bytes_per_launch(B, S, S):.3e}",
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
                      "launches_per_step": n_conv, "conv_ms_per_step": conv_ms, "algorithmic_gflop_per_step": conv_flop / 1e9,
                      "model_gflop_per_img": GFLOP_PER_IMG.get(args.model)},

@@ -48,3 +48,23 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{fn} imports the oracle"
+
+
+def test_ctypes_mirrors_match_the_header_struct_sizes(tmp_path):
+    """The ctypes Structure mirrors in yolov6_b200/_lib.py must have the sizes a C compiler gives the structs
+    of include/yv6.h (caught a silent field drift once)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from yolov6_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "yv6.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(yv6_conv_desc), '
+                   'sizeof(yv6_stem_desc), sizeof(yv6_loss_desc), sizeof(yv6_wgrad_desc), sizeof(yv6_bn_desc));return 0;}\n')
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(_lib.ConvDesc), C.sizeof(_lib.StemDesc), C.sizeof(_lib.LossDesc), C.sizeof(_lib.WgradDesc), C.sizeof(_lib.BnDesc)]
+    assert got == want, (got, want)

@@ -244,6 +244,21 @@ class InferEngine:
             total_ms += e0.elapsed_time(e1)
         return total_ms / steps, flops, len(convs)
 
+    def conv_bytes_per_launch(self, N, H, W):
+        """Algorithmic HBM bytes of an average conv launch: each conv reads its input slice and writes its output
+        slice once (bf16), weights once."""
+        plan = self._plan(N, H, W, torch.float32)
+        tot, n = 0.0, 0
+        for kind, d in plan["calls"]:
+            if kind != "conv":
+                continue
+            ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
+            wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
+            ysz = 4 if d.y_dtype == DT_F32 else 2
+            tot += d.N * (d.H * d.W * d.Cin * 2 + ho * wo * d.Cout * ysz) + d.Cout * d.kh * d.kw * d.Cin * 2
+            n += 1
+        return tot / max(n, 1)
+
     def profile_layers(self, x, iters=10, stream=None):
         """Per-launch timing table (name, shape, ms, TFLOP/s) with an L2 flush before every launch."""
         x = x.contiguous()
