@@ -2,7 +2,7 @@
 
 Same signature, assertions and return type as the reference's yolov6/utils/nms.py:31-105
 (`list` of B tensors [k,6] = xyxy, conf, cls on the input device; empty -> zeros((0,6))), but all
-images are processed by four kernel launches instead of a Python loop around torchvision.ops.nms.
+images are processed by three kernel launches (select, sort, greedy) instead of a Python loop around torchvision.ops.nms.
 """
 import ctypes as C
 
