@@ -81,3 +81,30 @@ def test_detect_pipeline_matches_eager_model_plus_nms():
         assert sum(len(d) for d in dets) > 0
         for d, r in zip(dets, ref):
             assert torch.equal(d, r.cpu())
+
+
+def test_detect_ring_overlapped_copies_match_eager():
+    """DetectRing: H2D copies on a copy stream overlapping the previous batch's kernels; results must equal the
+    eager model + NMS for every batch, in order."""
+    from yolov6_b200.model import build_model
+    from yolov6_b200.nms import non_max_suppression
+    from yolov6_b200.pipeline import DetectRing
+    from yolov6_b200.synth import randomize_
+    dev = torch.device("cuda:0")
+    m = randomize_(build_model("yolov6n", 80, dev), seed=3).eval()
+    B, S = 2, 160
+    kw = dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)
+    ring = DetectRing(m, B, S, S, **kw)
+    g = torch.Generator().manual_seed(4)
+    imgs = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8) for _ in range(5)]
+    outs = []
+    ring.submit(imgs[0])
+    for i in range(1, len(imgs)):
+        ring.submit(imgs[i])
+        outs.append(ring.collect())
+    outs.append(ring.collect())
+    for img, dets in zip(imgs, outs):
+        with torch.no_grad():
+            ref = non_max_suppression(m(img.to(dev))[0], **kw)
+        for d, r in zip(dets, ref):
+            assert torch.equal(d, r.cpu())

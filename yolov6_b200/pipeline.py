@@ -6,6 +6,11 @@ captures the same sequence -- pinned-host uint8 batch -> device (stem kernel sca
 fly) -> network kernels -> decode -> batched NMS -> detections back to pinned host memory -- into a
 CUDA graph once per (batch, size); `__call__` is then a single graph launch, so the ~80 kernel
 launches and all Python/ctypes work disappear from the steady state.
+
+`overlap_h2d=True` keeps the host->device copy of the images out of the graph and issues it on a copy
+stream instead: with two pipelines used alternately (see `DetectRing`) the copy of batch i+1 runs on the
+copy engine while the kernels of batch i run on the SMs, so a serving loop is bound by max(copy, compute)
+instead of their sum.
 """
 import torch
 
@@ -14,7 +19,7 @@ from .nms import nms_batched
 
 class DetectPipeline:
     def __init__(self, model, batch, height, width, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
-                 multi_label=False, max_det=300, host_input=True):
+                 multi_label=False, max_det=300, host_input=True, overlap_h2d=False, copy_stream=None):
         self.model = model.eval()
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -22,6 +27,12 @@ class DetectPipeline:
         self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, classes=classes, agnostic=agnostic,
                        multi_label=multi_label, max_det=max_det)
         self.host_input = host_input
+        self.overlap_h2d = bool(overlap_h2d and host_input)
+        if self.overlap_h2d:
+            self.copy_stream = copy_stream or torch.cuda.Stream(device=self.dev)
+            self.ev_copied = torch.cuda.Event()
+            self.ev_done = torch.cuda.Event()
+            self._used = False
         dt = torch.uint8 if host_input else torch.float32
         self.x_dev = torch.zeros(batch, 3, height, width, dtype=dt, device=self.dev)
         self.x_host = torch.zeros(batch, 3, height, width, dtype=torch.uint8).pin_memory() if host_input else None
@@ -32,7 +43,7 @@ class DetectPipeline:
         self._warm()
 
     def _body(self):
-        if self.host_input:
+        if self.host_input and not self.overlap_h2d:
             self.x_dev.copy_(self.x_host, non_blocking=True)
         pred = self.eng.forward(self.x_dev)
         out, count, src, overflow = nms_batched(pred, **self.kw)
@@ -56,6 +67,18 @@ class DetectPipeline:
 
     def launch(self):
         """Enqueue one batch (input already in `x_host` / `x_dev`); asynchronous."""
+        if self.overlap_h2d:
+            cur = torch.cuda.current_stream(self.dev)
+            if self._used:
+                self.copy_stream.wait_event(self.ev_done)      # the previous batch of THIS pipeline is done with x_dev
+            with torch.cuda.stream(self.copy_stream):
+                self.x_dev.copy_(self.x_host, non_blocking=True)
+                self.ev_copied.record(self.copy_stream)
+            cur.wait_event(self.ev_copied)
+            self.graph.replay()
+            self.ev_done.record(cur)
+            self._used = True
+            return
         self.graph.replay()
 
     def __call__(self, images=None):
@@ -63,7 +86,7 @@ class DetectPipeline:
         per-image [k,6] detections (host tensors when host_input) like `non_max_suppression`."""
         if images is not None:
             (self.x_host if self.host_input else self.x_dev).copy_(images)
-        self.graph.replay()
+        self.launch()
         torch.cuda.current_stream(self.dev).synchronize()
         if self.host_input:
             counts = self.count_host.tolist()
@@ -72,3 +95,37 @@ class DetectPipeline:
             return [self.out_host[i, :counts[i]].clone() for i in range(self.out_host.shape[0])]
         counts = self.count_dev.tolist()
         return [self.out_dev[i, :counts[i]] for i in range(self.out_dev.shape[0])]
+
+
+class DetectRing:
+    """Two `DetectPipeline`s used alternately with one shared copy stream: `submit(images)` enqueues a batch and
+    returns immediately, `collect()` returns the detections of the oldest batch in flight.  The H2D copy of a
+    batch overlaps the kernels of the batch before it (the reference's Inferer is strictly serial,
+    core/inferer.py:70-82)."""
+
+    def __init__(self, model, batch, height, width, depth=2, **kw):
+        dev = next(model.parameters()).device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.pipes = [DetectPipeline(model, batch, height, width, host_input=True, overlap_h2d=True,
+                                     copy_stream=self.copy_stream, **kw) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.head = self.tail = 0          # submitted / collected counters
+
+    def submit(self, images):
+        assert self.head - self.tail < len(self.pipes), "collect() a batch before submitting another"
+        p = self.pipes[self.head % len(self.pipes)]
+        p.x_host.copy_(images)
+        p.launch()
+        self.done[self.head % len(self.pipes)].record(torch.cuda.current_stream(p.dev))
+        self.head += 1
+
+    def collect(self):
+        assert self.tail < self.head, "nothing in flight"
+        i = self.tail % len(self.pipes)
+        self.done[i].synchronize()
+        p = self.pipes[i]
+        counts = p.count_host.tolist()
+        self.tail += 1
+        if counts[-1]:
+            raise RuntimeError("non_max_suppression: candidate overflow (> 65536 per image); raise conf_thres")
+        return [p.out_host[j, :counts[j]].clone() for j in range(p.out_host.shape[0])]
