@@ -61,10 +61,20 @@ __global__ void __launch_bounds__(kTrThreads) bn_stats_kernel(View x, int64_t pi
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
   }
+  // block-level reduction in shared memory first: one global atomic per channel per block instead of one per
+  // thread (the per-thread version serialised on C addresses and cost 56 % of a training step)
+  extern __shared__ double sred[];                      // [2][C]
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sred[c] = 0.0;
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sum[cg * 8 + j], (double)s[j]);
-    atomicAdd(&sumsq[cg * 8 + j], (double)q[j]);
+    atomicAdd(&sred[cg * 8 + j], (double)s[j]);
+    atomicAdd(&sred[C + cg * 8 + j], (double)q[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&sum[c], sred[c]);
+    atomicAdd(&sumsq[c], sred[C + c]);
   }
 }
 
@@ -214,10 +224,18 @@ __global__ void __launch_bounds__(kTrThreads) bn_bwd_reduce_kernel(const BwdPara
       for (int j = 0; j < 8; ++j) a2[b][j] += dz[j] * (v[j] - p.mean[b][cg * 8 + j]) * p.invstd[b][cg * 8 + j];
     }
   }
+  extern __shared__ double sred[];                      // [1 + nb][C]: block-level sums before the global atomics
+  for (int c = threadIdx.x; c < (1 + p.nb) * p.C; c += blockDim.x) sred[c] = 0.0;
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&p.s1[cg * 8 + j], (double)a1[j]);
-    for (int b = 0; b < p.nb; ++b) atomicAdd(&p.s2[b][cg * 8 + j], (double)a2[b][j]);
+    atomicAdd(&sred[cg * 8 + j], (double)a1[j]);
+    for (int b = 0; b < p.nb; ++b) atomicAdd(&sred[(1 + b) * p.C + cg * 8 + j], (double)a2[b][j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    atomicAdd(&p.s1[c], sred[c]);
+    for (int b = 0; b < p.nb; ++b) atomicAdd(&p.s2[b][c], sred[(1 + b) * p.C + c]);
   }
   if (p.dalpha != nullptr) {
 #pragma unroll
@@ -374,7 +392,7 @@ extern "C" int yv6_bn_stats(yv6_handle* h, const void* x, int64_t pixels, int32_
   YV6_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * C, s));
   YV6_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * C, s));
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((pixels + rows - 1) / rows, (int64_t)h->num_sms * 8));
-  bn_stats_kernel<<<grid, threads, 0, s>>>(View{reinterpret_cast<const __nv_bfloat16*>(x), pitch}, pixels, C, sum, sumsq);
+  bn_stats_kernel<<<grid, threads, sizeof(double) * 2 * C, s>>>(View{reinterpret_cast<const __nv_bfloat16*>(x), pitch}, pixels, C, sum, sumsq);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }
@@ -434,7 +452,13 @@ extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
   const int cgs = d->C / 8;
   const int rows = std::max(1, kTrThreads / cgs);
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((d->pixels + rows - 1) / rows, (int64_t)h->num_sms * 8));
-  bn_bwd_reduce_kernel<<<grid, cgs * rows, 0, s>>>(p);
+  const size_t red_smem = sizeof(double) * (1 + d->nb) * d->C;
+  static bool configured = false;
+  if (!configured) {
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * (int)sizeof(double)));
+    configured = true;
+  }
+  bn_bwd_reduce_kernel<<<grid, cgs * rows, red_smem, s>>>(p);
   bn_bwd_apply_kernel<<<grid_for(d->pixels * cgs, kTrThreads, h->num_sms), kTrThreads, 0, s>>>(p);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
