@@ -333,3 +333,34 @@ def test_training_steps_follow_the_oracle_trajectory(epoch):
         assert rel < (2e-3 if step < 3 else 2e-2)
         for a, b in zip(items, ref["items"]):
             assert abs(float(a) - b) < (2e-3 if step < 3 else 5e-2) * max(1.0, abs(b))
+
+
+def test_running_statistics_follow_the_reference_update():
+    """After one train-mode forward the BatchNorm running statistics equal what the reference model holds after the
+    same forward (momentum 0.03, unbiased variance; torch_utils.py:38-48, golden from tests/golden/make_golden_train.py)."""
+    from conftest import golden_npz
+    from yolov6_b200.model import build_model
+    g = golden_npz("train_yolov6n.npz")
+    dev = torch.device("cuda:0")
+    sd = fab.fabricate_state_dict(golden_keys("yolov6n"), seed=0)
+    for k in sd:
+        if (".cls_preds." in k or ".reg_preds." in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+    m = build_model("yolov6n", 80, dev)
+    m.load_state_dict(sd)
+    m.train()
+    x = fab.synthetic_images(4, 64, 64, seed=7)
+    with torch.no_grad():
+        (feats, cls, reg), _ = m(x.to(dev))
+    bn = str(g["bn_name"])
+    bufs = dict(m.named_buffers())
+    rm, rv = bufs[bn + ".running_mean"].cpu().double().numpy(), bufs[bn + ".running_var"].cpu().double().numpy()
+    old_m, old_v = sd[bn + ".running_mean"].double().numpy(), sd[bn + ".running_var"].double().numpy()
+    # compare the UPDATE (new - 0.97 * old = 0.03 * batch statistic), which is what the kernels compute in bf16 / fp32
+    upd_m, ref_m = rm - 0.97 * old_m, g["running_mean"] - 0.97 * old_m
+    upd_v, ref_v = rv - 0.97 * old_v, g["running_var"] - 0.97 * old_v
+    assert np.abs(upd_m - ref_m).max() <= 2e-2 * np.abs(ref_m).max()
+    assert np.abs(upd_v - ref_v).max() <= 2e-2 * np.abs(ref_v).max()
+    assert int(bufs[bn + ".num_batches_tracked"]) == int(sd[bn + ".num_batches_tracked"]) + 1
+    # head outputs of the same forward against the reference's (bf16 kernels vs float64: RMS bar, see the test above)
+    assert float(np.sqrt(np.mean((cls.cpu().double().numpy() - g["cls"]) ** 2))) < 2e-2

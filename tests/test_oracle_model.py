@@ -52,3 +52,41 @@ def test_config_scaling_matches_reference_shapes():
                     else "backbone.stem.block.conv.weight"][0] == chans[0]
         assert keys["detect.cls_preds.0.weight"][0] == 80
         assert keys["detect.reg_preds.0.weight"][0] == 4 * (om.CONFIGS[name]["reg_max"] + 1)
+
+
+@pytest.mark.parametrize("name,batch,size", [("yolov6n", 4, 64), ("yolov6m", 2, 64)])
+def test_oracle_train_mode_matches_reference(name, batch, size):
+    """Train mode (batch-statistics BatchNorm, train branch of Detect, BottleRep alpha) of oracle/model.py against
+    the reference model run in .train() mode in float64 (tests/golden/make_golden_train.py): head outputs, the
+    scalar L = sum(cls*wc) + sum(reg*wr), the gradient norm of EVERY parameter and selected full gradients."""
+    g = golden_npz(f"train_{name}.npz")
+    keys = golden_keys(name)
+    sd = fab.fabricate_state_dict(keys, seed=0)
+    for k in sd:
+        if (".cls_preds." in k or ".reg_preds." in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+        if k.endswith(".alpha"):
+            sd[k] = sd[k] * 0.75
+    x = fab.synthetic_images(batch, size, size, seed=7)
+    assert abs(fab.checksum(x) - float(g["x_checksum"])) < 1e-6 * abs(float(g["x_checksum"])), "input RNG drift"
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    with om.train_mode():
+        cls, reg, _ = om.forward(sd64, om.CONFIGS[name], x.double(), train_outputs=True)
+    assert rel_err(cls.detach().numpy(), g["cls"]) < 1e-9
+    assert rel_err(reg.detach().numpy(), g["reg"]) < 1e-9
+    gen = torch.Generator().manual_seed(11)
+    wc = torch.randn(cls.shape, generator=gen).double()
+    wr = torch.randn(reg.shape, generator=gen).double()
+    L = (cls * wc).sum() + (reg * wr).sum()
+    assert abs(L.item() - float(g["L"])) < 1e-8 * max(1.0, abs(float(g["L"])))
+    L.backward()
+    names, norms = [str(n) for n in g["grad_names"]], g["grad_norms"]
+    assert len(names) > 300
+    for n, ref in zip(names, norms):
+        assert sd64[n].grad is not None, n
+        got = float(sd64[n].grad.norm())
+        assert abs(got - ref) <= 1e-7 * max(1.0, ref), (n, got, ref)
+    for k in g.files:
+        if k.startswith("grad::"):
+            n = k[6:]
+            np.testing.assert_allclose(sd64[n].grad.numpy().reshape(g[k].shape), g[k], rtol=1e-7, atol=1e-9 * (1 + np.abs(g[k]).max()))
