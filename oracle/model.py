@@ -12,7 +12,10 @@ itself under test.  Each function cites the reference code it follows.
 
 Pinning: `tests/golden/make_golden.py` imports the unmodified reference from /root/reference,
 runs it on seeded inputs and stores small fixtures; `tests/test_oracle_model.py` checks this file
-against them (logits, decoded boxes, per-stage feature statistics).
+against them (logits, decoded boxes, per-stage feature statistics).  The train mode (`train_mode()`:
+batch-statistics BatchNorm, train branch of Detect, BottleRep alpha) is pinned the same way by
+`tests/golden/make_golden_train.py`: head outputs, a scalar loss and the gradient of every parameter of
+YOLOv6-N and -M against the reference model in `.train()` mode in float64 (agreement 1e-9 / 1e-7).
 """
 import math
 
