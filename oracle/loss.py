@@ -163,6 +163,16 @@ def compute_loss(sizes, pred_scores, pred_distri, targets, *, strides, num_class
     return loss, items
 
 
+def drop_targets(targets, drop):
+    """Golden-case helper (12th field of tests/golden/loss_cases.json): remove the boxes of image 1 ("img1") or of
+    every image ("all") -- the ragged / empty inputs of ComputeLoss.preprocess (loss.py:184-192)."""
+    if drop == "img1":
+        return targets[targets[:, 0] != 1]
+    if drop == "all":
+        return targets[:0]
+    return targets
+
+
 def synthetic_targets(batch, seed=1, mean_per_image=7.3, num_classes=80):
     """COCO-shaped synthetic labels (SURVEY.md section 8d config 3): per image n ~ clip(Poisson(7.3), 1, 60);
     cls ~ U{0..nc-1}; w,h ~ U(.02,.6); centres uniform such that the box stays inside.  [n,6] fp32."""

@@ -53,7 +53,20 @@ LOSS_CASES = [  # (name, nc, strides, img, use_dfl, reg_max, iou_type, warmup_ep
     ("m_tal_dfl", 80, [8, 16, 32], 320, True, 16, "giou", 0, 0, 4, 2),
     ("l6_atss_dfl", 20, [8, 16, 32, 64], 512, True, 16, "giou", 4, 0, 2, 3),
     ("l6_tal_dfl", 20, [8, 16, 32, 64], 512, True, 16, "giou", 4, 5, 2, 3),
+    # ragged / empty targets (12th field: which images lose their boxes)
+    ("s_tal_one_empty_image", 80, [8, 16, 32], 320, False, 0, "giou", 0, 0, 4, 5, "img1"),
+    ("s_tal_no_targets", 80, [8, 16, 32], 320, False, 0, "giou", 0, 0, 2, 6, "all"),
+    ("l6_atss_one_empty_image", 20, [8, 16, 32, 64], 512, True, 16, "giou", 4, 0, 2, 7, "img1"),
 ]
+
+
+def drop_targets(targets, drop):
+    """Test-case helper: remove the boxes of image 1 ("img1") or of every image ("all")."""
+    if drop == "img1":
+        return targets[targets[:, 0] != 1]
+    if drop == "all":
+        return targets[:0]
+    return targets
 
 
 def load_cfg(name):
@@ -107,12 +120,13 @@ def golden_nms():
 
 def golden_loss():
     store = {}
-    for (name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed) in LOSS_CASES:
+    for case in LOSS_CASES:
+        (name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed), drop = case[:11], (case[11] if len(case) > 11 else None)
         sizes = [(img // s, img // s) for s in strides]
         ps, pd = fab.synthetic_head_outputs(B, sizes, nc, 4 * (reg_max + 1), seed)
         ps.requires_grad_(True)
         pd.requires_grad_(True)
-        targets = oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc)
+        targets = drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc), drop)
         feats = [torch.zeros(B, 8, h, w) for h, w in sizes]
         cl = ComputeLoss(fpn_strides=strides, num_classes=nc, ori_img_size=img, warmup_epoch=warm, use_dfl=use_dfl,
                          reg_max=reg_max, iou_type=iou_type)
@@ -130,6 +144,7 @@ def golden_loss():
         loss, items = cl((feats, ps, pd), targets.clone(), epoch, 1, img, img)
         g_ps, g_pd = torch.autograd.grad(loss, [ps, pd], allow_unused=True)
         tl, tb, ts, fg = captured["out"]
+        fg = fg.bool()      # the no-target early return of the assigners yields a float zero mask (tal_assigner.py:41-46)
         nz = ts.nonzero()
         store[f"{name}_loss"] = np.float64(loss.item())
         store[f"{name}_items"] = items.double().numpy()
@@ -154,7 +169,8 @@ def golden_loss():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    golden_models()
-    golden_nms()
+    if "--loss-only" not in sys.argv:
+        golden_models()
+        golden_nms()
     golden_loss()
     print("golden vectors written to", HERE)

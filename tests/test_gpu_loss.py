@@ -15,21 +15,30 @@ from oracle import fabricate as fab
 from oracle import loss as oloss
 
 pytestmark = pytest.mark.gpu
-CASES = golden_json("loss_cases.json")
+ALL_CASES = golden_json("loss_cases.json")
+CASES = [c for c in ALL_CASES if len(c) == 11]
+RAGGED_CASES = [c for c in ALL_CASES if len(c) > 11]      # images without boxes / no boxes at all (12th field)
 
 
 def make_inputs(case):
-    name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed = case
+    name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed = case[:11]
     sizes = [(img // s, img // s) for s in strides]
     ps, pd = fab.synthetic_head_outputs(B, sizes, nc, 4 * (reg_max + 1), seed)
-    targets = oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc), case[11] if len(case) > 11 else None)
     return sizes, ps, pd, targets
+
+
+@pytest.mark.parametrize("case", RAGGED_CASES, ids=[c[0] for c in RAGGED_CASES])
+def test_compute_loss_ragged_and_empty_targets(case):
+    """ComputeLoss.preprocess pads ragged targets with [-1,0,0,0,0] rows and survives a batch without any box
+    (loss.py:184-192, tal_assigner.py:41-46): same goldens, same bars as the dense cases."""
+    test_compute_loss_matches_reference_golden(case)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_compute_loss_matches_reference_golden(case):
     from yolov6_b200.loss import ComputeLoss
-    name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed = case
+    name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed = case[:11]
     g = golden_npz("loss.npz")
     sizes, ps, pd, targets = make_inputs(case)
     dev = torch.device("cuda:0")

@@ -13,11 +13,11 @@ CASES = golden_json("loss_cases.json")
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_loss_and_assignment_match_reference(case):
-    name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed = case
+    name, nc, strides, img, use_dfl, reg_max, iou_type, warm, epoch, B, seed = case[:11]
     g = golden_npz("loss.npz")
     sizes = [(img // s, img // s) for s in strides]
     ps, pd = fab.synthetic_head_outputs(B, sizes, nc, 4 * (reg_max + 1), seed)
-    targets = oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc), case[11] if len(case) > 11 else None)
     chk = fab.checksum(ps) + fab.checksum(pd) + fab.checksum(targets)
     assert abs(chk - float(g[f"{name}_in_checksum"])) <= 1e-9 * abs(chk), "RNG drift"
     ps.requires_grad_(True)
@@ -34,15 +34,20 @@ def test_loss_and_assignment_match_reference(case):
     assert np.array_equal(asg["labels"].numpy(), ref_labels_bg)
     nz = asg["scores"].nonzero().numpy().astype(np.int32)
     assert np.array_equal(nz, g[f"{name}_scores_idx"])
-    # float outputs: same fp64 math -> tight
+    # float outputs: same fp64 math -> tight.  During the ATSS warm-up epochs the reference itself computes the soft labels
+    # and hence the three loss sums in float32 (atss_assigner.py:86-92: `target_scores *= ious` in place), so those cases carry
+    # float32 summation-order noise (the result depends on torch's CPU thread partitioning): 2e-6 instead of 1e-10.
+    tol = 2e-6 if epoch < warm else 1e-10
     np.testing.assert_allclose(asg["scores"][asg["scores"] != 0].double().numpy(), g[f"{name}_scores_val"], rtol=1e-12, atol=0)
-    assert abs(loss.item() - float(g[f"{name}_loss"])) <= 1e-10 * abs(loss.item())
-    np.testing.assert_allclose(items.double().numpy(), g[f"{name}_items"], rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(g_ps[asg["fg"]].double().numpy(), g[f"{name}_grad_scores_fg"], rtol=1e-9, atol=1e-12)
-    np.testing.assert_allclose(g_ps.flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=1e-9, atol=1e-12)
-    assert abs(g_ps.double().abs().sum().item() - float(g[f"{name}_grad_scores_abs"])) <= 1e-9 * float(g[f"{name}_grad_scores_abs"])
+    assert abs(loss.item() - float(g[f"{name}_loss"])) <= tol * abs(loss.item())
+    np.testing.assert_allclose(items.double().numpy(), g[f"{name}_items"], rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(g_ps[asg["fg"]].double().numpy(), g[f"{name}_grad_scores_fg"], rtol=max(1e-9, 10 * tol), atol=1e-12)
+    np.testing.assert_allclose(g_ps.flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=max(1e-9, 10 * tol), atol=1e-12)
+    assert abs(g_ps.double().abs().sum().item() - float(g[f"{name}_grad_scores_abs"])) <= max(1e-9, 10 * tol) * float(g[f"{name}_grad_scores_abs"])
     if g_pd is not None and f"{name}_grad_distri_fg" in g:
-        np.testing.assert_allclose(g_pd[asg["fg"]].double().numpy(), g[f"{name}_grad_distri_fg"], rtol=1e-9, atol=1e-12)
+        ref_gd = g[f"{name}_grad_distri_fg"]
+        np.testing.assert_allclose(g_pd[asg["fg"]].double().numpy(), ref_gd, rtol=max(1e-9, 10 * tol),
+                                   atol=1e-12 if tol < 1e-9 else 1e-6 * np.abs(ref_gd).max())
 
 
 def test_preprocess_pads_and_scales():
