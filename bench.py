@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
