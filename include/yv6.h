@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YV6_ABI_VERSION 1
+#define YV6_ABI_VERSION 2
 
 enum {
   YV6_OK = 0,
@@ -273,8 +273,33 @@ typedef struct yv6_bn_desc {
    * res_alpha * dy into dres and writes sum(dy * res) to dalpha[0] */
   const void* res; int64_t res_pitch; float res_alpha;
   void* dres; int64_t dres_pitch; double* dalpha;
+  /* ABI 2 */
+  const float* res_alpha_dev;                           /* when set, the shortcut weight is read from this device scalar (no
+                                                           host synchronisation, graph-capturable) instead of res_alpha      */
+  /* scratch of the two-pass backward (optional; the handle's scratch is used when work == NULL): work [nb][C] float64,
+   * counter one uint32, coef [nb][2][C] fp32.  zeroed != 0: the caller already zeroed s1, work, counter and dalpha
+   * (the training engine clears one arena per step instead of four memsets per block). */
+  double* work; uint32_t* counter; float* coef; int32_t zeroed;
 } yv6_bn_desc;
 int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);
+
+/* Batch statistics of up to three branch inputs and their finalisation in ONE launch: per-channel sum / sum of squares
+ * (float64 atomics of block-level partial sums), then -- in the thread block that finishes last -- mean, invstd,
+ * scale = gamma*invstd, shift = beta - mean*scale and the running-statistics update of nn.BatchNorm2d for every branch
+ * (ConvModule / RepVGGBlock in train mode, layers/common.py:46-49,245-255; eps / momentum of torch_utils.py:38-48). */
+typedef struct yv6_bn_stats_desc {
+  int32_t nb, C;
+  int64_t pixels;
+  const void* x[3]; int64_t x_pitch[3];                 /* bf16 NHWC slices                                              */
+  double* sums;                                         /* [nb][2][C] sum, sumsq                                          */
+  uint32_t* counter;                                    /* one uint32                                                     */
+  int32_t zeroed;                                       /* != 0: sums and counter are already zero                        */
+  const float* gamma[3]; const float* beta[3];
+  float* running_mean[3]; float* running_var[3];        /* may be NULL                                                    */
+  float* stats[3];                                      /* out [4][C]: mean, invstd, scale, shift; NULL = sums only       */
+  float eps, momentum;
+} yv6_bn_stats_desc;
+int yv6_bn_stats_finalize(yv6_handle* h, const yv6_bn_stats_desc* d, void* stream);
 int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);
 
 /* Head gradients: level slice [off, off+hw) of the [B,A,ch] fp32 tensors -> dense NHWC bf16 [B,hw,ch_pad];
@@ -288,6 +313,38 @@ int yv6_maxpool5_bwd(yv6_handle* h, const void* x, int64_t x_pitch, const void* 
 /* Weight gradient of the 3-channel stem conv (3x3 stride 2): dw fp32 [Cout][3][3][3] (overwritten). */
 int yv6_stem_wgrad(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy, int64_t dy_pitch,
                    int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw, void* stream);
+
+/* Both stem branches of a RepVGG stem in one pass over the image: dw3 fp32 [Cout][3][3][3] from dy3 and (optional) dw1 fp32
+ * [Cout][3] (the 1x1 stride-2 branch = centre tap) from dy1; ACCUMULATED into (zeroed != 0: the caller cleared them). */
+int yv6_stem_wgrad2(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy3, int64_t dy3_pitch,
+                    const void* dy1, int64_t dy1_pitch, int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw3, float* dw1,
+                    int32_t zeroed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step-level plumbing of the training engine: everything that the reference does with
+ * hundreds of small eager ops per step -- autocast weight casts, layout permutes, `.grad` accumulation,
+ * torch.optim.SGD (solver/build.py:10-33) and ModelEMA.update (utils/ema.py:28-37) -- as three launches.
+ * ---------------------------------------------------------------------------------------------- */
+#define YV6_XFORM_CHUNK 4096
+enum { YV6_XF_F32 = 0, YV6_XF_F64 = 1, YV6_XF_BF16 = 2 };
+/* dst[d0*ds0 + d1*ds1 + d2*ds2 + d3*ds3] (+)= cast(src[d0*ss0 + d1*ss1 + d2*ss2 + d3*ss3]) for d in n[0] x n[1] x n[2] x n[3];
+ * strides in elements, source strides may be negative (filter rotation for dgrad).  src: fp32 or float64; dst: bf16 or fp32. */
+typedef struct yv6_xform_seg {
+  void* dst; const void* src;
+  int32_t n[4], ds[4], ss[4];
+  int32_t dst_dtype, src_dtype;
+} yv6_xform_seg;
+/* segs / chunk tables live in DEVICE memory: chunk c of the launch works on segment chunk_seg[c], elements
+ * [(c - chunk_first[seg]) * YV6_XFORM_CHUNK, +YV6_XFORM_CHUNK).  accumulate applies to fp32 destinations. */
+int yv6_xform(yv6_handle* h, const yv6_xform_seg* segs_dev, const int32_t* chunk_seg_dev, const int32_t* chunk_first_dev,
+              int32_t n_chunks, int32_t accumulate, void* stream);
+
+/* SGD(momentum, nesterov) + weight decay + EMA over flat fp32 buffers of n elements (n % 4 == 0).  group_per4[i] is the
+ * parameter group of elements 4i..4i+3: 0 = BN weights, 1 = conv weights (weight decay), 2 = biases, 3 = float buffers
+ * (EMA only), 255 = padding.  hyper (device, 8 floats): lr[0..2], momentum, weight_decay, ema_decay, first_step, grad_scale.
+ * ema_or_null == NULL skips the EMA update. */
+int yv6_sgd_ema_step(yv6_handle* h, float* param, const float* grad, float* momentum_buf, float* ema_or_null,
+                     const uint8_t* group_per4, int64_t n, const float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/yv6.h but not exported"
     assert set(_lib.exported_symbols()) <= set(names)
-    assert lib.yv6_abi_version() == 1
+    assert lib.yv6_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -60,11 +60,13 @@ def test_ctypes_mirrors_match_the_header_struct_sizes(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "yv6.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(yv6_conv_desc), '
-                   'sizeof(yv6_stem_desc), sizeof(yv6_loss_desc), sizeof(yv6_wgrad_desc), sizeof(yv6_bn_desc));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "yv6.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(yv6_conv_desc), '
+                   'sizeof(yv6_stem_desc), sizeof(yv6_loss_desc), sizeof(yv6_wgrad_desc), sizeof(yv6_bn_desc), '
+                   'sizeof(yv6_bn_stats_desc), sizeof(yv6_xform_seg));return 0;}\n')
     exe = tmp_path / "sz"
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    want = [C.sizeof(_lib.ConvDesc), C.sizeof(_lib.StemDesc), C.sizeof(_lib.LossDesc), C.sizeof(_lib.WgradDesc), C.sizeof(_lib.BnDesc)]
+    want = [C.sizeof(_lib.ConvDesc), C.sizeof(_lib.StemDesc), C.sizeof(_lib.LossDesc), C.sizeof(_lib.WgradDesc), C.sizeof(_lib.BnDesc),
+            C.sizeof(_lib.BnStatsDesc), C.sizeof(_lib.XformSeg)]
     assert got == want, (got, want)

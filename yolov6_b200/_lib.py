@@ -84,7 +84,35 @@ class BnDesc(C.Structure):
         ("dx", C.c_void_p * 3), ("dx_pitch", C.c_int64 * 3), ("accumulate", C.c_int32 * 3),
         ("res", C.c_void_p), ("res_pitch", C.c_int64), ("res_alpha", C.c_float),
         ("dres", C.c_void_p), ("dres_pitch", C.c_int64), ("dalpha", C.c_void_p),
+        ("res_alpha_dev", C.c_void_p),
+        ("work", C.c_void_p), ("counter", C.c_void_p), ("coef", C.c_void_p), ("zeroed", C.c_int32),
     ]
+
+
+class BnStatsDesc(C.Structure):
+    """Mirror of `yv6_bn_stats_desc` (include/yv6.h)."""
+    _fields_ = [
+        ("nb", C.c_int32), ("C", C.c_int32), ("pixels", C.c_int64),
+        ("x", C.c_void_p * 3), ("x_pitch", C.c_int64 * 3),
+        ("sums", C.c_void_p), ("counter", C.c_void_p), ("zeroed", C.c_int32),
+        ("gamma", C.c_void_p * 3), ("beta", C.c_void_p * 3),
+        ("running_mean", C.c_void_p * 3), ("running_var", C.c_void_p * 3),
+        ("stats", C.c_void_p * 3),
+        ("eps", C.c_float), ("momentum", C.c_float),
+    ]
+
+
+class XformSeg(C.Structure):
+    """Mirror of `yv6_xform_seg` (include/yv6.h)."""
+    _fields_ = [
+        ("dst", C.c_void_p), ("src", C.c_void_p),
+        ("n", C.c_int32 * 4), ("ds", C.c_int32 * 4), ("ss", C.c_int32 * 4),
+        ("dst_dtype", C.c_int32), ("src_dtype", C.c_int32),
+    ]
+
+
+XF_F32, XF_F64, XF_BF16 = 0, 1, 2
+XFORM_CHUNK = 4096
 
 
 _lib = None
@@ -132,6 +160,12 @@ _SIGNATURES = {
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "yv6_stem_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "yv6_bn_stats_finalize": (C.c_int, [C.c_void_p, C.POINTER(BnStatsDesc), C.c_void_p]),
+    "yv6_stem_wgrad2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "yv6_xform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "yv6_sgd_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p]),
     "yv6_nms_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "yv6_nms_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -23,6 +23,12 @@ extern "C" int yv6_create(int device, yv6_handle** out) {
   int count = 0;
   YV6_CHECK_CUDA(cudaGetDeviceCount(&count));
   YV6_REQUIRE(device >= 0 && device < count, "yv6_create: device %d out of range (%d visible)", device, count);
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);
+  struct Restore {           // the caller's current device is left as it was (torch keeps its own notion of it)
+    int d;
+    ~Restore() { if (d >= 0) cudaSetDevice(d); }
+  } restore{prev_device};
   YV6_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   YV6_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -420,6 +420,7 @@ using namespace yv6;
 
 extern "C" int yv6_targets_pad(yv6_handle* h, const float* targets, int32_t n, int32_t B, int32_t G, float scale_w,
                                float scale_h, double* gt, int32_t* gt_count, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && gt && gt_count && (targets || n == 0), "targets_pad: null argument");
   YV6_REQUIRE(B > 0 && G >= 0 && n >= 0, "targets_pad: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
@@ -439,6 +440,7 @@ extern "C" int yv6_tal_assign(yv6_handle* h, const float* pd_scores, const float
                               const double* gt, const uint8_t* mask_gt, int32_t B, int32_t A, int32_t G, int32_t nc,
                               int32_t topk, double alpha, double beta, double eps, int32_t* gt_idx, uint8_t* fg,
                               double* norm, void* workspace, int64_t workspace_bytes, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && pd_scores && pd_bboxes && anc_points && gt_idx && fg && norm && workspace, "tal: null argument");
   YV6_REQUIRE(B > 0 && A > 0 && nc > 0 && G >= 0, "tal: bad sizes");
   YV6_REQUIRE(topk >= 1 && topk <= kTopkMax, "tal: topk=%d out of range (1..%d)", topk, kTopkMax);
@@ -476,6 +478,7 @@ extern "C" int yv6_atss_assign(yv6_handle* h, const float* anc_bboxes, const int
                                const double* gt, const uint8_t* mask_gt, const float* pd_bboxes, int32_t B, int32_t A,
                                int32_t G, int32_t nc, int32_t topk, int32_t* gt_idx, uint8_t* fg, double* norm,
                                void* workspace, int64_t workspace_bytes, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && anc_bboxes && n_level_bboxes && gt_idx && fg && norm && workspace, "atss: null argument");
   YV6_REQUIRE(nl >= 1 && nl <= kAtssMaxLevels, "atss: nl=%d out of range", nl);
   YV6_REQUIRE(topk >= 1 && topk <= kAtssTopkMax, "atss: topk=%d out of range (1..%d)", topk, kAtssTopkMax);
@@ -509,6 +512,7 @@ extern "C" int yv6_atss_assign(yv6_handle* h, const float* anc_bboxes, const int
 extern "C" int yv6_assign_expand(yv6_handle* h, const double* gt, const int32_t* gt_idx, const uint8_t* fg,
                                  const double* norm, int32_t B, int32_t A, int32_t G, int32_t nc, int32_t bg_label,
                                  int64_t* labels, double* bboxes, double* scores, uint8_t* fg_out, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && gt && gt_idx && fg && norm && labels && bboxes && scores && fg_out, "assign_expand: null argument");
   YV6_REQUIRE(G > 0, "assign_expand: needs at least one gt row");
   cudaStream_t s = (cudaStream_t)stream;

@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
 using namespace yv6;
 
 extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && d && d->x && d->w && d->y, "stem: null argument");
   YV6_REQUIRE(d->Cout > 0 && d->Cout <= kStemMaxCout && d->Cout % 16 == 0, "stem: Cout=%d must be 16/32/48/64", d->Cout);
   YV6_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "stem: nsplit must be 1 or 3");
@@ -494,6 +495,7 @@ extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream)
 
 extern "C" int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int32_t W, int32_t C, int32_t c_total,
                              int32_t nsplit, int64_t plane_stride, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && buf, "sppf_pool: null argument");
   YV6_REQUIRE(C % 8 == 0 && c_total >= 4 * C && c_total % 8 == 0, "sppf_pool: bad channels C=%d c_total=%d", C, c_total);
   const size_t smem = (size_t)4 * H * W * 8 * sizeof(float);
@@ -512,6 +514,7 @@ extern "C" int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int
 extern "C" int yv6_head_decode(yv6_handle* h, const float* cls, const float* reg, float* out, int32_t B, int32_t nc,
                                int32_t reg_ch, int32_t nl, const int32_t* lvl_h, const int32_t* lvl_w,
                                const float* lvl_stride, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && cls && reg && out && lvl_h && lvl_w && lvl_stride, "head_decode: null argument");
   YV6_REQUIRE(nl >= 1 && nl <= kMaxLevels, "head_decode: nl=%d out of range", nl);
   YV6_REQUIRE(reg_ch == 4 || reg_ch % 4 == 0, "head_decode: reg_ch=%d", reg_ch);

@@ -999,6 +999,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
 using namespace yv6;
 
 extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out8) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h != nullptr && out8 != nullptr, "conv_plan: null argument");
   ConvPlan plan;
   int rc = plan_conv(h, d, &plan);
@@ -1017,6 +1018,7 @@ extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out
 }
 
 extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h != nullptr, "conv_fwd: null handle");
   ConvPlan plan;
   int rc = plan_conv(h, d, &plan);
@@ -1101,12 +1103,11 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
   static const KernelFn kernels[2][3] = {
       {conv_igemm_kernel<2, 0>, conv_igemm_kernel<2, 1>, conv_igemm_kernel<2, 2>},
       {conv_igemm_kernel<4, 0>, conv_igemm_kernel<4, 1>, conv_igemm_kernel<4, 2>}};
-  static bool configured = false;
-  if (!configured) {
+  if (!(h->configured & YV6_CFG_CONV)) {
     for (int g = 0; g < 2; ++g)
       for (int m = 0; m < 3; ++m)
         YV6_CHECK_CUDA(cudaFuncSetAttribute(kernels[g][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
-    configured = true;
+    h->configured |= YV6_CFG_CONV;
   }
   const int mode = k.halo ? (k.b_resident ? 2 : 1) : 0;
   kernels[k.groups == 4 ? 1 : 0][mode]<<<plan.grid, 64 + 128 * k.groups, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);

@@ -170,6 +170,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 using namespace yv6;
 
 extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && d && d->x && d->dy && d->dw, "wgrad: null argument");
   YV6_REQUIRE(h->encode_tiled != nullptr, "wgrad: cuTensorMapEncodeTiled unavailable");
   YV6_REQUIRE(d->Cin > 0 && d->Cin % 16 == 0 && d->x_c_total % 8 == 0 && d->dy_c_total % 8 == 0, "wgrad: channel counts");
@@ -238,10 +239,9 @@ extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stre
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { yv6_set_error("wgrad: cuTensorMapEncodeTiled(X) failed with %d", (int)cr); return YV6_ERR_CUDA; }
   }
-  static bool configured = false;
-  if (!configured) {
+  if (!(h->configured & YV6_CFG_WGRAD)) {
     YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
-    configured = true;
+    h->configured |= YV6_CFG_WGRAD;
   }
   const size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024 + 512;
   conv_wgrad_kernel<<<units, kWgThreads, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);

@@ -16,4 +16,22 @@ struct yv6_handle {
   yv6_encode_tiled_fn encode_tiled;  // resolved through cudaGetDriverEntryPoint (no -lcuda)
   void* scratch;                   // device scratch for kernels that need counters / partials
   size_t scratch_bytes;
+  unsigned configured;             // YV6_CFG_* bits: cudaFuncSetAttribute is per device, so the flags live in the handle
+};
+
+enum { YV6_CFG_CONV = 1u, YV6_CFG_WGRAD = 2u, YV6_CFG_NMS = 4u, YV6_CFG_BN = 8u, YV6_CFG_TRAIN2 = 16u };
+
+// Every entry point runs on the handle's device whatever the caller's current device is, and leaves the
+// caller's current device untouched (several handles / GPUs in one process, nn.DataParallel-style callers).
+struct yv6_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit yv6_device_guard(const yv6_handle* h) {
+    if (h != nullptr && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = (cudaSetDevice(h->device) == cudaSuccess);
+  }
+  ~yv6_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  yv6_device_guard(const yv6_device_guard&) = delete;
+  yv6_device_guard& operator=(const yv6_device_guard&) = delete;
 };

@@ -358,6 +358,7 @@ using namespace yv6;
 
 extern "C" int yv6_box_decode(yv6_handle* h, const float* pred_distri, const float* anc_points, const float* strides,
                               int32_t B, int32_t A, int32_t reg_ch, int32_t scale_to_pixels, float* boxes, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && pred_distri && anc_points && strides && boxes, "box_decode: null argument");
   YV6_REQUIRE(reg_ch == 4 || (reg_ch % 4 == 0 && reg_ch / 4 <= kMaxBins), "box_decode: reg_ch=%d", reg_ch);
   DecodeBoxParams p{pred_distri, anc_points, strides, boxes, B, A, reg_ch, reg_ch / 4 - 1, scale_to_pixels};
@@ -373,6 +374,7 @@ extern "C" int64_t yv6_det_loss_workspace_bytes(int32_t B, int32_t A) {
 }
 
 extern "C" int yv6_det_loss(yv6_handle* h, const yv6_loss_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && d, "det_loss: null argument");
   YV6_REQUIRE(d->pred_scores && d->pred_distri && d->anc_points && d->strides && d->gt_idx && d->fg && d->norm &&
                   d->grad_scores && d->grad_distri && d->out && d->workspace,

@@ -27,11 +27,14 @@ constexpr int kNmsTile = 256;       // anchors per block in scan/emit
 constexpr int kMaxNms = 30000;      // nms.py:55
 constexpr int kMultiCap = 65536;    // candidate capacity per image in multi-label mode
 constexpr int kSortSmemMax = 16384; // keys sorted in shared memory up to this many
+constexpr int kHistBins = 4096;     // overflow pre-selection: bins over bits [30:19] of the (positive) fp32 score
 
 struct NmsWs {
   int32_t* cand_count;   // [B] slots taken (may exceed cap; clamped by the consumers)
   int32_t* overflow;     // [1]
   uint64_t* keys;        // [B][cap2]
+  uint32_t* hist;        // [B][kHistBins] score histogram of the images that overflowed `cap` (null when cap covers A*nc)
+  int32_t* cutoff;       // [B] lowest histogram bin that still enters the sort, -1 = image did not overflow
   int32_t cap, cap2, T;
 };
 
@@ -203,6 +206,101 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
         slot[q] += __popc(m);
       }
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// More than `cap` multi-label candidates in one image (an under-trained model at the Evaler's conf 0.03):
+// the reference keeps the 30000 best by confidence (nms.py:90-91).  The three kernels below do nothing for
+// images that fit.  For an image that overflowed they (1) histogram the candidate scores over 4096 bins
+// that are monotone in the score, (2) find the lowest bin such that the bins from it upwards hold at least
+// max_nms candidates, (3) re-emit only the candidates of those bins.  The sort then orders them by the full
+// key, so the first 30000 are exactly the 30000 best under the stable order.  Only if the kept bins still
+// hold more than `cap` keys (tens of thousands of scores equal to 8 significant bits) is `overflow` raised.
+__device__ __forceinline__ int score_bin(float s) { return (int)((__float_as_uint(s) >> 19) & (kHistBins - 1)); }
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) nms_overflow_pass_kernel(const NmsParams p) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cut = 0;
+  if (EMIT) {
+    cut = p.ws.cutoff[b];
+    if (cut < 0) return;
+  } else if (p.ws.cand_count[b] <= p.ws.cap) {
+    return;
+  }
+  const int a = blockIdx.x * 8 + warp;
+  if (a >= p.A) return;
+  const float* row = p.pred + ((int64_t)b * p.A + a) * p.no;
+  const float obj = __ldg(row + 4);
+  float raw_max = -INFINITY;
+  for (int c = lane; c < p.nc; c += 32) raw_max = fmaxf(raw_max, __ldg(row + 5 + c));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) raw_max = fmaxf(raw_max, __shfl_xor_sync(0xffffffffu, raw_max, o));
+  if (!((obj > p.conf) && (raw_max > p.conf))) return;                    // nms.py:48
+  uint64_t* keys = p.ws.keys + (int64_t)b * p.ws.cap2;
+  uint32_t* hist = p.ws.hist + (int64_t)b * kHistBins;
+  for (int c0 = 0; c0 < p.nc; c0 += 32) {
+    const int c = c0 + lane;
+    const bool cls_ok = (c < p.nc) && ((p.class_mask == nullptr) || (p.class_mask[c] != 0));
+    const float sv = (c < p.nc) ? __fmul_rn(__ldg(row + 5 + c), obj) : 0.f;
+    const bool hit = cls_ok && (sv > p.conf);
+    if (!EMIT) {
+      if (hit) atomicAdd(&hist[score_bin(sv)], 1u);
+    } else {
+      const bool take = hit && (score_bin(sv) >= cut);
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m == 0u) continue;
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(&p.ws.cand_count[b], __popc(m));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (take) {
+        const int my = slot0 + __popc(m & ((1u << lane) - 1u));
+        if (my < p.ws.cap) keys[my] = make_key(sv, a * p.nc + c);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) nms_cutoff_kernel(const NmsParams p) {
+  __shared__ uint32_t part[1024];
+  __shared__ int s_cut;
+  const int b = blockIdx.x;
+  if (p.ws.cand_count[b] <= p.ws.cap) {
+    if (threadIdx.x == 0) p.ws.cutoff[b] = -1;
+    return;
+  }
+  constexpr int PER = kHistBins / 1024;
+  const uint32_t* hist = p.ws.hist + (int64_t)b * kHistBins;
+  uint32_t mine[PER], tot = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { mine[j] = hist[threadIdx.x * PER + j]; tot += mine[j]; }
+  part[threadIdx.x] = tot;
+  if (threadIdx.x == 0) s_cut = 0;
+  __syncthreads();
+  // suffix sums over threads (Hillis-Steele on 1024 entries)
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t add = (threadIdx.x + o < 1024) ? part[threadIdx.x + o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const uint32_t above = (threadIdx.x + 1 < 1024) ? part[threadIdx.x + 1] : 0u;   // candidates in higher bins than mine
+  if (above < (uint32_t)kMaxNms && part[threadIdx.x] >= (uint32_t)kMaxNms) {        // the crossing lies in my bins
+    uint32_t acc = above;
+    int cut = threadIdx.x * PER;
+    for (int j = PER - 1; j >= 0; --j) {
+      acc += mine[j];
+      if (acc >= (uint32_t)kMaxNms) { cut = threadIdx.x * PER + j; break; }
+    }
+    s_cut = cut;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.ws.cutoff[b] = s_cut;
+    p.ws.cand_count[b] = 0;            // the kept bins are re-emitted from scratch
   }
 }
 
@@ -398,6 +496,9 @@ static void nms_layout(int32_t B, int32_t A, int32_t nc, int32_t multi_label, Nm
   ws->cand_count = (int32_t*)take((int64_t)B * 4);
   ws->overflow = (int32_t*)take(4);
   ws->keys = (uint64_t*)take((int64_t)B * cap2 * 8);
+  const bool can_overflow = multi_label && (int64_t)A * nc > cap;
+  ws->hist = can_overflow ? (uint32_t*)take((int64_t)B * kHistBins * 4) : nullptr;
+  ws->cutoff = can_overflow ? (int32_t*)take((int64_t)B * 4) : nullptr;
   ws->cap = (int32_t)cap;
   ws->cap2 = (int32_t)cap2;
   ws->T = T;
@@ -419,6 +520,7 @@ extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int3
                                double iou_thres, int32_t agnostic, int32_t multi_label, const uint8_t* class_mask,
                                int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
                                void* workspace, int64_t workspace_bytes, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && pred && out && out_count && out_src && workspace, "nms: null argument");
   YV6_REQUIRE(B > 0 && A > 0 && nc > 0, "nms: bad shape B=%d A=%d nc=%d", B, A, nc);
   YV6_REQUIRE(conf_thres >= 0.f && conf_thres <= 1.f, "nms: conf_thres must be in [0,1]");       // nms.py:50
@@ -449,11 +551,17 @@ extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int3
   YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.cand_count, 0, sizeof(int32_t) * B, s));
   dim3 grid(p.ws.T, B);
   nms_select_kernel<<<grid, kNmsTile, 0, s>>>(p);
-  static bool configured = false;
-  if (!configured) {
+  if (p.ws.hist != nullptr) {   // A * nc exceeds the key capacity: keep the max_nms best of an overflowing image (nms.py:90-91)
+    YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.hist, 0, sizeof(uint32_t) * (size_t)B * kHistBins, s));
+    dim3 g8((A + 7) / 8, B);
+    nms_overflow_pass_kernel<false><<<g8, 256, 0, s>>>(p);
+    nms_cutoff_kernel<<<B, 1024, 0, s>>>(p);
+    nms_overflow_pass_kernel<true><<<g8, 256, 0, s>>>(p);
+  }
+  if (!(h->configured & YV6_CFG_NMS)) {
     YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemMax * 8));
     YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 20));
-    configured = true;
+    h->configured |= YV6_CFG_NMS;
   }
   const size_t sort_smem = (size_t)std::min<int64_t>(p.ws.cap2, kSortSmemMax) * 8;
   nms_sort_kernel<<<B, 1024, sort_smem, s>>>(p);

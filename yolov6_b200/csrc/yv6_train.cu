@@ -100,6 +100,126 @@ __global__ void bn_finalize_kernel(const double* sum, const double* sumsq, doubl
   }
 }
 
+// ---------------------------------------------------------------------------------- thread mapping
+// All per-channel kernels below use thread = (pixel row `prow`, channel group `cg` of 8 channels = one 16-byte
+// load); a thread keeps its channel group for the whole kernel, so the per-channel constants live in registers
+// and the pixel loop is nothing but 16-byte loads, FMAs and (for the elementwise kernels) 16-byte stores.
+struct ChanMap {
+  int cgs, cg, prow, prows;
+  __device__ __forceinline__ explicit ChanMap(int C) {
+    cgs = C >> 3;
+    cg = threadIdx.x % cgs;
+    prow = threadIdx.x / cgs;
+    prows = blockDim.x / cgs;
+  }
+};
+__device__ __forceinline__ void ldc8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// column sums of per-thread partials: red[prows][C] floats in shared memory -> one double atomic per channel
+__device__ __forceinline__ void block_colsum(const ChanMap& m, int C, const float (&part)[8], float* red, double* dst) {
+  float4* row = reinterpret_cast<float4*>(red + (size_t)m.prow * C + m.cg * 8);
+  row[0] = make_float4(part[0], part[1], part[2], part[3]);
+  row[1] = make_float4(part[4], part[5], part[6], part[7]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < m.prows; ++r) a += (double)red[(size_t)r * C + c];
+    atomicAdd(&dst[c], a);
+  }
+  __syncthreads();
+}
+// true in exactly one block per launch: the one that finishes last (its reads see every other block's atomics)
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+
+// ---------------------------------------------------------------------------------- fused statistics
+// sum / sum of squares of up to three branch inputs in ONE pass per branch tensor, then -- in the block that
+// finishes last -- mean / invstd / scale / shift and the running-statistics update of every branch
+// (nn.BatchNorm2d training semantics, eps / momentum as set by initialize_weights, torch_utils.py:38-48).
+struct StatsParams {
+  View x[3];
+  int nb, C;
+  int64_t pixels;
+  double* sums;                 // [nb][2][C], zero on entry
+  unsigned int* counter;        // zero on entry
+  const float* gamma[3];
+  const float* beta[3];
+  float* rmean[3];
+  float* rvar[3];
+  float* stats[3];              // out [4][C]: mean, invstd, scale, shift; null = no finalize for that branch
+  float eps, momentum;
+};
+__device__ __forceinline__ void bn_finalize_one(double sum, double sumsq, double count, float gamma, float beta, float eps,
+                                                float momentum, float* rmean, float* rvar, float* stats, int C, int c) {
+  const double m = sum / count;
+  double var = sumsq / count - m * m;
+  if (var < 0) var = 0;
+  const double inv = 1.0 / sqrt(var + (double)eps);
+  const double g = gamma;
+  stats[c] = (float)m;
+  stats[C + c] = (float)inv;
+  stats[2 * C + c] = (float)(g * inv);
+  stats[3 * C + c] = (float)((double)beta - m * g * inv);
+  if (rmean != nullptr) {
+    const double unb = (count > 1) ? var * count / (count - 1.0) : var;
+    rmean[c] = (float)((1.0 - momentum) * rmean[c] + momentum * m);
+    rvar[c] = (float)((1.0 - momentum) * rvar[c] + momentum * unb);
+  }
+}
+template <int NB>
+__global__ void __launch_bounds__(kTrThreads) bn_stats_multi_kernel(const StatsParams p) {
+  extern __shared__ float red[];            // [prows][C]
+  const ChanMap m(p.C);
+  float s[NB][8], q[NB][8];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[b][j] = q[b][j] = 0.f;
+  if (m.prow < m.prows) {
+    const int64_t step = (int64_t)gridDim.x * m.prows;
+    for (int64_t px = (int64_t)blockIdx.x * m.prows + m.prow; px < p.pixels; px += 2 * step) {
+      const bool two = (px + step) < p.pixels;
+      float v0[NB][8], v1[NB][8];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        ld8(p.x[b].p + px * p.x[b].pitch + m.cg * 8, v0[b]);
+        if (two) ld8(p.x[b].p + (px + step) * p.x[b].pitch + m.cg * 8, v1[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[b][j] += v0[b][j]; q[b][j] += v0[b][j] * v0[b][j]; }
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s[b][j] += v1[b][j]; q[b][j] += v1[b][j] * v1[b][j]; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    block_colsum(m, p.C, s[b], red, p.sums + (size_t)(2 * b) * p.C);
+    block_colsum(m, p.C, q[b], red, p.sums + (size_t)(2 * b + 1) * p.C);
+  }
+  if (!last_block_done(p.counter)) return;
+  for (int i = threadIdx.x; i < NB * p.C; i += blockDim.x) {
+    const int b = i / p.C, c = i - b * p.C;
+    if (p.stats[b] == nullptr) continue;
+    bn_finalize_one(ld_cg(p.sums + (size_t)(2 * b) * p.C + c), ld_cg(p.sums + (size_t)(2 * b + 1) * p.C + c), (double)p.pixels,
+                    p.gamma[b][c], p.beta[b][c], p.eps, p.momentum, p.rmean[b], p.rvar[b], p.stats[b], p.C, c);
+  }
+}
+
 // ---------------------------------------------------------------------------------- bn_apply_fwd
 struct ApplyParams {
   View x[3];
@@ -111,40 +231,48 @@ struct ApplyParams {
   int64_t y_pitch;
   View res;                  // optional shortcut: y = act(z) + alpha * res (BottleRep, common.py:600-617)
   float alpha;
+  const float* alpha_dev;    // when set, the shortcut weight is read from device memory (no host sync, graph-capturable)
 };
 __device__ __forceinline__ float act_fwd(float z, int act) {
   if (act == YV6_ACT_RELU) return fmaxf(z, 0.f);
   if (act == YV6_ACT_SILU) return z / (1.f + __expf(-z));
   return z;
 }
+template <int NB>
 __global__ void __launch_bounds__(kTrThreads) bn_apply_fwd_kernel(const ApplyParams p) {
-  const int cgs = p.C / 8;
-  const int64_t total = p.pixels * cgs;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    const int64_t px = i / cgs;
+  const ChanMap m(p.C);
+  if (m.prow >= m.prows) return;
+  float sc[NB][8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = 0.f;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float t[8];
+    ldc8(p.scale[b] + m.cg * 8, sc[b]);
+    ldc8(p.shift[b] + m.cg * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[j] += t[j];
+  }
+  const float alpha = (p.alpha_dev != nullptr) ? __ldg(p.alpha_dev) : p.alpha;
+  const int64_t step = (int64_t)gridDim.x * m.prows;
+  for (int64_t px = (int64_t)blockIdx.x * m.prows + m.prow; px < p.pixels; px += step) {
+    float v[NB][8], r[8];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ld8(p.x[b].p + px * p.x[b].pitch + m.cg * 8, v[b]);
+    if (p.res.p != nullptr) ld8(p.res.p + px * p.res.pitch + m.cg * 8, r);
     float z[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = 0.f;
-    for (int b = 0; b < p.nb; ++b) {
-      float v[8];
-      ld8(p.x[b].p + px * p.x[b].pitch + cg * 8, v);
-      const float4 s0 = *reinterpret_cast<const float4*>(p.scale[b] + cg * 8), s1 = *reinterpret_cast<const float4*>(p.scale[b] + cg * 8 + 4);
-      const float4 h0 = *reinterpret_cast<const float4*>(p.shift[b] + cg * 8), h1 = *reinterpret_cast<const float4*>(p.shift[b] + cg * 8 + 4);
-      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    for (int j = 0; j < 8; ++j) {
+      float a = sh[j];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += v[j] * sc[j] + sh[j];
+      for (int b = 0; b < NB; ++b) a += v[b][j] * sc[b][j];
+      z[j] = act_fwd(a, p.act);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = act_fwd(z[j], p.act);
     if (p.res.p != nullptr) {
-      float r[8];
-      ld8(p.res.p + px * p.res.pitch + cg * 8, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += p.alpha * r[j];
+      for (int j = 0; j < 8; ++j) z[j] += alpha * r[j];
     }
-    st8(p.y + px * p.y_pitch + cg * 8, z);
+    st8(p.y + px * p.y_pitch + m.cg * 8, z);
   }
 }
 
@@ -158,119 +286,149 @@ struct BwdParams {
   View dy;                   // gradient w.r.t. the block output
   View res;                  // optional shortcut input (y = act(z) + alpha * res)
   float alpha;
+  const float* alpha_dev;
   __nv_bfloat16* dres;       // g(res) += alpha * dy
   int64_t dres_pitch;
   double* dalpha;            // += sum dy * res
   int nb, act, C;
   int64_t pixels;
-  double* s1;                // [C]      sum dz            (shared by the branches)
-  double* s2[3];             // [C] each sum dz * xhat_b
-  // apply
+  double* s1;                // [C]      sum dz            (shared by the branches) = dbeta
+  double* s2[3];             // [C] each sum dz * xhat_b   = dgamma_b (written by the last block of the reduce pass)
+  double* work;              // [nb][C]  sum dz * x_b, zero on entry
+  unsigned int* counter;     // zero on entry
+  float* coef;               // [nb][2][C]: dx_b = scale_b * dz + coef[b][0] * x_b + coef[b][1]
   __nv_bfloat16* dx[3];
   int64_t dx_pitch[3];
   int accumulate[3];         // dx_b += ... instead of =
   double inv_count;
 };
-
-__device__ __forceinline__ void bwd_dz(const BwdParams& p, int64_t px, int cg, float (&dz)[8]) {
-  ld8(p.dy.p + px * p.dy.pitch + cg * 8, dz);
-  if (p.act != YV6_ACT_NONE) {   // the pre-activation is recomputed from the branch inputs (same fp32 arithmetic as the forward)
-    float z[8];
+__device__ __forceinline__ void act_bwd(float (&dz)[8], const float (&z)[8], int act) {
+  if (act == YV6_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = 0.f;
-    for (int b = 0; b < p.nb; ++b) {
-      float v[8];
-      ld8(p.x[b].p + px * p.x[b].pitch + cg * 8, v);
+    for (int j = 0; j < 8; ++j) dz[j] = (z[j] > 0.f) ? dz[j] : 0.f;
+  } else if (act == YV6_ACT_SILU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += v[j] * p.scale[b][cg * 8 + j] + p.shift[b][cg * 8 + j];
-    }
-    if (p.act == YV6_ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = (z[j] > 0.f) ? dz[j] : 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float sg = 1.f / (1.f + __expf(-z[j]));
-        dz[j] *= sg * (1.f + z[j] * (1.f - sg));
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.f / (1.f + __expf(-z[j]));
+      dz[j] *= sg * (1.f + z[j] * (1.f - sg));
     }
   }
 }
-
-__global__ void __launch_bounds__(kTrThreads) bn_bwd_reduce_kernel(const BwdParams p) {
-  const int cgs = p.C / 8;
-  const int cg = threadIdx.x % cgs;
-  const int prow = threadIdx.x / cgs, prows = blockDim.x / cgs;
-  float a1[8], a2[3][8];
+// pass 1: S1 = sum dz, T_b = sum dz * x_b (and dalpha); the last block turns them into dgamma_b and the
+// coefficients of pass 2:  dx_b = scale_b (dz - S1/M - xhat_b S2_b/M) = scale_b dz + B_b x_b + C_b  with
+// S2_b = invstd_b (T_b - mean_b S1), B_b = -scale_b invstd_b S2_b / M, C_b = -scale_b S1 / M - B_b mean_b.
+template <int NB>
+__global__ void __launch_bounds__(kTrThreads, 2) bn_bwd_reduce_kernel(const BwdParams p) {
+  extern __shared__ float red[];            // [prows][C]
+  const ChanMap m(p.C);
+  float sc[NB][8], sh[8], a1[8], t[NB][8];
   float da = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[0][j] = a2[1][j] = a2[2][j] = 0.f; }
-  for (int64_t px = (int64_t)blockIdx.x * prows + prow; px < p.pixels; px += (int64_t)gridDim.x * prows) {
-    float dz[8];
-    if (p.dalpha != nullptr) {
-      float g[8], r[8];
-      ld8(p.dy.p + px * p.dy.pitch + cg * 8, g);
-      ld8(p.res.p + px * p.res.pitch + cg * 8, r);
+  for (int j = 0; j < 8; ++j) { sh[j] = 0.f; a1[j] = 0.f; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) da += g[j] * r[j];
+  for (int b = 0; b < NB; ++b) {
+    float tmp[8];
+    ldc8(p.scale[b] + m.cg * 8, sc[b]);
+    ldc8(p.shift[b] + m.cg * 8, tmp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sh[j] += tmp[j]; t[b][j] = 0.f; }
+  }
+  if (m.prow < m.prows) {
+    const int64_t step = (int64_t)gridDim.x * m.prows;
+    for (int64_t px = (int64_t)blockIdx.x * m.prows + m.prow; px < p.pixels; px += step) {
+      float dz[8], v[NB][8], z[8];
+      ld8(p.dy.p + px * p.dy.pitch + m.cg * 8, dz);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) ld8(p.x[b].p + px * p.x[b].pitch + m.cg * 8, v[b]);
+      if (p.dalpha != nullptr) {
+        float r[8];
+        ld8(p.res.p + px * p.res.pitch + m.cg * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) da += dz[j] * r[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = sh[j];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) a += v[b][j] * sc[b][j];
+        z[j] = a;
+      }
+      act_bwd(dz, z, p.act);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += dz[j];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) t[b][j] += dz[j] * v[b][j];
+      }
     }
-    bwd_dz(p, px, cg, dz);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a1[j] += dz[j];
-    for (int b = 0; b < p.nb; ++b) {
-      float v[8];
-      ld8(p.x[b].p + px * p.x[b].pitch + cg * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a2[b][j] += dz[j] * (v[j] - p.mean[b][cg * 8 + j]) * p.invstd[b][cg * 8 + j];
-    }
   }
-  extern __shared__ double sred[];                      // [1 + nb][C]: block-level sums before the global atomics
-  for (int c = threadIdx.x; c < (1 + p.nb) * p.C; c += blockDim.x) sred[c] = 0.0;
-  __syncthreads();
+  block_colsum(m, p.C, a1, red, p.s1);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sred[cg * 8 + j], (double)a1[j]);
-    for (int b = 0; b < p.nb; ++b) atomicAdd(&sred[(1 + b) * p.C + cg * 8 + j], (double)a2[b][j]);
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    atomicAdd(&p.s1[c], sred[c]);
-    for (int b = 0; b < p.nb; ++b) atomicAdd(&p.s2[b][c], sred[(1 + b) * p.C + c]);
-  }
+  for (int b = 0; b < NB; ++b) block_colsum(m, p.C, t[b], red, p.work + (size_t)b * p.C);
   if (p.dalpha != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(p.dalpha, (double)da);
   }
+  if (!last_block_done(p.counter)) return;
+  for (int i = threadIdx.x; i < NB * p.C; i += blockDim.x) {
+    const int b = i / p.C, c = i - b * p.C;
+    const double S1 = ld_cg(p.s1 + c), T = ld_cg(p.work + (size_t)b * p.C + c);
+    const double mean = p.mean[b][c], inv = p.invstd[b][c], scale = p.scale[b][c];
+    const double S2 = inv * (T - mean * S1);
+    p.s2[b][c] = S2;
+    const double B = -scale * inv * S2 * p.inv_count;
+    p.coef[(size_t)(2 * b) * p.C + c] = (float)B;
+    p.coef[(size_t)(2 * b + 1) * p.C + c] = (float)(-scale * S1 * p.inv_count - B * mean);
+  }
 }
 
-__global__ void __launch_bounds__(kTrThreads) bn_bwd_apply_kernel(const BwdParams p) {
-  const int cgs = p.C / 8;
-  const int64_t total = p.pixels * cgs;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    const int64_t px = i / cgs;
-    float dz[8];
+template <int NB>
+__global__ void __launch_bounds__(kTrThreads, 2) bn_bwd_apply_kernel(const BwdParams p) {
+  const ChanMap m(p.C);
+  if (m.prow >= m.prows) return;
+  float sc[NB][8], sh[8], cb[NB][8], cc[NB][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = 0.f;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float tmp[8];
+    ldc8(p.scale[b] + m.cg * 8, sc[b]);
+    ldc8(p.shift[b] + m.cg * 8, tmp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[j] += tmp[j];
+    ldc8(p.coef + (size_t)(2 * b) * p.C + m.cg * 8, cb[b]);
+    ldc8(p.coef + (size_t)(2 * b + 1) * p.C + m.cg * 8, cc[b]);
+  }
+  const float alpha = (p.alpha_dev != nullptr) ? __ldg(p.alpha_dev) : p.alpha;
+  const int64_t step = (int64_t)gridDim.x * m.prows;
+  for (int64_t px = (int64_t)blockIdx.x * m.prows + m.prow; px < p.pixels; px += step) {
+    float dz[8], v[NB][8], z[8];
+    ld8(p.dy.p + px * p.dy.pitch + m.cg * 8, dz);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ld8(p.x[b].p + px * p.x[b].pitch + m.cg * 8, v[b]);
     if (p.dres != nullptr) {
-      float g[8], old[8];
-      ld8(p.dy.p + px * p.dy.pitch + cg * 8, g);
-      __nv_bfloat16* dst = p.dres + px * p.dres_pitch + cg * 8;
+      float old[8];
+      __nv_bfloat16* dst = p.dres + px * p.dres_pitch + m.cg * 8;
       ld8(dst, old);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) old[j] += p.alpha * g[j];
+      for (int j = 0; j < 8; ++j) old[j] += alpha * dz[j];
       st8(dst, old);
     }
-    bwd_dz(p, px, cg, dz);
-    for (int b = 0; b < p.nb; ++b) {
-      float v[8], o[8];
-      ld8(p.x[b].p + px * p.x[b].pitch + cg * 8, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
-        const float xh = (v[j] - p.mean[b][c]) * p.invstd[b][c];
-        o[j] = p.scale[b][c] * (dz[j] - (float)(p.s1[c] * p.inv_count) - xh * (float)(p.s2[b][c] * p.inv_count));
-      }
-      __nv_bfloat16* dst = p.dx[b] + px * p.dx_pitch[b] + cg * 8;
+    for (int j = 0; j < 8; ++j) {
+      float a = sh[j];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) a += v[b][j] * sc[b][j];
+      z[j] = a;
+    }
+    act_bwd(dz, z, p.act);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = sc[b][j] * dz[j] + cb[b][j] * v[b][j] + cc[b][j];
+      __nv_bfloat16* dst = p.dx[b] + px * p.dx_pitch[b] + m.cg * 8;
       if (p.accumulate[b]) {
         float old[8];
         ld8(dst, old);
@@ -342,33 +500,162 @@ __global__ void __launch_bounds__(kTrThreads) add_f32_to_bf16_kernel(const float
 }
 
 // ---------------------------------------------------------------------------------- stem wgrad
-// dW[co][r][s][c] = sum_pixels dY[p][co] * x[n, c, 2ho + r - 1, 2wo + s - 1]; 27 * Cout outputs.
-__global__ void __launch_bounds__(kTrThreads) stem_wgrad_kernel(const void* x, int x_u8, float in_scale, const __nv_bfloat16* dy,
-                                                               int64_t dy_pitch, int N, int H, int W, int Cout, float* dw) {
-  extern __shared__ float acc[];  // [27 * Cout]
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
+// dW3[co][r][s][c] = sum_pixels dY3[p][co] * x[n, c, 2ho + r - 1, 2wo + s - 1]   (3x3 stride-2 branch)
+// dW1[co][c]       = sum_pixels dY1[p][co] * x[n, c, 2ho, 2wo]                    (1x1 stride-2 branch of a RepVGG stem)
+// Persistent blocks walk 8x32 output tiles: the input patch (3 x 17 x 65 fp32) and the dY tile(s) are staged in
+// shared memory, thread (tap group, co) accumulates its <= 7 taps over the 256 pixels in registers; one fp32
+// atomic per (block, output) at the very end.
+constexpr int kSwTH = 8, kSwTW = 32, kSwPH = 2 * kSwTH + 1, kSwPW = 2 * kSwTW + 1, kSwMaxTaps = 7;
+constexpr int kSwPatchFloats = (3 * kSwPH * (kSwPW + 1) + 3) & ~3;      // keeps the dY tiles 16-byte aligned
+__global__ void __launch_bounds__(kTrThreads) stem_wgrad_kernel(const void* x, int x_u8, float in_scale, View dy3, View dy1, int N, int H,
+                                                               int W, int Cout, float* dw3, float* dw1) {
+  extern __shared__ float sw_smem[];
+  float* patch = sw_smem;                                               // [3][kSwPH][kSwPW + 1]
+  __nv_bfloat16* g3 = reinterpret_cast<__nv_bfloat16*>(patch + kSwPatchFloats);   // [256][Cout]
+  __nv_bfloat16* g1 = g3 + kSwTH * kSwTW * Cout;                        // [256][Cout] (only when dy1 is given)
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const int64_t pixels = (int64_t)N * Ho * Wo;
-  // thread = (pixel lane, tap k): each thread owns one of the 27 input taps for a strided set of pixels
-  const int k = threadIdx.x % 27, lane = threadIdx.x / 27, lanes = blockDim.x / 27;
-  if (lane < lanes) {
-    const int r = k / 9, s = (k / 3) % 3, c = k % 3;
-    float part[64];
-    for (int co = 0; co < Cout; ++co) part[co] = 0.f;
-    for (int64_t px = (int64_t)blockIdx.x * lanes + lane; px < pixels; px += (int64_t)gridDim.x * lanes) {
-      const int wo = (int)(px % Wo), ho = (int)((px / Wo) % Ho), n = (int)(px / ((int64_t)Wo * Ho));
-      const int hi = 2 * ho - 1 + r, wi = 2 * wo - 1 + s;
-      if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-      const int64_t idx = (((int64_t)n * 3 + c) * H + hi) * W + wi;
-      const float xv = x_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[idx] * in_scale : reinterpret_cast<const float*>(x)[idx];
-      const __nv_bfloat16* g = dy + px * dy_pitch;
-      for (int co = 0; co < Cout; ++co) part[co] += xv * __bfloat162float(g[co]);
+  const int tiles_w = (Wo + kSwTW - 1) / kSwTW, tiles_h = (Ho + kSwTH - 1) / kSwTH;
+  const int64_t tiles = (int64_t)N * tiles_h * tiles_w;
+  const int groups = blockDim.x / Cout;                                 // tap groups
+  const int co = threadIdx.x % Cout, grp = threadIdx.x / Cout;
+  const bool active = grp < groups;
+  const bool has1 = dy1.p != nullptr;
+  float acc[kSwMaxTaps], acc1 = 0.f;
+  int off[kSwMaxTaps];                                                  // patch offset of my taps (-1 = none)
+  int centre_i = -1, centre_off = 0;                                    // my centre tap (r = s = 1), if any: feeds dW1 as well
+#pragma unroll
+  for (int i = 0; i < kSwMaxTaps; ++i) {
+    acc[i] = 0.f;
+    const int k = grp + i * groups;                                     // k = (r*3 + s)*3 + c
+    off[i] = -1;
+    if (active && k < 27) {
+      const int r = k / 9, sx = (k / 3) % 3, c = k % 3;
+      off[i] = (c * kSwPH + r) * (kSwPW + 1) + sx;
+      if (r == 1 && sx == 1) { centre_i = i; centre_off = off[i]; }
     }
-    for (int co = 0; co < Cout; ++co) atomicAdd(&acc[co * 27 + (r * 3 + s) * 3 + c], part[co]);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) atomicAdd(&dw[i], acc[i]);
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int tw = (int)(t % tiles_w), th = (int)((t / tiles_w) % tiles_h), n = (int)(t / ((int64_t)tiles_w * tiles_h));
+    const int ho0 = th * kSwTH, wo0 = tw * kSwTW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * kSwPH * kSwPW; i += blockDim.x) {
+      const int pc = i % kSwPW, pr = (i / kSwPW) % kSwPH, c = i / (kSwPW * kSwPH);
+      const int hi = 2 * ho0 - 1 + pr, wi = 2 * wo0 - 1 + pc;
+      float v = 0.f;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const int64_t idx = (((int64_t)n * 3 + c) * H + hi) * W + wi;
+        v = x_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[idx] * in_scale : reinterpret_cast<const float*>(x)[idx];
+      }
+      patch[(c * kSwPH + pr) * (kSwPW + 1) + pc] = v;
+    }
+    const int vec = Cout / 8;                                           // 16-byte chunks per pixel
+    for (int i = threadIdx.x; i < kSwTH * kSwTW * vec; i += blockDim.x) {
+      const int j = i % vec, px = i / vec;
+      const int ho = ho0 + px / kSwTW, wo = wo0 + px % kSwTW;
+      uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+      if (ho < Ho && wo < Wo) {
+        const int64_t gp = ((int64_t)n * Ho + ho) * Wo + wo;
+        a = *reinterpret_cast<const uint4*>(dy3.p + gp * dy3.pitch + j * 8);
+        if (has1) b = *reinterpret_cast<const uint4*>(dy1.p + gp * dy1.pitch + j * 8);
+      }
+      *reinterpret_cast<uint4*>(g3 + (size_t)px * Cout + j * 8) = a;
+      if (has1) *reinterpret_cast<uint4*>(g1 + (size_t)px * Cout + j * 8) = b;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int py = 0; py < kSwTH; ++py) {
+#pragma unroll 4
+      for (int pxx = 0; pxx < kSwTW; ++pxx) {
+        const int px = py * kSwTW + pxx;
+        const float g = __bfloat162float(g3[(size_t)px * Cout + co]);
+        const float* pp = patch + (2 * py) * (kSwPW + 1) + 2 * pxx;
+#pragma unroll
+        for (int i = 0; i < kSwMaxTaps; ++i)
+          if (off[i] >= 0) acc[i] += g * pp[off[i]];
+        if (has1 && centre_i >= 0) acc1 += __bfloat162float(g1[(size_t)px * Cout + co]) * pp[centre_off];
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < kSwMaxTaps; ++i) {
+    const int k = grp + i * groups;
+    if (off[i] >= 0) atomicAdd(&dw3[co * 27 + k], acc[i]);
+    if (has1 && i == centre_i) atomicAdd(&dw1[co * 3 + (k % 3)], acc1);
+  }
+}
+
+// ---------------------------------------------------------------------------------- table-driven repack
+// dst[d0][d1][d2][d3] (arbitrary strides) (+)= cast(src[d0][d1][d2][d3] (arbitrary, possibly negative strides)).
+// One launch repacks every parameter of the network: fp32 master weights -> bf16 KRSC forward weights, rotated /
+// transposed / parity-split dgrad weights, padded biases (per optimizer step), and -- in the other direction --
+// fp32 KRSC weight gradients and float64 BatchNorm sums -> the flat fp32 gradient buffer in the reference's
+// parameter layouts.
+__global__ void __launch_bounds__(256) xform_kernel(const yv6_xform_seg* segs, const int32_t* chunk_seg, const int32_t* chunk_first,
+                                                    int accumulate) {
+  const int si = chunk_seg[blockIdx.x];
+  const yv6_xform_seg sg = segs[si];
+  const int64_t total = (int64_t)sg.n[0] * sg.n[1] * sg.n[2] * sg.n[3];
+  const int64_t begin = (int64_t)(blockIdx.x - chunk_first[si]) * YV6_XFORM_CHUNK;
+  const int64_t end = min(total, begin + YV6_XFORM_CHUNK);
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    int64_t r = i;
+    const int d3 = (int)(r % sg.n[3]); r /= sg.n[3];
+    const int d2 = (int)(r % sg.n[2]); r /= sg.n[2];
+    const int d1 = (int)(r % sg.n[1]); r /= sg.n[1];
+    const int d0 = (int)r;
+    const int64_t so = (int64_t)d0 * sg.ss[0] + (int64_t)d1 * sg.ss[1] + (int64_t)d2 * sg.ss[2] + (int64_t)d3 * sg.ss[3];
+    const int64_t dofs = (int64_t)d0 * sg.ds[0] + (int64_t)d1 * sg.ds[1] + (int64_t)d2 * sg.ds[2] + (int64_t)d3 * sg.ds[3];
+    float v;
+    if (sg.src_dtype == YV6_XF_F64) v = (float)reinterpret_cast<const double*>(sg.src)[so];
+    else v = reinterpret_cast<const float*>(sg.src)[so];
+    if (sg.dst_dtype == YV6_XF_BF16) {
+      reinterpret_cast<__nv_bfloat16*>(sg.dst)[dofs] = __float2bfloat16_rn(v);
+    } else {
+      float* d = reinterpret_cast<float*>(sg.dst) + dofs;
+      *d = accumulate ? (*d + v) : v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- fused optimizer step
+// torch.optim.SGD(momentum, nesterov=True) over the three parameter groups of build_optimizer (solver/build.py:10-33:
+// BN weights / conv weights with weight decay / biases) and the ModelEMA update (utils/ema.py:28-37) in ONE pass over
+// the flat fp32 parameter / gradient / momentum / EMA buffers.  Hyper-parameters come from device memory so that a
+// captured CUDA graph follows the learning-rate schedule:
+//   hyper = [lr_bnw, lr_w, lr_b, momentum, weight_decay (group w only), ema_decay, first_step, grad_scale]
+__global__ void __launch_bounds__(256) sgd_ema_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ mom,
+                                                      float* __restrict__ ema, const uint8_t* __restrict__ group, int64_t n4,
+                                                      const float* __restrict__ hyper) {
+  const float lr[3] = {__ldg(hyper), __ldg(hyper + 1), __ldg(hyper + 2)};
+  const float mu = __ldg(hyper + 3), wd = __ldg(hyper + 4), d = __ldg(hyper + 5), gs = __ldg(hyper + 7);
+  const bool first = __ldg(hyper + 6) != 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gidx = group[i];                                          // one group id per 4 elements (segments are 16-byte aligned)
+    float4 p = reinterpret_cast<float4*>(param)[i];
+    if (gidx < 3) {
+      const float4 g4 = reinterpret_cast<const float4*>(grad)[i];
+      float4 b = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(mom)[i];
+      const float w = (gidx == 1) ? wd : 0.f, l = lr[gidx];
+      float pe[4] = {p.x, p.y, p.z, p.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float g = ge[j] * gs + w * pe[j];
+        be[j] = first ? g : (mu * be[j] + g);
+        g += mu * be[j];                                                // nesterov
+        pe[j] -= l * g;
+      }
+      p = make_float4(pe[0], pe[1], pe[2], pe[3]);
+      reinterpret_cast<float4*>(param)[i] = p;
+      reinterpret_cast<float4*>(mom)[i] = make_float4(be[0], be[1], be[2], be[3]);
+    }
+    if (ema != nullptr && gidx < 4) {                                   // group 3 = float buffers (running statistics): EMA only
+      float4 e = reinterpret_cast<float4*>(ema)[i];
+      e.x = e.x * d + (1.f - d) * p.x; e.y = e.y * d + (1.f - d) * p.y;
+      e.z = e.z * d + (1.f - d) * p.z; e.w = e.w * d + (1.f - d) * p.w;
+      reinterpret_cast<float4*>(ema)[i] = e;
+    }
+  }
 }
 
 }  // namespace yv6
@@ -382,6 +669,7 @@ static inline unsigned grid_for(int64_t total, int threads, int num_sms) {
 
 extern "C" int yv6_bn_stats(yv6_handle* h, const void* x, int64_t pixels, int32_t C, int64_t pitch, double* sum, double* sumsq,
                             void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && x && sum && sumsq, "bn_stats: null argument");
   YV6_REQUIRE(C % 8 == 0 && C <= 2048 && pitch % 8 == 0, "bn_stats: C=%d pitch=%lld", C, (long long)pitch);
   const int cgs = C / 8;
@@ -400,6 +688,7 @@ extern "C" int yv6_bn_stats(yv6_handle* h, const void* x, int64_t pixels, int32_
 extern "C" int yv6_bn_finalize(yv6_handle* h, const double* sum, const double* sumsq, double count, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                float* mean_out, float* invstd_out, float* scale, float* shift, int32_t C, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && sum && sumsq && gamma && beta && mean_out && invstd_out && scale && shift, "bn_finalize: null argument");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, count, gamma, beta, eps, momentum, running_mean,
                                                                       running_var, mean_out, invstd_out, scale, shift, C);
@@ -407,10 +696,56 @@ extern "C" int yv6_bn_finalize(yv6_handle* h, const double* sum, const double* s
   return YV6_OK;
 }
 
+static inline int chan_threads(int C) {
+  const int cgs = C / 8;
+  return cgs * std::max(1, kTrThreads / cgs);
+}
+static inline unsigned chan_grid(int64_t pixels, int C, int num_sms, int per_sm) {
+  const int rows = std::max(1, kTrThreads / (C / 8));
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((pixels + rows - 1) / rows, (int64_t)num_sms * per_sm));
+}
+static int configure_train(yv6_handle* h) {
+  if (h->configured & YV6_CFG_BN) return YV6_OK;
+  YV6_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  h->configured |= YV6_CFG_BN;
+  return YV6_OK;
+}
+
+extern "C" int yv6_bn_stats_finalize(yv6_handle* h, const yv6_bn_stats_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && d && d->nb >= 1 && d->nb <= 3 && d->sums && d->counter, "bn_stats_finalize: bad descriptor");
+  YV6_REQUIRE(d->C % 8 == 0 && d->C >= 8 && d->C <= 2048, "bn_stats_finalize: C=%d (multiple of 8, <= 2048)", d->C);
+  StatsParams p;
+  memset(&p, 0, sizeof(p));
+  for (int b = 0; b < d->nb; ++b) {
+    YV6_REQUIRE(d->x[b] && d->x_pitch[b] % 8 == 0, "bn_stats_finalize: branch %d input", b);
+    YV6_REQUIRE(!d->stats[b] || (d->gamma[b] && d->beta[b]), "bn_stats_finalize: branch %d affine parameters", b);
+    p.x[b] = View{reinterpret_cast<const __nv_bfloat16*>(d->x[b]), d->x_pitch[b]};
+    p.gamma[b] = d->gamma[b]; p.beta[b] = d->beta[b]; p.rmean[b] = d->running_mean[b]; p.rvar[b] = d->running_var[b];
+    p.stats[b] = d->stats[b];
+  }
+  p.nb = d->nb; p.C = d->C; p.pixels = d->pixels; p.sums = d->sums; p.counter = d->counter; p.eps = d->eps; p.momentum = d->momentum;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!d->zeroed) {
+    YV6_CHECK_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(double) * 2 * d->nb * d->C, s));
+    YV6_CHECK_CUDA(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), s));
+  }
+  const int threads = chan_threads(d->C);
+  const unsigned grid = chan_grid(d->pixels, d->C, h->num_sms, 4);
+  const size_t smem = sizeof(float) * (size_t)(threads / (d->C / 8)) * d->C;
+  if (d->nb == 1) bn_stats_multi_kernel<1><<<grid, threads, smem, s>>>(p);
+  else if (d->nb == 2) bn_stats_multi_kernel<2><<<grid, threads, smem, s>>>(p);
+  else bn_stats_multi_kernel<3><<<grid, threads, smem, s>>>(p);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
+
 extern "C" int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && d && d->nb >= 1 && d->nb <= 3 && d->y, "bn_apply_fwd: bad descriptor");
-  YV6_REQUIRE(d->C % 8 == 0, "bn_apply_fwd: C must be a multiple of 8");
+  YV6_REQUIRE(d->C % 8 == 0 && d->C >= 8 && d->C <= 2048, "bn_apply_fwd: C must be a multiple of 8, <= 2048");
   ApplyParams p;
+  memset(&p, 0, sizeof(p));
   for (int b = 0; b < d->nb; ++b) {
     p.x[b] = View{reinterpret_cast<const __nv_bfloat16*>(d->x[b]), d->x_pitch[b]};
     p.scale[b] = d->scale[b];
@@ -420,15 +755,23 @@ extern "C" int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* strea
   p.y = reinterpret_cast<__nv_bfloat16*>(d->y); p.y_pitch = d->y_pitch;
   p.res = View{reinterpret_cast<const __nv_bfloat16*>(d->res), d->res_pitch};
   p.alpha = d->res_alpha;
-  bn_apply_fwd_kernel<<<grid_for(d->pixels * (d->C / 8), kTrThreads, h->num_sms), kTrThreads, 0, (cudaStream_t)stream>>>(p);
+  p.alpha_dev = d->res_alpha_dev;
+  const int threads = chan_threads(d->C);
+  const unsigned grid = chan_grid(d->pixels, d->C, h->num_sms, 16);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->nb == 1) bn_apply_fwd_kernel<1><<<grid, threads, 0, s>>>(p);
+  else if (d->nb == 2) bn_apply_fwd_kernel<2><<<grid, threads, 0, s>>>(p);
+  else bn_apply_fwd_kernel<3><<<grid, threads, 0, s>>>(p);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }
 
 extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && d && d->nb >= 1 && d->nb <= 3 && d->dy && d->s1, "bn_bwd: bad descriptor");
-  YV6_REQUIRE(d->C % 8 == 0 && d->C <= 2048, "bn_bwd: C");
+  YV6_REQUIRE(d->C % 8 == 0 && d->C >= 8 && d->C <= 2048, "bn_bwd: C");
   BwdParams p;
+  memset(&p, 0, sizeof(p));
   for (int b = 0; b < d->nb; ++b) {
     p.x[b] = View{reinterpret_cast<const __nv_bfloat16*>(d->x[b]), d->x_pitch[b]};
     p.mean[b] = d->mean[b]; p.invstd[b] = d->invstd[b]; p.scale[b] = d->scale[b]; p.shift[b] = d->shift[b];
@@ -438,6 +781,7 @@ extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
   p.dy = View{reinterpret_cast<const __nv_bfloat16*>(d->dy), d->dy_pitch};
   p.res = View{reinterpret_cast<const __nv_bfloat16*>(d->res), d->res_pitch};
   p.alpha = d->res_alpha;
+  p.alpha_dev = d->res_alpha_dev;
   p.dres = d->res ? reinterpret_cast<__nv_bfloat16*>(d->dres) : nullptr;
   p.dres_pitch = d->dres_pitch;
   p.dalpha = d->res ? d->dalpha : nullptr;
@@ -446,26 +790,42 @@ extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
   p.s1 = d->s1;
   p.inv_count = 1.0 / (double)d->pixels;
   cudaStream_t s = (cudaStream_t)stream;
-  YV6_CHECK_CUDA(cudaMemsetAsync(d->s1, 0, sizeof(double) * d->C, s));
-  for (int b = 0; b < d->nb; ++b) YV6_CHECK_CUDA(cudaMemsetAsync(d->s2[b], 0, sizeof(double) * d->C, s));
-  if (p.dalpha) YV6_CHECK_CUDA(cudaMemsetAsync(p.dalpha, 0, sizeof(double), s));
-  const int cgs = d->C / 8;
-  const int rows = std::max(1, kTrThreads / cgs);
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((d->pixels + rows - 1) / rows, (int64_t)h->num_sms * 8));
-  const size_t red_smem = sizeof(double) * (1 + d->nb) * d->C;
-  static bool configured = false;
-  if (!configured) {
-    YV6_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * (int)sizeof(double)));
-    configured = true;
+  // scratch of the two-pass scheme: caller-provided (training engine: one arena zeroed once per step) or the handle's
+  if (d->work != nullptr) {
+    YV6_REQUIRE(d->counter && d->coef, "bn_bwd: work without counter / coef");
+    p.work = d->work; p.counter = d->counter; p.coef = d->coef;
+  } else {
+    char* base = reinterpret_cast<char*>(h->scratch);
+    p.work = reinterpret_cast<double*>(base);
+    p.coef = reinterpret_cast<float*>(base + sizeof(double) * 3 * 2048);
+    p.counter = reinterpret_cast<unsigned int*>(base + sizeof(double) * 3 * 2048 + sizeof(float) * 6 * 2048);
   }
-  bn_bwd_reduce_kernel<<<grid, cgs * rows, red_smem, s>>>(p);
-  bn_bwd_apply_kernel<<<grid_for(d->pixels * cgs, kTrThreads, h->num_sms), kTrThreads, 0, s>>>(p);
+  if (d->work == nullptr || !d->zeroed) {
+    YV6_CHECK_CUDA(cudaMemsetAsync(d->s1, 0, sizeof(double) * d->C, s));
+    YV6_CHECK_CUDA(cudaMemsetAsync(p.work, 0, sizeof(double) * d->nb * d->C, s));
+    YV6_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s));
+    if (p.dalpha) YV6_CHECK_CUDA(cudaMemsetAsync(p.dalpha, 0, sizeof(double), s));
+  }
+  const int threads = chan_threads(d->C);
+  const size_t smem = sizeof(float) * (size_t)(threads / (d->C / 8)) * d->C;
+  const unsigned grid_r = chan_grid(d->pixels, d->C, h->num_sms, 4), grid_a = chan_grid(d->pixels, d->C, h->num_sms, 16);
+  if (d->nb == 1) {
+    bn_bwd_reduce_kernel<1><<<grid_r, threads, smem, s>>>(p);
+    bn_bwd_apply_kernel<1><<<grid_a, threads, 0, s>>>(p);
+  } else if (d->nb == 2) {
+    bn_bwd_reduce_kernel<2><<<grid_r, threads, smem, s>>>(p);
+    bn_bwd_apply_kernel<2><<<grid_a, threads, 0, s>>>(p);
+  } else {
+    bn_bwd_reduce_kernel<3><<<grid_r, threads, smem, s>>>(p);
+    bn_bwd_apply_kernel<3><<<grid_a, threads, 0, s>>>(p);
+  }
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }
 
 extern "C" int yv6_head_grad_prep(yv6_handle* h, const float* grad, const float* scores_or_null, int32_t B, int32_t A, int32_t ch,
                                   int32_t level_off, int32_t level_hw, int32_t ch_pad, void* out_bf16, void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && grad && out_bf16 && ch_pad >= ch, "head_grad_prep: bad argument");
   const int64_t total = (int64_t)B * level_hw * ch_pad;
   head_grad_prep_kernel<<<grid_for(total, kTrThreads, h->num_sms), kTrThreads, 0, (cudaStream_t)stream>>>(
@@ -477,6 +837,7 @@ extern "C" int yv6_head_grad_prep(yv6_handle* h, const float* grad, const float*
 extern "C" int yv6_maxpool5_bwd(yv6_handle* h, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, int32_t N,
                                 int32_t H, int32_t W, int32_t C, float* dx_scratch, void* dx, int64_t dx_pitch, int32_t accumulate,
                                 void* stream) {
+  yv6_device_guard _dev(h);
   YV6_REQUIRE(h && x && dy && dx_scratch && dx, "maxpool5_bwd: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t total = (int64_t)N * H * W * C;
@@ -490,15 +851,50 @@ extern "C" int yv6_maxpool5_bwd(yv6_handle* h, const void* x, int64_t x_pitch, c
   return YV6_OK;
 }
 
+extern "C" int yv6_stem_wgrad2(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy3, int64_t dy3_pitch,
+                               const void* dy1, int64_t dy1_pitch, int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw3, float* dw1,
+                               int32_t zeroed, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && x && dy3 && dw3 && Cout >= 8 && Cout <= 64 && Cout % 8 == 0, "stem_wgrad: bad argument");
+  YV6_REQUIRE(dy3_pitch % 8 == 0 && (!dy1 || (dw1 && dy1_pitch % 8 == 0)), "stem_wgrad: dY pitch / dW1");
+  if (int rc = configure_train(h)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!zeroed) {
+    YV6_CHECK_CUDA(cudaMemsetAsync(dw3, 0, sizeof(float) * 27 * Cout, s));
+    if (dy1) YV6_CHECK_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * 3 * Cout, s));
+  }
+  const int threads = (kTrThreads / Cout) * Cout;
+  const size_t smem = sizeof(float) * kSwPatchFloats + (size_t)(dy1 ? 2 : 1) * kSwTH * kSwTW * Cout * sizeof(__nv_bfloat16);
+  stem_wgrad_kernel<<<h->num_sms * 2, threads, smem, s>>>(x, x_dtype == YV6_DT_U8, in_scale,
+                                                          View{reinterpret_cast<const __nv_bfloat16*>(dy3), dy3_pitch},
+                                                          View{reinterpret_cast<const __nv_bfloat16*>(dy1), dy1_pitch}, N, H, W, Cout, dw3, dw1);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
+
 extern "C" int yv6_stem_wgrad(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy, int64_t dy_pitch,
                               int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw, void* stream) {
-  YV6_REQUIRE(h && x && dy && dw && Cout <= 64, "stem_wgrad: bad argument");
-  cudaStream_t s = (cudaStream_t)stream;
-  YV6_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * Cout, s));
-  const int threads = 27 * 9;  // 9 pixel lanes x 27 taps
-  stem_wgrad_kernel<<<h->num_sms * 4, threads, sizeof(float) * 27 * Cout, s>>>(x, x_dtype == YV6_DT_U8, in_scale,
-                                                                               reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, N, H, W,
-                                                                               Cout, dw);
+  return yv6_stem_wgrad2(h, x, x_dtype, in_scale, dy, dy_pitch, nullptr, 0, N, H, W, Cout, dw, nullptr, 0, stream);
+}
+
+extern "C" int yv6_xform(yv6_handle* h, const yv6_xform_seg* segs_dev, const int32_t* chunk_seg_dev, const int32_t* chunk_first_dev,
+                         int32_t n_chunks, int32_t accumulate, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && segs_dev && chunk_seg_dev && chunk_first_dev && n_chunks >= 0, "xform: bad argument");
+  if (n_chunks == 0) return YV6_OK;
+  xform_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(segs_dev, chunk_seg_dev, chunk_first_dev, accumulate);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}
+
+extern "C" int yv6_sgd_ema_step(yv6_handle* h, float* param, const float* grad, float* momentum_buf, float* ema_or_null,
+                                const uint8_t* group_per4, int64_t n, const float* hyper_dev, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && param && grad && momentum_buf && group_per4 && hyper_dev && n >= 0 && n % 4 == 0, "sgd_ema_step: bad argument");
+  if (n == 0) return YV6_OK;
+  const int64_t n4 = n / 4;
+  const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)h->num_sms * 16);
+  sgd_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, ema_or_null, group_per4, n4, hyper_dev);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }

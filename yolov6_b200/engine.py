@@ -41,7 +41,9 @@ class InferEngine:
         self.handle = _lib.handle(device.index or 0)
         self.lib = _lib.lib()
         self.weights = {}     # op index -> dict(w=..., bias=..., alpha=...)
-        self._plans = {}
+        self._plans = {}      # (N, H, W, dtype) -> plan, least recently used first; bounded (rect-shaped evaluation
+        self.max_plans = 4    # would otherwise keep one full activation set per distinct shape)
+        self._pinned = set()  # shapes captured into CUDA graphs (their buffers must outlive the graph)
         self._pack(state_dict)
 
     # ------------------------------------------------------------------ weight packing
@@ -73,7 +75,14 @@ class InferEngine:
     def _plan(self, N, H, W, in_dtype):
         key = (N, H, W, in_dtype)
         if key in self._plans:
-            return self._plans[key]
+            plan = self._plans.pop(key)
+            self._plans[key] = plan          # most recently used last
+            return plan
+        while len(self._plans) >= self.max_plans:
+            victim = next((k for k in self._plans if k not in self._pinned), None)
+            if victim is None:
+                break
+            del self._plans[victim]
         g, dev, P = self.g, self.device, self.nsplit
         maxs = max(g.strides)
         if H % maxs or W % maxs:
@@ -167,6 +176,11 @@ class InferEngine:
                 plan["calls"].append(("pool", (buf.data_ptr(), N, h, w, op.cin, ct, P, buf.stride(0) if P == 3 else 0)))
         self._plans[key] = plan
         return plan
+
+    def pin(self, N, H, W, in_dtype=torch.float32):
+        """Keep the buffers of this shape for the engine's lifetime (they are referenced by a captured CUDA graph)."""
+        self._plan(N, H, W, in_dtype)
+        self._pinned.add((N, H, W, in_dtype))
 
     # ------------------------------------------------------------------ execution
     def launch_count(self, N, H, W, in_dtype=torch.float32):

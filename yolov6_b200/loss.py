@@ -57,10 +57,21 @@ class ComputeLoss:
 
     def __call__(self, outputs, targets, epoch_num, step_num, batch_height, batch_width):
         feats, pred_scores, pred_distri = outputs
+        sizes = [tuple(f.shape[2:]) for f in feats]
+        state = self.forward_backward(pred_scores, pred_distri, sizes, targets, epoch_num, batch_height, batch_width)
+        loss = _DetLossFn.apply(pred_scores, pred_distri, state)
+        return loss, state["out"][1:4].detach().clone()
+
+    def forward_backward(self, pred_scores, pred_distri, sizes, targets, epoch_num, batch_height, batch_width, max_gt=None,
+                         grad_scores=None, grad_distri=None, grad_scale=1.0):
+        """Loss value and its gradients w.r.t. the head outputs in one pass (no autograd): returns
+        {"out": float64[8] (loss, iou, dfl, cls, target_scores_sum, num_pos), "grad_scores", "grad_distri", "gt_count"}.
+        `max_gt` fixes the padded target count G (static shapes for CUDA-graph capture; images with more boxes are
+        reported through gt_count > G); otherwise G is the largest per-image count, as in loss.py:184-192 (one small
+        host read when `targets` lives on the device).  `grad_*` let the caller provide the output buffers."""
         dev = pred_scores.device
         if dev.type != "cuda":
             raise RuntimeError("yolov6_b200.ComputeLoss runs on CUDA tensors only (no CPU fallback)")
-        sizes = [tuple(f.shape[2:]) for f in feats]
         anchors, anchor_points, n_list, stride_t = self._get_anchors(sizes, dev)
         B, A, nc = pred_scores.shape
         R = pred_distri.shape[2]
@@ -68,10 +79,16 @@ class ComputeLoss:
         ps = pred_scores.detach().float().contiguous()
         pd = pred_distri.detach().float().contiguous()
         strides = stride_t.reshape(-1).contiguous()
-        # targets -> padded float64 gts (loss.py:184-192); G = n rows is an upper bound that needs no host sync
+        n = targets.shape[0]
+        if max_gt is not None:
+            G = max(int(max_gt), 1)
+        elif n == 0:
+            G = 1
+        else:   # loss.py:184-192 pads to the largest per-image count
+            img = targets[:, 0].detach()
+            valid = img[(img >= 0) & (img < B)].long()
+            G = max(int(torch.bincount(valid, minlength=1).max()), 1) if valid.numel() else 1
         tg = targets.detach().float().contiguous().to(dev)
-        n = tg.shape[0]
-        G = max(n, 1)
         gt = torch.empty(B, G, 5, dtype=torch.float64, device=dev)
         gt_count = torch.empty(B, dtype=torch.int32, device=dev)
         _lib.check(lib.yv6_targets_pad(h, _p(tg), n, B, G, float(batch_width), float(batch_height), _p(gt), _p(gt_count), sp))
@@ -85,8 +102,10 @@ class ComputeLoss:
             c = tal_compact(ps, pboxes, anchor_points, gt, mask, 13, 1.0, 6.0)
         self.last_assignment = c
         d = _lib.LossDesc()
-        grad_scores = torch.empty_like(ps)
-        grad_distri = torch.empty_like(pd)
+        if grad_scores is None:
+            grad_scores = torch.empty_like(ps)
+        if grad_distri is None:
+            grad_distri = torch.empty_like(pd)
         out = torch.zeros(8, dtype=torch.float64, device=dev)
         ws = torch.empty(int(lib.yv6_det_loss_workspace_bytes(B, A)), dtype=torch.uint8, device=dev)
         d.pred_scores, d.pred_distri, d.anc_points, d.strides = ps.data_ptr(), pd.data_ptr(), anchor_points.data_ptr(), strides.data_ptr()
@@ -94,10 +113,9 @@ class ComputeLoss:
         d.B, d.A, d.G, d.nc, d.reg_ch = B, A, G, nc, R
         d.iou_type = IOU_TYPES[self.iou_type]
         d.w_cls, d.w_iou, d.w_dfl = float(self.loss_weight['class']), float(self.loss_weight['iou']), float(self.loss_weight['dfl'])
-        d.grad_scale = 1.0
+        d.grad_scale = float(grad_scale)
         d.grad_scores, d.grad_distri, d.out = grad_scores.data_ptr(), grad_distri.data_ptr(), out.data_ptr()
         d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.yv6_det_loss(h, C.byref(d), sp))
-        state = {"grad_scores": grad_scores, "grad_distri": grad_distri, "out": out}
-        loss = _DetLossFn.apply(pred_scores, pred_distri, state)
-        return loss, out[1:4].detach().clone()
+        return {"grad_scores": grad_scores, "grad_distri": grad_distri, "out": out, "gt_count": gt_count, "G": G,
+                "keep": (ps, pd, gt, mask, pboxes, ws, tg)}

@@ -103,6 +103,7 @@ class Model(nn.Module):
         self.precision = "bf16"
         self._engine = None
         self._engine_key = None
+        self._weights_epoch = 0      # bumped by writers that bypass autograd's version counters (fused optimizer kernel)
 
     # graph is rebuilt on demand so that the pickled module stays small and version-proof
     @property
@@ -168,17 +169,26 @@ class Model(nn.Module):
     def engine(self):
         dev = next(self.parameters()).device
         key = (self.precision, str(dev), sum(p._version for p in self.parameters()) +
-               sum(b._version for b in self.buffers()))
+               sum(b._version for b in self.buffers()), self.__dict__.get("_weights_epoch", 0))
         if self._engine is None or self._engine_key != key:
             self._engine = InferEngine(self.graph, self.state_dict(), dev, self.precision)
             self._engine_key = key
         return self._engine
 
-    def train_engine(self):
+    def mark_weights_changed(self):
+        """Tell the model that its parameters were rewritten through raw device pointers (yv6_sgd_ema_step): the folded
+        inference engine is rebuilt on the next eval forward."""
+        self.__dict__["_weights_epoch"] = self.__dict__.get("_weights_epoch", 0) + 1
+
+    def train_engine(self, n_buckets=None, rebuild=False):
+        """The training engine of this model (train.py).  `n_buckets` > 1 splits the flat gradient buffer into that many
+        contiguous buckets, completed one after the other during the backward pass (overlapped all-reduce, dist.py)."""
         eng = self.__dict__.get("_train_engine")
-        if eng is None or eng.dev != next(self.parameters()).device:
+        stale = eng is not None and (eng.dev != next(self.parameters()).device or not eng.flat.valid() or
+                                     (n_buckets is not None and eng.n_buckets != n_buckets))
+        if eng is None or stale or rebuild:
             from .train import TrainEngine
-            eng = TrainEngine(self)
+            eng = TrainEngine(self, n_buckets or 1)
             self.__dict__["_train_engine"] = eng
         return eng
 
@@ -194,11 +204,13 @@ class Model(nn.Module):
             return [(feats, cls, reg), feats]
         export_mode = torch.onnx.is_in_onnx_export() or self.export
         eng = self.engine()
-        pred = eng.forward(x)
+        # the engine owns (and reuses) its output buffers; callers of the drop-in API get their own tensors, as with the
+        # reference's nn.Module (p1 = model(x1)[0]; p2 = model(x2)[0] must not alias).  DetectPipeline uses the engine directly.
+        pred = eng.forward(x).clone()
         if export_mode:
             return pred
         N, _, H, W = x.shape
-        return [pred, eng.feature_maps(N, H, W, x.dtype if x.dtype == torch.uint8 else torch.float32)]
+        return [pred, [f.clone() for f in eng.feature_maps(N, H, W, x.dtype if x.dtype == torch.uint8 else torch.float32)]]
 
 
 def build_model(cfg, num_classes, device, fuse_ab=False, distill_ns=False):

@@ -21,10 +21,16 @@ def _workspace(dev, nbytes):
     return buf
 
 
+def workspace_bytes(B, A, nc, multi_label):
+    return int(_lib.lib().yv6_nms_workspace_bytes(B, A, nc, 1 if (multi_label and nc > 1) else 0))
+
+
 def nms_batched(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-                max_det=300, stream=None):
-    """Raw batched form: returns (out [B,max_det,6], count [B] int32, src [B,max_det,2] int32 (anchor, class)),
-    all on the device, no host synchronisation."""
+                max_det=300, stream=None, workspace=None):
+    """Raw batched form: returns (out [B,max_det,6], count [B] int32, src [B,max_det,2] int32 (anchor, class),
+    overflow [1] int32), all on the device, no host synchronisation.  `workspace` (uint8 device tensor of at least
+    `workspace_bytes(...)`) lets a caller that captures the call into a CUDA graph own the scratch memory; eager calls
+    share one growable buffer per device."""
     if prediction.device.type != "cuda":
         raise RuntimeError("yolov6_b200.non_max_suppression runs on CUDA tensors only (no CPU fallback)")
     assert 0 <= conf_thres <= 1, f'conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided.'
@@ -38,7 +44,15 @@ def nms_batched(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnos
     lib = _lib.lib()
     ml = 1 if (multi_label and nc > 1) else 0
     nbytes = lib.yv6_nms_workspace_bytes(B, A, nc, ml)
-    ws = _workspace(dev, nbytes)
+    if workspace is not None:
+        if workspace.device != dev or workspace.numel() < nbytes:
+            raise RuntimeError(f"nms workspace too small ({workspace.numel()} < {nbytes} bytes) or on the wrong device")
+        ws = workspace
+    else:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("nms_batched inside a CUDA-graph capture needs a caller-owned `workspace` (the shared "
+                               "per-device buffer may be replaced later while the graph still points at it)")
+        ws = _workspace(dev, nbytes)
     out = torch.zeros(B, max_det, 6, dtype=torch.float32, device=dev)
     count = torch.zeros(B, dtype=torch.int32, device=dev)
     src = torch.zeros(B, max_det, 2, dtype=torch.int32, device=dev)
@@ -63,6 +77,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     out, count, _, overflow = nms_batched(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det)
     host = torch.cat([count, overflow]).tolist()          # the one host sync: detection counts
     if host[-1]:
-        raise RuntimeError("non_max_suppression: more than 65536 (anchor, class) candidates in one image; "
-                           "raise conf_thres (the reference keeps the 30000 best of them, nms.py:90-91)")
+        # images with more than 65536 candidates are reduced to their 30000 best on the device (nms.py:90-91); this
+        # remains only for > 65536 candidates whose scores agree to 8 significant bits (see csrc/yv6_nms.cu)
+        raise RuntimeError("non_max_suppression: more than 65536 near-identical candidate scores in one image; raise conf_thres")
     return [out[i, :host[i]] for i in range(out.shape[0])]

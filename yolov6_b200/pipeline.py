@@ -14,7 +14,7 @@ instead of their sum.
 """
 import torch
 
-from .nms import nms_batched
+from .nms import nms_batched, workspace_bytes
 
 
 class DetectPipeline:
@@ -39,6 +39,11 @@ class DetectPipeline:
         self.out_host = torch.zeros(batch, max_det, 6).pin_memory()
         self.count_host = torch.zeros(batch + 1, dtype=torch.int32).pin_memory()
         self.eng = model.engine()
+        self.eng.pin(batch, height, width, dt)          # the graph points at this shape's buffers
+        A = sum((height // int(s)) * (width // int(s)) for s in model.graph.strides)
+        nc = model.graph.num_classes
+        # scratch owned by this pipeline: a shared cache could be replaced (freed) while the graph still references it
+        self.nms_ws = torch.empty(workspace_bytes(batch, A, nc, multi_label), dtype=torch.uint8, device=self.dev)
         self.graph = None
         self._warm()
 
@@ -46,7 +51,7 @@ class DetectPipeline:
         if self.host_input and not self.overlap_h2d:
             self.x_dev.copy_(self.x_host, non_blocking=True)
         pred = self.eng.forward(self.x_dev)
-        out, count, src, overflow = nms_batched(pred, **self.kw)
+        out, count, src, overflow = nms_batched(pred, workspace=self.nms_ws, **self.kw)
         self.out_dev, self.count_dev = out, count
         if self.host_input:
             self.out_host.copy_(out, non_blocking=True)
@@ -91,7 +96,7 @@ class DetectPipeline:
         if self.host_input:
             counts = self.count_host.tolist()
             if counts[-1]:
-                raise RuntimeError("non_max_suppression: candidate overflow (> 65536 per image); raise conf_thres")
+                raise RuntimeError("non_max_suppression: more than 65536 near-identical candidate scores in one image; raise conf_thres")
             return [self.out_host[i, :counts[i]].clone() for i in range(self.out_host.shape[0])]
         counts = self.count_dev.tolist()
         return [self.out_dev[i, :counts[i]] for i in range(self.out_dev.shape[0])]
@@ -127,5 +132,5 @@ class DetectRing:
         counts = p.count_host.tolist()
         self.tail += 1
         if counts[-1]:
-            raise RuntimeError("non_max_suppression: candidate overflow (> 65536 per image); raise conf_thres")
+            raise RuntimeError("non_max_suppression: more than 65536 near-identical candidate scores in one image; raise conf_thres")
         return [p.out_host[j, :counts[j]].clone() for j in range(p.out_host.shape[0])]

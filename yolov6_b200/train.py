@@ -7,25 +7,35 @@ branches, common.py:245-255), this engine does by walking the same layer graph a
 engine (arch.py):
 
   forward : raw convs on tcgen05 (yv6_conv_fwd, bf16 operands, fp32 accumulate, no bias/act)
-            -> yv6_bn_stats / yv6_bn_finalize (batch statistics, running-stat update, eps 1e-3,
-            momentum 0.03 as set by initialize_weights, torch_utils.py:38-48)
+            -> yv6_bn_stats_finalize (batch statistics of all branches of a block + running-stat update in
+               one launch; eps 1e-3, momentum 0.03 as set by initialize_weights, torch_utils.py:38-48)
             -> yv6_bn_apply_fwd (sum of the BN-ed branches + activation, written into concat slices);
   backward: yv6_bn_bwd (activation + BatchNorm backward of all branches of a block in two passes)
             -> dgrad = yv6_conv_fwd with rotated / transposed weights, accumulating into the input
                gradient through the residual epilogue (stride-2 convs: four parity sub-convolutions)
             -> yv6_conv_wgrad (MN-major tcgen05 GEMM over pixels, fp32 split-K accumulation).
 
-Parameters stay fp32 `nn.Parameter`s of the Model (master weights); every step they are cast to bf16
-KRSC for the kernels, and gradients are written to `.grad` in the reference's tensor layouts so that the
-reference's optimizer / EMA / DDP all-reduce apply unchanged.  BottleRep shortcuts (M / L6,
-common.py:600-617) ride in the BN apply / backward kernels (y = act(z) + alpha * x).
+Step-level structure: everything is planned once per input shape -- activation, raw-conv and
+gradient buffers, one zero-initialised arena for all per-step accumulators (BatchNorm sums, fp32 KRSC weight
+gradients, counters), and a list of C-ABI descriptors for the forward and the backward pass -- so a step is
+    arena.zero_()  ->  yv6_xform (fp32 master weights -> every bf16 layout the kernels need, ONE launch)
+    ->  forward descriptors  ->  loss  ->  backward descriptors  ->  yv6_xform (gradients -> flat fp32 buffer)
+with no allocation, no host synchronisation and no per-layer PyTorch op; it can be captured in a CUDA graph
+(step.py).  Parameters are views of one flat fp32 buffer and gradients land in one flat fp32 buffer in the
+reference's tensor layouts (flat.py), laid out in the order the backward pass completes them, so the DDP
+gradient all-reduce (core/engine.py:464-466) is a few large NCCL calls that overlap the rest of the backward
+(dist.py) and SGD + EMA are one kernel (optim.py).  BottleRep shortcuts (M / L6, common.py:600-617) ride in
+the BN apply / backward kernels (y = act(z) + alpha * x, alpha read from device memory).
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT_CODES, DT_BF16, DT_F32, DT_U8, BnDesc, ConvDesc, StemDesc, WgradDesc
+from ._lib import (ACT_CODES, DT_BF16, DT_F32, DT_U8, XF_BF16, XF_F32, XF_F64, XFORM_CHUNK, BnDesc, BnStatsDesc, ConvDesc,
+                   StemDesc, WgradDesc, XformSeg)
+from .flat import FlatState
 
 BN_EPS, BN_MOMENTUM = 1e-3, 0.03
 
@@ -34,8 +44,74 @@ def _p(t):
     return t.data_ptr() if t is not None else 0
 
 
+def op_branches(op):
+    """(prefix, kernel size) of the conv branches of a BN-ed block; k = 0 marks RepVGG's identity BatchNorm."""
+    if op.layout == "rep":
+        br = [(op.name + ".rbr_dense", 3), (op.name + ".rbr_1x1", 1)]
+        if op.kind != "stem" and op.cin == op.cout and op.s == 1:
+            br.append((op.name + ".rbr_identity", 0))
+        return br
+    return [(op.name + ".block", op.k)]
+
+
+def op_param_names(op):
+    """Trainable parameters owned by a graph op, in the order their gradients are produced."""
+    if op.kind == "pool":
+        return []
+    if op.kind == "pred":
+        return [op.name + ".weight", op.name + ".bias"]
+    if op.kind == "convT":
+        return [op.name + ".upsample_transpose.weight", op.name + ".upsample_transpose.bias"]
+    names = []
+    for prefix, k in op_branches(op):
+        bn = prefix + (".bn" if k else "")
+        if k:
+            names.append(prefix + ".conv.weight")
+        names += [bn + ".weight", bn + ".bias"]
+    if op.alpha:
+        names.append(op.alpha)
+    return names
+
+
+class XformTable:
+    """Device tables of one yv6_xform launch."""
+
+    def __init__(self, segs, dev):
+        self.n = len(segs)
+        arr = (XformSeg * max(self.n, 1))(*segs)
+        raw = np.frombuffer(arr, dtype=np.uint8).copy()
+        self.segs = torch.from_numpy(raw).to(dev)
+        chunk_seg, chunk_first = [], []
+        for i, s in enumerate(segs):
+            total = s.n[0] * s.n[1] * s.n[2] * s.n[3]
+            chunk_first.append(len(chunk_seg))
+            chunk_seg += [i] * ((total + XFORM_CHUNK - 1) // XFORM_CHUNK)
+        self.n_chunks = len(chunk_seg)
+        self.chunk_seg = torch.tensor(chunk_seg or [0], dtype=torch.int32).to(dev)
+        self.chunk_first = torch.tensor(chunk_first or [0], dtype=torch.int32).to(dev)
+
+    def launch(self, lib, h, accumulate, sp):
+        if self.n_chunks:
+            _lib.check(lib.yv6_xform(h, self.segs.data_ptr(), self.chunk_seg.data_ptr(), self.chunk_first.data_ptr(), self.n_chunks,
+                                     int(bool(accumulate)), sp))
+
+
+def _seg(dst, src, n, ds, ss, dst_dtype, src_dtype):
+    s = XformSeg()
+    s.dst, s.src = dst, src
+    n, ds, ss = list(n), list(ds), list(ss)
+    while len(n) < 4:
+        n.insert(0, 1)
+        ds.insert(0, 0)
+        ss.insert(0, 0)
+    for i in range(4):
+        s.n[i], s.ds[i], s.ss[i] = int(n[i]), int(ds[i]), int(ss[i])
+    s.dst_dtype, s.src_dtype = dst_dtype, src_dtype
+    return s
+
+
 class TrainEngine:
-    def __init__(self, model):
+    def __init__(self, model, n_buckets=1):
         self.model = model
         self.g = model.graph
         self.dev = next(model.parameters()).device
@@ -43,17 +119,210 @@ class TrainEngine:
             raise RuntimeError("yolov6_b200 training runs on sm_100a CUDA kernels only (no CPU fallback)")
         self.lib = _lib.lib()
         self.h = _lib.handle(self.dev.index or 0)
-        self.params = dict(model.named_parameters())
-        self.buffers_ = dict(model.named_buffers())
-        self._shape = None
+        self.n_buckets = max(1, int(n_buckets))
         self.debug = False      # tests: snapshot the incoming gradient of every op into self.dbg[op index]
         self.dbg = {}
+        self._shape = None
+        self.bucket_hook = None     # callable(k) invoked (eager mode) right after bucket k's gradients are unpacked
+        self._build_state()
 
-    # ------------------------------------------------------------------ helpers
-    def _conv(self, x, x_off, cin, w, y, y_off, cout, k, stride, *, pad=None, out_hw=None, bias=None, act=None,
-              y_strides=None, y_elem_off=0, accumulate=False, y_f32=False):
-        """y[..., y_off:+cout] (+)= conv(x[..., x_off:+cin], w) via the C ABI.  x: [N,H,W,Ct] bf16,
-        w: [cout,kh,kw,cin] bf16 KRSC, y: [N,Ho,Wo,Cyt] bf16 (or fp32 head tensor with explicit strides)."""
+    # ================================================================== parameter-level state (shape independent)
+    def _build_state(self):
+        g, dev = self.g, self.dev
+        order = [n for op in reversed(g.ops) for n in op_param_names(op)]
+        self.flat = FlatState(self.model, order)
+        self.params = dict(self.model.named_parameters())
+        self.buffers_ = dict(self.model.named_buffers())
+        fl = self.flat
+        # ---- zero arena layout: per-step accumulators (float64 sums, counters, fp32 KRSC weight gradients)
+        zoff, ztot = {}, 0
+
+        def ztake(key, nbytes):
+            nonlocal ztot
+            zoff[key] = ztot
+            ztot += (int(nbytes) + 15) // 16 * 16
+
+        for i, op in enumerate(g.ops):
+            if op.kind == "pool":
+                continue
+            if op.kind == "pred":
+                chp = (op.cout + 15) // 16 * 16
+                ztake((i, "bsum"), 16 * chp)
+                ztake((i, "bcnt"), 16)
+                ztake((i, "dw"), 4 * op.cout * op.cin)
+            elif op.kind == "convT":
+                ztake((i, "bsum"), 16 * op.cout)
+                ztake((i, "bcnt"), 16)
+                ztake((i, "dw"), 4 * 4 * op.cout * op.cin)
+            else:
+                br = op_branches(op)
+                nb, c = len(br), op.cout
+                ztake((i, "fsum"), 16 * nb * c)
+                ztake((i, "fcnt"), 16)
+                ztake((i, "s1"), 8 * c)
+                ztake((i, "work"), 8 * nb * c)
+                ztake((i, "s2"), 8 * nb * c)
+                ztake((i, "dalpha"), 16)
+                ztake((i, "bcnt"), 16)
+                for b, (prefix, k) in enumerate(br):
+                    if k == 0:
+                        continue
+                    if op.kind == "stem":
+                        ztake((i, "dw", b), 4 * op.cout * (27 if k == 3 else 3))
+                    else:
+                        ztake((i, "dw", b), 4 * op.cout * k * k * op.cin)
+        self.zero_arena = torch.zeros(ztot, dtype=torch.uint8, device=dev)
+        zbase = self.zero_arena.data_ptr()
+        self._z = lambda *key: zbase + zoff[key]
+        # ---- per-op fp32 outputs that need no clearing: BN statistics [nb][4][C] and backward coefficients [nb][2][C]
+        self.stat_out, self.coef_out = {}, {}
+        # ---- packed weights + the two xform tables
+        pack, self.ctx, self.wts = [], [None] * len(g.ops), {}
+        grad_segs, self.bucket_of_op = [], {}
+        P = self.params
+
+        def bf16(*shape):
+            return torch.zeros(*shape, dtype=torch.bfloat16, device=dev)
+
+        for i, op in enumerate(g.ops):
+            if op.kind == "pool":
+                continue
+            W = self.wts[i] = {}
+            if op.kind == "pred":
+                ch, cin, chp = op.cout, op.cin, (op.cout + 15) // 16 * 16
+                W["w"] = bf16(ch, 1, 1, cin)
+                W["bias"] = torch.zeros((ch + 255) // 256 * 256, dtype=torch.float32, device=dev)
+                W["wt"] = bf16(cin, 1, 1, chp)                                   # dgrad: [Cin][ch_pad], zero padded
+                wsrc, bsrc = fl.ptr(op.name + ".weight"), fl.ptr(op.name + ".bias")
+                pack.append(_seg(W["w"].data_ptr(), wsrc, [ch * cin], [1], [1], XF_BF16, XF_F32))
+                pack.append(_seg(W["bias"].data_ptr(), bsrc, [ch], [1], [1], XF_F32, XF_F32))
+                pack.append(_seg(W["wt"].data_ptr(), wsrc, [cin, ch], [chp, 1], [1, cin], XF_BF16, XF_F32))
+                self.ctx[i] = dict(w=W["w"])
+                continue
+            if op.kind == "convT":
+                co, ci = op.cout, op.cin
+                W["w"] = bf16(4, co, 1, 1, ci)                                   # quadrant q = dy*2+dx: [Cout][Cin]
+                W["wt"] = bf16(4, ci, 1, 1, co)                                  # dgrad of quadrant q: [Cin][Cout]
+                W["bias"] = torch.zeros((co + 255) // 256 * 256, dtype=torch.float32, device=dev)
+                wsrc = fl.ptr(op.name + ".upsample_transpose.weight")            # [Cin][Cout][2][2]
+                pack.append(_seg(W["w"].data_ptr(), wsrc, [4, co, ci], [co * ci, ci, 1], [1, 4, co * 4], XF_BF16, XF_F32))
+                pack.append(_seg(W["wt"].data_ptr(), wsrc, [4, ci, co], [ci * co, co, 1], [1, co * 4, 4], XF_BF16, XF_F32))
+                pack.append(_seg(W["bias"].data_ptr(), fl.ptr(op.name + ".upsample_transpose.bias"), [co], [1], [1], XF_F32, XF_F32))
+                self.ctx[i] = dict(w=[W["w"][q] for q in range(4)])
+                continue
+            # ---- BN-ed blocks
+            br = op_branches(op)
+            nb, co, ci = len(br), op.cout, op.cin
+            self.stat_out[i] = torch.zeros(nb, 4, co, dtype=torch.float32, device=dev)
+            self.coef_out[i] = torch.zeros(nb, 2, co, dtype=torch.float32, device=dev)
+            W["br"] = []
+            for b, (prefix, k) in enumerate(br):
+                ent = dict(prefix=prefix, k=k, w=None)
+                if k == 0:
+                    W["br"].append(ent)
+                    continue
+                wsrc = fl.ptr(prefix + ".conv.weight")                           # [Cout][Cin][k][k]
+                if op.kind == "stem":
+                    ent["w"] = torch.zeros(3, 3, 3, co, dtype=torch.float32, device=dev)   # [r][s][c][Cout], fp32 math
+                    if k == 3:
+                        pack.append(_seg(ent["w"].data_ptr(), wsrc, [9, 3, co], [3 * co, co, 1], [1, 9, 27], XF_F32, XF_F32))
+                    else:       # 1x1 stride-2 branch = centre tap of a 3x3 stride-2 conv
+                        pack.append(_seg(ent["w"].data_ptr() + 4 * (4 * 3 * co), wsrc, [3, co], [co, 1], [1, 3], XF_F32, XF_F32))
+                    W["br"].append(ent)
+                    continue
+                kk = k * k
+                ent["w"] = bf16(co, k, k, ci)                                    # forward: KRSC
+                pack.append(_seg(ent["w"].data_ptr(), wsrc, [co, kk, ci], [kk * ci, ci, 1], [ci * kk, 1, kk], XF_BF16, XF_F32))
+                if op.s == 1:   # dgrad = conv with the 180-degree rotated, transposed filter [Cin][k][k][Cout]
+                    ent["wt"] = [bf16(ci, k, k, co)]
+                    pack.append(_seg(ent["wt"][0].data_ptr(), wsrc + 4 * (kk - 1), [ci, kk, co], [kk * co, co, 1], [kk, -1, ci * kk],
+                                     XF_BF16, XF_F32))
+                elif k == 1:    # 1x1 stride 2 touches even positions only
+                    ent["wt"] = [bf16(ci, 1, 1, co)]
+                    pack.append(_seg(ent["wt"][0].data_ptr(), wsrc, [ci, co], [co, 1], [1, ci], XF_BF16, XF_F32))
+                else:           # 3x3 stride 2: the input gradient at parity (ph, pw) is a 1- or 2-tap stride-1 conv
+                    ent["wt"] = []
+                    for ph in range(2):
+                        for pw in range(2):
+                            r0, dr, nr = (1, 0, 1) if ph == 0 else (2, -2, 2)    # tap t reads dc[i + t]: W[2] at t=0, W[0] at t=1
+                            c0, dc, ncol = (1, 0, 1) if pw == 0 else (2, -2, 2)
+                            wt = bf16(ci, nr, ncol, co)
+                            pack.append(_seg(wt.data_ptr(), wsrc + 4 * (r0 * 3 + c0), [ci, nr, ncol, co],
+                                             [nr * ncol * co, ncol * co, co, 1], [9, 3 * dr, dc, ci * 9], XF_BF16, XF_F32))
+                            ent["wt"].append(wt)
+                W["br"].append(ent)
+            self.ctx[i] = dict(branches=[dict(prefix=e["prefix"], k=e["k"], w=e["w"], x=None) for e in W["br"]])
+        self.pack_table = XformTable(pack, dev)
+
+        # ---- gradient unpack table, in backward order = flat gradient order; buckets = contiguous op ranges
+        ops_with_params = [i for i in range(len(g.ops) - 1, -1, -1) if op_param_names(g.ops[i])]
+        total = fl.n_train
+        bounds, acc, k = [], 0, 0
+        per_bucket = [[] for _ in range(self.n_buckets)]
+        self.bucket_range = []
+        lo = 0
+        for i in ops_with_params:
+            op = g.ops[i]
+            segs = self._grad_segs(i, op)
+            size = sum(fl.slots[n][1] for n in op_param_names(op))
+            per_bucket[k].extend(segs)
+            self.bucket_of_op[i] = k
+            acc += size
+            if k < self.n_buckets - 1 and acc >= total * (k + 1) / self.n_buckets:
+                hi = fl.slots[op_param_names(op)[-1]][0] + (fl.slots[op_param_names(op)[-1]][1] + 3) // 4 * 4
+                self.bucket_range.append((lo, hi))
+                lo = hi
+                k += 1
+        self.bucket_range.append((lo, total))
+        while len(self.bucket_range) < self.n_buckets:
+            self.bucket_range.append((total, total))
+        self.grad_tables = [XformTable(s, dev) for s in per_bucket]
+        self.last_op_of_bucket = {}
+        for i in ops_with_params:
+            self.last_op_of_bucket[self.bucket_of_op[i]] = i      # ops are visited in backward order: the last one wins
+        self._zero_bytes = ztot
+
+    def _grad_segs(self, i, op):
+        """xform segments that move op i's gradients (fp32 KRSC arena / float64 sums) into the flat gradient buffer."""
+        fl, z = self.flat, self._z
+        segs = []
+        if op.kind == "pred":
+            ch, cin = op.cout, op.cin
+            segs.append(_seg(fl.grad_ptr(op.name + ".weight"), z(i, "dw"), [ch * cin], [1], [1], XF_F32, XF_F32))
+            segs.append(_seg(fl.grad_ptr(op.name + ".bias"), z(i, "bsum"), [ch], [1], [1], XF_F32, XF_F64))
+            return segs
+        if op.kind == "convT":
+            co, ci = op.cout, op.cin
+            segs.append(_seg(fl.grad_ptr(op.name + ".upsample_transpose.weight"), z(i, "dw"), [ci, co, 4], [co * 4, 4, 1],
+                             [1, ci, co * ci], XF_F32, XF_F32))
+            segs.append(_seg(fl.grad_ptr(op.name + ".upsample_transpose.bias"), z(i, "bsum"), [co], [1], [1], XF_F32, XF_F64))
+            return segs
+        br = op_branches(op)
+        co, ci = op.cout, op.cin
+        for b, (prefix, k) in enumerate(br):
+            bn = prefix + (".bn" if k else "")
+            if k:
+                if op.kind == "stem":
+                    if k == 3:      # dw3 [Cout][(r*3+s)*3 + c] -> [Cout][c][r][s]
+                        segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co, 3, 9], [27, 9, 1], [27, 1, 3],
+                                         XF_F32, XF_F32))
+                    else:
+                        segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co * 3], [1], [1], XF_F32, XF_F32))
+                else:
+                    kk = k * k      # dw [Cout][kk][Cin] -> [Cout][Cin][kk]
+                    segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co, ci, kk], [ci * kk, kk, 1],
+                                     [kk * ci, 1, ci], XF_F32, XF_F32))
+            segs.append(_seg(fl.grad_ptr(bn + ".weight"), z(i, "s2") + 8 * b * co, [co], [1], [1], XF_F32, XF_F64))   # dgamma = sum dz * xhat
+            segs.append(_seg(fl.grad_ptr(bn + ".bias"), z(i, "s1"), [co], [1], [1], XF_F32, XF_F64))                 # dbeta = sum dz
+        if op.alpha:
+            segs.append(_seg(fl.grad_ptr(op.alpha), z(i, "dalpha"), [1], [1], [1], XF_F32, XF_F64))
+        return segs
+
+    # ================================================================== per-shape plan
+    def _conv_desc(self, x, x_off, cin, w, y, y_off, cout, k, stride, *, pad=None, out_hw=None, bias=None, act=None,
+                   y_strides=None, y_elem_off=0, accumulate=False, y_f32=False):
+        """y[..., y_off:+cout] (+)= conv(x[..., x_off:+cin], w).  x: [N,H,W,Ct] bf16, w: [cout,kh,kw,cin] bf16 KRSC,
+        y: [N,Ho,Wo,Cyt] bf16 (or fp32 head tensor with explicit strides)."""
         d = ConvDesc()
         N, H, W, Ct = x.shape
         d.x = x.data_ptr() + x_off * 2
@@ -77,9 +346,9 @@ class TrainEngine:
             d.res = d.y
             d.alpha = 1.0
             d.res_img_stride, d.res_h_stride, d.res_w_stride = y_strides
-        _lib.check(self.lib.yv6_conv_fwd(self.h, C.byref(d), _lib.stream_ptr()))
+        return d
 
-    def _wgrad(self, x, x_off, cin, dy, dy_off, cout, k, stride, dw):
+    def _wgrad_desc(self, x, x_off, cin, dy, dy_off, cout, k, stride, dw_ptr):
         d = WgradDesc()
         N, H, W, Ct = x.shape
         d.x = x.data_ptr() + x_off * 2
@@ -88,39 +357,56 @@ class TrainEngine:
         d.Cout, d.dy_c_total = cout, dy.shape[3]
         d.kh = d.kw = k
         d.stride, d.pad = stride, k // 2
-        d.dw = dw.data_ptr()
-        _lib.check(self.lib.yv6_conv_wgrad(self.h, C.byref(d), _lib.stream_ptr()))
+        d.dw = dw_ptr
+        return d
 
-    def _stats(self, t, c_off, c):
-        s = torch.empty(2, c, dtype=torch.float64, device=self.dev)
-        N, H, W, Ct = t.shape
-        _lib.check(self.lib.yv6_bn_stats(self.h, t.data_ptr() + c_off * 2, N * H * W, c, Ct, s[0].data_ptr(), s[1].data_ptr(),
-                                         _lib.stream_ptr()))
-        return s
+    def _stats_desc(self, xs, c, pixels, sums_ptr, cnt_ptr, finalize=None):
+        """xs: [(tensor, channel offset)]; finalize: [(bn prefix, stats tensor [4][C])] or None (sums only)."""
+        d = BnStatsDesc()
+        d.nb, d.C, d.pixels = len(xs), c, pixels
+        for b, (t, off) in enumerate(xs):
+            d.x[b] = t.data_ptr() + off * 2
+            d.x_pitch[b] = t.shape[3]
+        d.sums, d.counter, d.zeroed = sums_ptr, cnt_ptr, 1
+        d.eps, d.momentum = BN_EPS, BN_MOMENTUM
+        if finalize is not None:
+            fl = self.flat
+            for b, (prefix, st) in enumerate(finalize):
+                d.gamma[b], d.beta[b] = fl.ptr(prefix + ".weight"), fl.ptr(prefix + ".bias")
+                d.running_mean[b], d.running_var[b] = fl.ptr(prefix + ".running_mean"), fl.ptr(prefix + ".running_var")
+                d.stats[b] = st.data_ptr()
+        return d
 
-    def _finalize(self, stats, count, prefix, c):
-        """-> dict(mean, invstd, scale, shift) fp32 [C]; updates the running stats of BatchNorm `prefix`."""
-        out = torch.empty(4, c, dtype=torch.float32, device=self.dev)
-        g, b = self.params[prefix + ".weight"], self.params[prefix + ".bias"]
-        rm, rv = self.buffers_[prefix + ".running_mean"], self.buffers_[prefix + ".running_var"]
-        _lib.check(self.lib.yv6_bn_finalize(self.h, stats[0].data_ptr(), stats[1].data_ptr(), float(count), g.data_ptr(), b.data_ptr(),
-                                            BN_EPS, BN_MOMENTUM, rm.data_ptr(), rv.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
-                                            out[2].data_ptr(), out[3].data_ptr(), c, _lib.stream_ptr()))
-        self.buffers_[prefix + ".num_batches_tracked"].add_(1)
+    def _dgrad_descs(self, dc, ent, k, stride, gsrc, g_off, cin):
+        """g(src)[..., g_off:+cin] += conv_transpose(dc, w) as one (stride 1) or up to four (stride 2) accumulating convs."""
+        cout = dc.shape[3]
+        if stride == 1:
+            return [self._conv_desc(dc, 0, cout, ent["wt"][0], gsrc, g_off, cin, k, 1, accumulate=True)]
+        n, hs, ws, gct = gsrc.shape
+        ho, wo = dc.shape[1], dc.shape[2]
+        out = []
+        j = 0
+        for ph in range(2):
+            for pw in range(2):
+                if k == 1:
+                    if ph or pw:
+                        continue
+                    wt = ent["wt"][0]
+                else:
+                    wt = ent["wt"][j]
+                    j += 1
+                out.append(self._conv_desc(dc, 0, cout, wt, gsrc, g_off, cin, k, 1, pad=(0, 0), out_hw=(ho, wo), accumulate=True,
+                                           y_strides=(hs * ws * gct, 2 * ws * gct, 2 * gct), y_elem_off=(ph * ws + pw) * gct))
         return out
 
-    @staticmethod
-    def _krsc(w):
-        """torch conv weight [Cout,Cin,kh,kw] fp32 -> bf16 KRSC."""
-        return w.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
-
-    # ------------------------------------------------------------------ buffers
-    def _alloc(self, N, H, W):
-        if self._shape == (N, H, W):
+    def _plan(self, N, H, W, in_dtype):
+        key = (N, H, W, in_dtype)
+        if self._shape == key:
             return
-        self._shape = (N, H, W)
-        g, dev = self.g, self.dev
-        self.bufs = [torch.zeros(N, H >> b.level, W >> b.level, b.c_total, dtype=torch.bfloat16, device=dev) for b in g.bufs]
+        self._shape = key
+        g, dev, fl, z = self.g, self.dev, self.flat, self._z
+        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)   # noqa: E731
+        self.bufs = [bf(N, H >> b.level, W >> b.level, b.c_total) for b in g.bufs]
         self.gbufs = [torch.zeros_like(t) for t in self.bufs]
         self.sizes = [(H // s, W // s) for s in g.strides]
         self.offs = [0]
@@ -129,263 +415,278 @@ class TrainEngine:
         A = self.offs[-1]
         self.cls = torch.empty(N, A, g.num_classes, dtype=torch.float32, device=dev)
         self.reg = torch.empty(N, A, 4 * (g.reg_max + 1), dtype=torch.float32, device=dev)
-
-    def _view(self, t):
-        return self.bufs[t.buf], self.gbufs[t.buf]
-
-    # ------------------------------------------------------------------ forward
-    def forward(self, x):
-        """x [N,3,H,W] fp32 in [0,1] (or uint8).  Returns (cls [N,A,nc] post-sigmoid, reg [N,A,R]) fp32."""
-        x = x.contiguous()
-        N, _, H, W = x.shape
-        self._alloc(N, H, W)
-        self.x = x
-        self.ctx = []
-        P = self.params
-        for i, op in enumerate(self.g.ops):
+        self.grad_cls = torch.zeros_like(self.cls)
+        self.grad_reg = torch.zeros_like(self.reg)
+        self.x_static = torch.zeros(N, 3, H, W, dtype=in_dtype, device=dev)   # the stem reads this buffer (graph-stable address)
+        view = lambda t: (self.bufs[t.buf], self.gbufs[t.buf])   # noqa: E731
+        # shared scratch: BN-backward outputs (gradients w.r.t. the raw conv outputs) live only until their dgrad / wgrad ran
+        dc_elems = max([N * (H >> g.bufs[op.dst.buf].level) * (W >> g.bufs[op.dst.buf].level) * op.cout
+                        for op in g.ops if op.kind in ("conv", "stem")] + [1])
+        dc_pool = [torch.zeros(dc_elems, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        pool_scr, dq_pool = None, None
+        fwd, bwd_rev = [], []        # bwd_rev[j] = list of calls of op j (assembled in reverse op order afterwards)
+        x_dt = DT_U8 if in_dtype == torch.uint8 else DT_F32
+        for i, op in enumerate(g.ops):
+            calls = []
             if op.kind == "pool":
-                buf, _ = self._view(op.dst)
-                n, h, w, ct = buf.shape
-                _lib.check(self.lib.yv6_sppf_pool(self.h, buf.data_ptr(), n, h, w, op.cin, ct, 1, 0, _lib.stream_ptr()))
-                self.ctx.append(None)
-                continue
-            if op.kind == "pred":
-                src, _ = self._view(op.src)
-                which, lvl = op.head
-                out = self.cls if which == "cls" else self.reg
-                ch = out.shape[2]
-                lh, lw = self.sizes[lvl]
-                A = self.offs[-1]
-                w = self._krsc(P[op.name + ".weight"])
-                bias = torch.zeros((op.cout + 255) // 256 * 256, dtype=torch.float32, device=self.dev)
-                bias[:op.cout] = P[op.name + ".bias"].detach()
-                self._conv(src, op.src.c_off, op.cin, w, out, 0, op.cout, 1, 1, bias=bias, act=op.act, y_f32=True,
-                           y_strides=(A * ch, lw * ch, ch), y_elem_off=self.offs[lvl] * ch)
-                self.ctx.append(dict(w=w))
-                continue
-            if op.kind == "convT":
-                src, _ = self._view(op.src)
-                dst, _ = self._view(op.dst)
-                wt = P[op.name + ".upsample_transpose.weight"].detach()          # [Cin, Cout, 2, 2]
-                bias = torch.zeros((op.cout + 255) // 256 * 256, dtype=torch.float32, device=self.dev)
-                bias[:op.cout] = P[op.name + ".upsample_transpose.bias"].detach()
-                _, dh, dw, dct = dst.shape
-                ws = []
-                for q in range(4):
-                    dy, dx = q // 2, q % 2
-                    wq = wt[:, :, dy, dx].t().reshape(op.cout, 1, 1, op.cin).to(torch.bfloat16).contiguous()
-                    ws.append(wq)
-                    self._conv(src, op.src.c_off, op.cin, wq, dst, op.dst.c_off, op.cout, 1, 1, bias=bias,
-                               y_strides=(dh * dw * dct, 2 * dw * dct, 2 * dct), y_elem_off=(dy * dw + dx) * dct)
-                self.ctx.append(dict(w=ws))
-                continue
-            # ---- BN-ed blocks: stem / rep / cba ----
-            dst, _ = self._view(op.dst)
-            n, ho, wo, _ = dst.shape
-            count = n * ho * wo
-            branches = []   # (raw tensor [N,Ho,Wo,C], c_off, bn prefix, conv info)
-            if op.layout == "rep":
-                specs = [(op.name + ".rbr_dense", 3), (op.name + ".rbr_1x1", 1)]
-            else:
-                specs = [(op.name + ".block", op.k)]
-            for prefix, k in specs:
-                raw = torch.empty(n, ho, wo, op.cout, dtype=torch.bfloat16, device=self.dev)
-                wt = P[prefix + ".conv.weight"].detach()
-                if op.kind == "stem":
-                    w33 = wt if k == 3 else torch.nn.functional.pad(wt, [1, 1, 1, 1])      # 1x1 s2 = centre tap of a 3x3 s2
-                    wdev = w33.permute(2, 3, 1, 0).contiguous().float()                     # [3][3][3][Cout]
-                    d = StemDesc()
-                    d.x, d.x_dtype, d.in_scale = self.x.data_ptr(), (DT_U8 if self.x.dtype == torch.uint8 else DT_F32), 1.0 / 255.0
-                    d.N, d.H, d.W = N, H, W
-                    d.w, d.bias, d.Cout, d.act = wdev.data_ptr(), 0, op.cout, 0
-                    d.y, d.y_plane_stride, d.nsplit, d.fp32_math = raw.data_ptr(), 0, 1, 1
-                    _lib.check(self.lib.yv6_stem_fwd(self.h, C.byref(d), _lib.stream_ptr()))
-                    wk = wdev
-                else:
-                    src, _ = self._view(op.src)
-                    wk = self._krsc(wt)
-                    self._conv(src, op.src.c_off, op.cin, wk, raw, 0, op.cout, k, op.s)
-                st = self._finalize(self._stats(raw, 0, op.cout), count, prefix + ".bn", op.cout)
-                branches.append(dict(x=raw, off=0, st=st, prefix=prefix, k=k, w=wk))
-            if op.layout == "rep" and op.cin == op.cout and op.s == 1:
-                src, _ = self._view(op.src)
-                st = self._finalize(self._stats(src, op.src.c_off, op.cin), count, op.name + ".rbr_identity", op.cin)
-                branches.append(dict(x=src, off=op.src.c_off, st=st, prefix=op.name + ".rbr_identity", k=0, w=None))
-            d = BnDesc()
-            d.nb, d.act, d.C, d.pixels = len(branches), ACT_CODES[op.act], op.cout, count
-            for b, br in enumerate(branches):
-                d.x[b] = br["x"].data_ptr() + br["off"] * 2
-                d.x_pitch[b] = br["x"].shape[3]
-                d.scale[b], d.shift[b] = br["st"][2].data_ptr(), br["st"][3].data_ptr()
-            d.y, d.y_pitch = dst.data_ptr() + op.dst.c_off * 2, dst.shape[3]
-            alpha = 1.0
-            if op.res is not None:
-                rbuf, _ = self._view(op.res)
-                alpha = float(P[op.alpha].detach()) if op.alpha in P else 1.0
-                d.res, d.res_pitch, d.res_alpha = rbuf.data_ptr() + op.res.c_off * 2, rbuf.shape[3], alpha
-            _lib.check(self.lib.yv6_bn_apply_fwd(self.h, C.byref(d), _lib.stream_ptr()))
-            self.ctx.append(dict(branches=branches, count=count, alpha=alpha))
-        return self.cls, self.reg
-
-    # ------------------------------------------------------------------ backward
-    def _add_grad(self, name, value):
-        p = self.params[name]
-        value = value.to(p.dtype).reshape(p.shape)
-        p.grad = value.clone() if p.grad is None else p.grad + value
-
-    def _dgrad(self, dc, w_krsc, k, stride, gsrc, g_off, cin):
-        """g(src)[..., g_off:+cin] += conv_transpose(dc, w).  dc [N,Ho,Wo,Cout] bf16, w [Cout,k,k,Cin] bf16."""
-        cout = w_krsc.shape[0]
-        if stride == 1:
-            wt = w_krsc.flip(1, 2).permute(3, 1, 2, 0).contiguous()            # [Cin, k, k, Cout], rotated 180 degrees
-            self._conv(dc, 0, cout, wt, gsrc, g_off, cin, k, 1, accumulate=True)
-            return
-        # stride 2: the input gradient at parity (ph, pw) is a 1- or 2-tap stride-1 conv of dc
-        n, hs, ws, gct = gsrc.shape
-        ho, wo = dc.shape[1], dc.shape[2]
-        for ph in range(2):
-            for pw in range(2):
-                if k == 1:
-                    if ph or pw:
-                        continue                                               # a 1x1 s2 conv only touches even positions
-                    wt = w_krsc.permute(3, 1, 2, 0).contiguous()
-                else:
-                    rows = [1] if ph == 0 else [2, 0]                          # tap t reads dc[i + t]: W[2] at t=0, W[0] at t=1
-                    cols = [1] if pw == 0 else [2, 0]
-                    wt = w_krsc[:, rows][:, :, cols].permute(3, 1, 2, 0).contiguous()   # [Cin, kh', kw', Cout]
-                self._conv(dc, 0, cout, wt, gsrc, g_off, cin, k, 1, pad=(0, 0), out_hw=(ho, wo), accumulate=True,
-                           y_strides=(hs * ws * gct, 2 * ws * gct, 2 * gct), y_elem_off=(ph * ws + pw) * gct)
-
-    def backward(self, grad_cls, grad_reg):
-        """Accumulates d(loss)/d(parameter) into `.grad` given d(loss)/d(cls), d(loss)/d(reg) ([N,A,*] fp32)."""
-        P, dev = self.params, self.dev
-        for gb in self.gbufs:
-            gb.zero_()
-        N = self.cls.shape[0]
-        A = self.offs[-1]
-        for i in range(len(self.g.ops) - 1, -1, -1):
-            op, ctx = self.g.ops[i], self.ctx[i]
-            if op.kind == "pool":
-                buf, gbuf = self._view(op.dst)
+                buf, gbuf = view(op.dst)
                 n, h, w, ct = buf.shape
                 c = op.cin
-                if self.debug:
-                    self.dbg[i] = dict(gdst=gbuf[..., :4 * c].clone())
-                scratch = torch.empty(n, h, w, c, dtype=torch.float32, device=dev)
+                fwd.append(("pool", (buf.data_ptr(), n, h, w, c, ct, 1, 0)))
+                if pool_scr is None or pool_scr.numel() < n * h * w * c:
+                    pool_scr = torch.zeros(n * h * w * c, dtype=torch.float32, device=dev)
+                calls.append(("dbg", (i, gbuf[..., :4 * c])))
                 for j in (3, 2, 1):   # y_j = pool(y_{j-1}); slice j of the concat
-                    _lib.check(self.lib.yv6_maxpool5_bwd(self.h, buf.data_ptr() + (j - 1) * c * 2, ct, gbuf.data_ptr() + j * c * 2, ct,
-                                                         n, h, w, c, scratch.data_ptr(), gbuf.data_ptr() + (j - 1) * c * 2, ct, 1,
-                                                         _lib.stream_ptr()))
+                    calls.append(("pool_bwd", (buf.data_ptr() + (j - 1) * c * 2, ct, gbuf.data_ptr() + j * c * 2, ct, n, h, w, c,
+                                               pool_scr, gbuf.data_ptr() + (j - 1) * c * 2, ct, 1)))
+                bwd_rev.append(calls)
                 continue
+            Wt = self.wts[i]
             if op.kind == "pred":
+                src, gsrc = view(op.src)
                 which, lvl = op.head
-                grad, scores = (grad_cls, self.cls) if which == "cls" else (grad_reg, None)
-                ch = grad.shape[2]
-                ch_pad = (ch + 15) // 16 * 16
+                out, grad = (self.cls, self.grad_cls) if which == "cls" else (self.reg, self.grad_reg)
+                ch = out.shape[2]
+                chp = (ch + 15) // 16 * 16
                 lh, lw = self.sizes[lvl]
-                dl = torch.empty(N, lh, lw, ch_pad, dtype=torch.bfloat16, device=dev)
-                _lib.check(self.lib.yv6_head_grad_prep(self.h, grad.data_ptr(), _p(scores), N, A, ch, self.offs[lvl], lh * lw, ch_pad,
-                                                       dl.data_ptr(), _lib.stream_ptr()))
-                src, gsrc = self._view(op.src)
-                dw = torch.zeros(ch, 1, 1, op.cin, dtype=torch.float32, device=dev)
-                self._wgrad(src, op.src.c_off, op.cin, dl, 0, ch, 1, 1, dw)
-                self._add_grad(op.name + ".weight", dw.permute(0, 3, 1, 2))
-                self._add_grad(op.name + ".bias", self._stats(dl, 0, ch_pad)[0][:ch])
-                wpad = torch.zeros(ch_pad, 1, 1, op.cin, dtype=torch.bfloat16, device=dev)
-                wpad[:ch] = ctx["w"]
-                self._dgrad(dl, wpad, 1, 1, gsrc, op.src.c_off, op.cin)
+                fwd.append(("conv", self._conv_desc(src, op.src.c_off, op.cin, Wt["w"], out, 0, op.cout, 1, 1, bias=Wt["bias"], act=op.act,
+                                                    y_f32=True, y_strides=(A * ch, lw * ch, ch), y_elem_off=self.offs[lvl] * ch)))
+                dl = bf(N, lh, lw, chp)
+                calls.append(("hgp", (grad.data_ptr(), self.cls.data_ptr() if which == "cls" else 0, N, A, ch, self.offs[lvl], lh * lw, chp,
+                                      dl.data_ptr()), dl))
+                calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dl, 0, ch, 1, 1, z(i, "dw"))))
+                calls.append(("stats", self._stats_desc([(dl, 0)], chp, N * lh * lw, z(i, "bsum"), z(i, "bcnt"))))
+                calls.append(("conv", self._conv_desc(dl, 0, chp, Wt["wt"], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True)))
+                bwd_rev.append(calls)
                 continue
             if op.kind == "convT":
-                src, gsrc = self._view(op.src)
-                _, gdst = self._view(op.dst)
-                gd = gdst[..., op.dst.c_off:op.dst.c_off + op.cout]
-                if self.debug:
-                    self.dbg[i] = dict(gdst=gd.clone())
-                dwt = torch.zeros(op.cin, op.cout, 2, 2, dtype=torch.float32, device=dev)
-                db = torch.zeros(op.cout, dtype=torch.float64, device=dev)
+                src, gsrc = view(op.src)
+                dst, gdst = view(op.dst)
+                _, dh, dw, dct = dst.shape
+                _, sh, sw, _ = src.shape
                 for q in range(4):
                     dy, dx = q // 2, q % 2
-                    dq = gd[:, dy::2, dx::2, :].contiguous()                      # gradient of quadrant q, dense [N,H,W,Cout]
-                    dw = torch.zeros(op.cout, 1, 1, op.cin, dtype=torch.float32, device=dev)
-                    self._wgrad(src, op.src.c_off, op.cin, dq, 0, op.cout, 1, 1, dw)
-                    dwt[:, :, dy, dx] = dw.reshape(op.cout, op.cin).t()
-                    db += self._stats(dq, 0, op.cout)[0]
-                    self._dgrad(dq, ctx["w"][q], 1, 1, gsrc, op.src.c_off, op.cin)
-                self._add_grad(op.name + ".upsample_transpose.weight", dwt)
-                self._add_grad(op.name + ".upsample_transpose.bias", db)
+                    fwd.append(("conv", self._conv_desc(src, op.src.c_off, op.cin, Wt["w"][q], dst, op.dst.c_off, op.cout, 1, 1, bias=Wt["bias"],
+                                                        y_strides=(dh * dw * dct, 2 * dw * dct, 2 * dct), y_elem_off=(dy * dw + dx) * dct)))
+                gd = gdst[..., op.dst.c_off:op.dst.c_off + op.cout]
+                calls.append(("dbg", (i, gd)))
+                # bias gradient = column sums of the whole upsampled gradient slice
+                calls.append(("stats", self._stats_desc([(gdst, op.dst.c_off)], op.cout, N * dh * dw, z(i, "bsum"), z(i, "bcnt"))))
+                need = N * sh * sw * op.cout
+                if dq_pool is None or dq_pool[0].numel() < need:
+                    dq_pool = [torch.zeros(need, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+                for q in range(4):
+                    dy, dx = q // 2, q % 2
+                    dq = dq_pool[q][:need].view(N, sh, sw, op.cout)
+                    calls.append(("copy", (dq, gd[:, dy::2, dx::2, :])))               # gradient of quadrant q, dense
+                    calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dq, 0, op.cout, 1, 1, z(i, "dw") + 4 * q * op.cout * op.cin)))
+                    calls.append(("conv", self._conv_desc(dq, 0, op.cout, Wt["wt"][q], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True)))
+                bwd_rev.append(calls)
                 continue
-            # ---- BN-ed blocks ----
-            dst, gdst = self._view(op.dst)
-            brs = ctx["branches"]
+            # ---- BN-ed blocks: stem / rep / cba ----
+            dst, gdst = view(op.dst)
             n, ho, wo, dct = dst.shape
+            count = n * ho * wo
+            br = Wt["br"]
+            nb = len(br)
+            st = self.stat_out[i]
+            xs = []
+            for b, ent in enumerate(br):
+                k = ent["k"]
+                if k == 0:
+                    src, _ = view(op.src)
+                    xs.append((src, op.src.c_off))
+                    self.ctx[i]["branches"][b]["x"] = src
+                    continue
+                raw = bf(n, ho, wo, op.cout)
+                self.ctx[i]["branches"][b]["x"] = raw
+                if op.kind == "stem":
+                    d = StemDesc()
+                    d.x, d.x_dtype, d.in_scale = self.x_static.data_ptr(), x_dt, 1.0 / 255.0
+                    d.N, d.H, d.W = N, H, W
+                    d.w, d.bias, d.Cout, d.act = ent["w"].data_ptr(), 0, op.cout, 0
+                    d.y, d.y_plane_stride, d.nsplit, d.fp32_math = raw.data_ptr(), 0, 1, 1
+                    fwd.append(("stem", d))
+                else:
+                    src, _ = view(op.src)
+                    fwd.append(("conv", self._conv_desc(src, op.src.c_off, op.cin, ent["w"], raw, 0, op.cout, k, op.s)))
+                xs.append((raw, 0))
+            fin = [(ent["prefix"] + (".bn" if ent["k"] else ""), st[b]) for b, ent in enumerate(br)]
+            fwd.append(("stats", self._stats_desc(xs, op.cout, count, z(i, "fsum"), z(i, "fcnt"), fin)))
             d = BnDesc()
-            d.nb, d.act, d.C, d.pixels = len(brs), ACT_CODES[op.act], op.cout, ctx["count"]
-            sums = torch.empty(4, op.cout, dtype=torch.float64, device=dev)
-            d.s1 = sums[0].data_ptr()
+            d.nb, d.act, d.C, d.pixels = nb, ACT_CODES[op.act], op.cout, count
             dcs = []
-            for b, br in enumerate(brs):
-                d.x[b], d.x_pitch[b] = br["x"].data_ptr() + br["off"] * 2, br["x"].shape[3]
-                d.mean[b], d.invstd[b] = br["st"][0].data_ptr(), br["st"][1].data_ptr()
-                d.scale[b], d.shift[b] = br["st"][2].data_ptr(), br["st"][3].data_ptr()
-                d.s2[b] = sums[1 + b].data_ptr()
-                if br["k"] == 0:      # identity branch: its input gradient goes straight into g(src)
-                    _, gsrc = self._view(op.src)
+            for b, (t, off) in enumerate(xs):
+                d.x[b], d.x_pitch[b] = t.data_ptr() + off * 2, t.shape[3]
+                d.mean[b], d.invstd[b] = st[b, 0].data_ptr(), st[b, 1].data_ptr()
+                d.scale[b], d.shift[b] = st[b, 2].data_ptr(), st[b, 3].data_ptr()
+                d.s2[b] = z(i, "s2") + 8 * b * op.cout
+                if br[b]["k"] == 0:      # identity branch: its input gradient goes straight into g(src)
+                    _, gsrc = view(op.src)
                     d.dx[b], d.dx_pitch[b], d.accumulate[b] = gsrc.data_ptr() + op.src.c_off * 2, gsrc.shape[3], 1
                     dcs.append(None)
                 else:
-                    dc = torch.empty(n, ho, wo, op.cout, dtype=torch.bfloat16, device=dev)
+                    dc = dc_pool[len([t for t in dcs if t is not None])][:count * op.cout].view(n, ho, wo, op.cout)
                     d.dx[b], d.dx_pitch[b], d.accumulate[b] = dc.data_ptr(), op.cout, 0
                     dcs.append(dc)
             d.y, d.y_pitch = dst.data_ptr() + op.dst.c_off * 2, dct
             d.dy, d.dy_pitch = gdst.data_ptr() + op.dst.c_off * 2, dct
+            d.s1 = z(i, "s1")
+            d.work, d.counter, d.coef, d.zeroed = z(i, "work"), z(i, "bcnt"), self.coef_out[i].data_ptr(), 1
             if op.res is not None:
-                rbuf, grbuf = self._view(op.res)
-                dalpha = torch.empty(1, dtype=torch.float64, device=dev)
-                d.res, d.res_pitch, d.res_alpha = rbuf.data_ptr() + op.res.c_off * 2, rbuf.shape[3], ctx["alpha"]
-                d.dres, d.dres_pitch, d.dalpha = grbuf.data_ptr() + op.res.c_off * 2, grbuf.shape[3], dalpha.data_ptr()
-            _lib.check(self.lib.yv6_bn_bwd(self.h, C.byref(d), _lib.stream_ptr()))
-            if op.res is not None and op.alpha in P and P[op.alpha].requires_grad:
-                self._add_grad(op.alpha, dalpha)
-            if self.debug:
-                self.dbg[i] = dict(gdst=gdst[..., op.dst.c_off:op.dst.c_off + op.cout].clone(), dcs=dcs)
-            for b, br in enumerate(brs):
-                bnp = br["prefix"] + (".bn" if br["k"] else "")
-                self._add_grad(bnp + ".weight", sums[1 + b])        # dgamma = sum dz * xhat
-                self._add_grad(bnp + ".bias", sums[0])              # dbeta  = sum dz
-                if br["k"] == 0:
-                    continue
-                dc, k = dcs[b], br["k"]
-                if op.kind == "stem":
-                    dw = torch.empty(op.cout, 3, 3, 3, dtype=torch.float32, device=dev)
-                    _lib.check(self.lib.yv6_stem_wgrad(self.h, self.x.data_ptr(), DT_U8 if self.x.dtype == torch.uint8 else DT_F32,
-                                                       1.0 / 255.0, dc.data_ptr(), op.cout, N, self.x.shape[2], self.x.shape[3], op.cout,
-                                                       dw.data_ptr(), _lib.stream_ptr()))
-                    dw = dw.permute(0, 3, 1, 2)                     # [Cout][r][s][c] -> [Cout, c, r, s]
-                    self._add_grad(br["prefix"] + ".conv.weight", dw if k == 3 else dw[:, :, 1:2, 1:2])
-                    continue
-                src, gsrc = self._view(op.src)
-                dw = torch.zeros(op.cout, k, k, op.cin, dtype=torch.float32, device=dev)
-                self._wgrad(src, op.src.c_off, op.cin, dc, 0, op.cout, k, op.s, dw)
-                self._add_grad(br["prefix"] + ".conv.weight", dw.permute(0, 3, 1, 2))
-                self._dgrad(dc, br["w"], k, op.s, gsrc, op.src.c_off, op.cin)
+                rbuf, grbuf = view(op.res)
+                d.res, d.res_pitch, d.res_alpha = rbuf.data_ptr() + op.res.c_off * 2, rbuf.shape[3], 1.0
+                if op.alpha in self.params:
+                    d.res_alpha_dev = fl.ptr(op.alpha)
+                d.dres, d.dres_pitch, d.dalpha = grbuf.data_ptr() + op.res.c_off * 2, grbuf.shape[3], z(i, "dalpha")
+            fwd.append(("apply", d))
+            calls.append(("dbg", (i, gdst[..., op.dst.c_off:op.dst.c_off + op.cout])))
+            calls.append(("bn_bwd", d))
+            if op.kind == "stem":
+                dy3 = dcs[0]
+                dy1 = dcs[1] if nb > 1 else None
+                calls.append(("stem_wgrad", (self.x_static.data_ptr(), x_dt, 1.0 / 255.0, dy3.data_ptr(), op.cout, _p(dy1), op.cout, N, H, W,
+                                             op.cout, z(i, "dw", 0), z(i, "dw", 1) if nb > 1 else 0, 1)))
+            else:
+                src, gsrc = view(op.src)
+                for b, ent in enumerate(br):
+                    if ent["k"] == 0:
+                        continue
+                    calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dcs[b], 0, op.cout, ent["k"], op.s, z(i, "dw", b))))
+                    for dd in self._dgrad_descs(dcs[b], ent, ent["k"], op.s, gsrc, op.src.c_off, op.cin):
+                        calls.append(("conv", dd))
+            bwd_rev.append(calls)
+        self.fwd_calls = fwd
+        bwd = []
+        for i in range(len(g.ops) - 1, -1, -1):
+            bwd.extend(bwd_rev[i])
+            k = self.bucket_of_op.get(i)
+            if k is not None and self.last_op_of_bucket[k] == i:
+                bwd.append(("bucket", k))
+        self.bwd_calls = bwd
+        self._keep = (dc_pool, pool_scr, dq_pool)
+
+    # ================================================================== execution
+    def launch_counts(self):
+        """(forward, backward) kernel launches of the current plan, excluding the arena memset and the two repack launches."""
+        f = len(self.fwd_calls)
+        b = 0
+        for c in self.bwd_calls:
+            kind = c[0]
+            if kind == "bn_bwd" or kind == "pool_bwd":
+                b += 2
+            elif kind in ("dbg", "bucket"):
+                continue
+            else:
+                b += 1
+        return f, b + len(self.grad_tables)
+
+    def begin_step(self, sp=None):
+        """Clears the per-step accumulators and repacks the master weights into the kernels' layouts."""
+        sp = sp or _lib.stream_ptr()
+        self.zero_arena.zero_()
+        self.pack_table.launch(self.lib, self.h, False, sp)
+
+    def forward(self, x):
+        """x [N,3,H,W] fp32 in [0,1] (or uint8).  Returns (cls [N,A,nc] post-sigmoid, reg [N,A,R]) fp32 (engine-owned)."""
+        if not self.flat.valid():
+            raise RuntimeError("the model's tensors were replaced after the training engine was built (model.to / .half); "
+                               "call model.train_engine(rebuild=True)")
+        N, _, H, W = x.shape
+        if x.dtype not in (torch.float32, torch.uint8):
+            x = x.float()
+        self._plan(N, H, W, x.dtype)
+        if x.data_ptr() != self.x_static.data_ptr():
+            self.x_static.copy_(x)
+        sp = _lib.stream_ptr()
+        self.begin_step(sp)
+        self.flat.iflat.add_(1)                     # BatchNorm.num_batches_tracked
+        self.run_forward(sp)
+        return self.cls, self.reg
+
+    def run_forward(self, sp):
+        lib, h, chk = self.lib, self.h, _lib.check
+        for kind, d in self.fwd_calls:
+            if kind == "conv":
+                chk(lib.yv6_conv_fwd(h, C.byref(d), sp))
+            elif kind == "stats":
+                chk(lib.yv6_bn_stats_finalize(h, C.byref(d), sp))
+            elif kind == "apply":
+                chk(lib.yv6_bn_apply_fwd(h, C.byref(d), sp))
+            elif kind == "stem":
+                chk(lib.yv6_stem_fwd(h, C.byref(d), sp))
+            else:
+                chk(lib.yv6_sppf_pool(h, C.c_void_p(d[0]), d[1], d[2], d[3], d[4], d[5], d[6], d[7], sp))
+
+    def backward(self, grad_cls, grad_reg, accumulate=False, first=0, last=None):
+        """Writes d(loss)/d(parameter) of every trainable parameter into the flat gradient buffer (`accumulate`: adds to it)
+        given d(loss)/d(cls), d(loss)/d(reg) ([N,A,*] fp32).  `first`/`last` restrict the run to a slice of the call list
+        (graph capture in bucket-sized segments)."""
+        if grad_cls is not None and grad_cls.data_ptr() != self.grad_cls.data_ptr():
+            self.grad_cls.copy_(grad_cls)
+        if grad_reg is not None and grad_reg.data_ptr() != self.grad_reg.data_ptr():
+            self.grad_reg.copy_(grad_reg)
+        lib, h, chk = self.lib, self.h, _lib.check
+        sp = _lib.stream_ptr()
+        if first == 0:
+            for gb in self.gbufs:
+                gb.zero_()
+        calls = self.bwd_calls if last is None else self.bwd_calls[:last]
+        for c in calls[first:]:
+            kind, d = c[0], c[1]
+            if kind == "conv":
+                chk(lib.yv6_conv_fwd(h, C.byref(d), sp))
+            elif kind == "wgrad":
+                chk(lib.yv6_conv_wgrad(h, C.byref(d), sp))
+            elif kind == "bn_bwd":
+                chk(lib.yv6_bn_bwd(h, C.byref(d), sp))
+            elif kind == "stats":
+                chk(lib.yv6_bn_stats_finalize(h, C.byref(d), sp))
+            elif kind == "copy":
+                d[0].copy_(d[1])
+            elif kind == "hgp":
+                chk(lib.yv6_head_grad_prep(h, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], sp))
+            elif kind == "pool_bwd":
+                chk(lib.yv6_maxpool5_bwd(h, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8].data_ptr(), d[9], d[10], d[11], sp))
+            elif kind == "stem_wgrad":
+                chk(lib.yv6_stem_wgrad2(h, *d, sp))
+            elif kind == "bucket":
+                self.grad_tables[d].launch(lib, h, accumulate, sp)
+                if self.bucket_hook is not None:
+                    self.bucket_hook(d)
+            elif kind == "dbg":
+                if self.debug:
+                    self.dbg[d[0]] = dict(gdst=d[1].clone())
+
+    def bucket_call_index(self):
+        """Indices into the backward call list right after each bucket's unpack (segment boundaries for graph capture)."""
+        return [j + 1 for j, c in enumerate(self.bwd_calls) if c[0] == "bucket"]
 
 
 class _HeadFn(torch.autograd.Function):
-    """Connects the engine to autograd: forward returns the head tensors, backward runs the engine's
-    backward pass with the incoming gradients (parameter gradients land in `.grad`)."""
+    """Connects the engine to autograd: forward returns the head tensors, backward runs the engine's backward pass and
+    hands every parameter its gradient, so `loss.backward()`, GradScaler, gradient accumulation and the reducer hooks of
+    DistributedDataParallel (core/engine.py:456-468) behave as they do for the reference's nn.Module."""
 
     @staticmethod
-    def forward(ctx, engine, x, token):
+    def forward(ctx, engine, x, *params):
         ctx.engine = engine
         cls, reg = engine.forward(x)
         return cls.clone(), reg.clone()
 
     @staticmethod
     def backward(ctx, g_cls, g_reg):
-        ctx.engine.backward(g_cls.contiguous().float(), g_reg.contiguous().float())
-        return None, None, None
+        eng = ctx.engine
+        eng.backward(g_cls.contiguous().float(), g_reg.contiguous().float())
+        flat = eng.flat
+        g = flat.gflat.clone()          # autograd may keep (steal) what it is given; the flat buffer is reused next step
+        grads = []
+        for n in flat.names:
+            o, k, shape = flat.slots[n]
+            grads.append(g[o:o + k].view(shape))
+        return (None, None, *grads)
 
 
 def train_forward(engine, x):
-    token = torch.zeros(1, device=engine.dev, requires_grad=True)   # makes the outputs part of the autograd graph
-    return _HeadFn.apply(engine, x, token)
+    params = [engine.params[n] for n in engine.flat.names]
+    return _HeadFn.apply(engine, x, *params)
