@@ -1,6 +1,13 @@
 """bench.py -- images/sec of the YOLOv6-S 640x640 bs32 inference hot path on N x B200 (BASELINE.json).
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+                    [--mode infer|train] [--model yolov6s] [--batch 32] [--size 640] [--no-extra]
+
+The default run prints ONE JSON line whose headline (`value`, `e2e`, `roofline`) is BASELINE.json's config 2 and which
+also carries, under `modes`, the fp32-equivalent (bf16x3) precision mode with the measured bf16-vs-fp32 deviation on the
+benchmark input, and under `configs` short measurements of the other GPU configurations of BASELINE.json: config 3
+(YOLOv6-S bs32 training step), config 4 (YOLOv6-M training, 8 images per GPU, gradient all-reduce when N > 1) and
+config 5 (YOLOv6-L6 1280x1280, 2 images per GPU).  `--mode train` makes the training step the headline instead.
 
 One "step" = one batch through the whole hot path: stem -> backbone -> neck -> head -> decode
 (sm_100a kernels via the C ABI) -> batched NMS (eval settings conf 0.03 / iou 0.65 / multi_label,
@@ -154,22 +161,219 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def barrier(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps, warmup, world, dev):
+    """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events, max over ranks -> ms per step."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    barrier(world)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item() / steps
+
+
+def load_peaks():
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            return json.load(f)
+    return {}
+
+
+def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf16", e2e=True, roofline=True, graph=True):
+    """Forward + decode + batched NMS of `model_name` on B images of S x S per GPU.  Returns a dict of measurements."""
+    from yolov6_b200.model import build_model
+    from yolov6_b200.nms import nms_batched
+    from yolov6_b200.pipeline import DetectPipeline
+    from yolov6_b200.synth import randomize_
+    model = randomize_(build_model(model_name, 80, dev), seed=0)   # seeded synthetic checkpoint
+    model.eval().set_precision(precision)
+    eng = model.engine()
+    g = torch.Generator().manual_seed(1 + rank)   # per-rank data like tools/train.py:104 seeds per rank
+    host_u8 = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8).pin_memory() for _ in range(2)]
+    dev_f32 = [h.to(dev).float() / 255 for h in host_u8]
+    out = {"model": model_name, "batch_per_gpu": B, "size": S, "precision": precision}
+    if graph:
+        # steady state = one CUDA-graph launch per batch (yolov6_b200/pipeline.py); two pipelines with
+        # separate static buffers alternate so that consecutive steps never reuse a cached input
+        pipes_dev = [DetectPipeline(model, B, S, S, host_input=False, **NMS_KW) for _ in range(2)]
+        for i in range(2):
+            pipes_dev[i].x_dev.copy_(dev_f32[i])
+
+        def step_device(i):
+            pipes_dev[i & 1].launch()
+    else:
+        def step_device(i):
+            pred = eng.forward(dev_f32[i & 1])
+            return nms_batched(pred, **NMS_KW)
+    with torch.no_grad():
+        ms_dev = timed(step_device, steps, warmup, world, dev)
+        out["ms_per_step"] = ms_dev
+        out["value"] = world * B / (ms_dev * 1e-3)
+        if e2e:
+            if graph:
+                copy_stream = torch.cuda.Stream(device=dev)   # H2D of batch i+1 overlaps the kernels of batch i
+                pipes_e2e = [DetectPipeline(model, B, S, S, host_input=True, overlap_h2d=True, copy_stream=copy_stream, **NMS_KW)
+                             for _ in range(2)]
+                for i in range(2):
+                    pipes_e2e[i].x_host.copy_(host_u8[i])
+
+                def step_e2e(i):
+                    pipes_e2e[i & 1].launch()      # H2D (u8, copy stream) -> graph: kernels -> D2H detections
+            else:
+                def step_e2e(i):
+                    x = host_u8[i & 1].to(dev, non_blocking=True)
+                    o, c, _, _ = nms_batched(eng.forward(x), **NMS_KW)
+                    return o.cpu(), c.cpu()
+            ms_e2e = timed(step_e2e, steps, warmup, world, dev)
+            out["e2e"] = {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                          "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * NMS_KW["max_det"] * 6 * 4 + B * 4}
+        if roofline:
+            conv_ms, conv_flop, n_conv = eng.profile_convs(dev_f32[0], steps=5)
+            out["conv"] = {"ms": conv_ms, "flop": conv_flop, "launches": n_conv, "bytes_per_launch": eng.conv_bytes_per_launch(B, S, S)}
+    out["launches_per_step"] = eng.launch_count(B, S, S) + (7 if 8400 * 80 > 65536 else 3)
+    out["_model"], out["_input"] = model, dev_f32[0]
+    return out
+
+
+def precision_check(model, x, dev):
+    """bf16 speed mode against the fp32-equivalent (bf16x3) mode on the benchmark input: max |a-b|/(1+|b|) over the
+    [B, A, 85] predictions and the fraction of NMS output rows (box, score, class) that are identical."""
+    from yolov6_b200.nms import nms_batched
+    with torch.no_grad():
+        model.set_precision("bf16")
+        p16 = model.engine().forward(x).clone()
+        o16, c16, _, _ = nms_batched(p16, **NMS_KW)
+        model.set_precision("fp32")
+        p32 = model.engine().forward(x).clone()
+        o32, c32, _, _ = nms_batched(p32, **NMS_KW)
+        err = float(((p16 - p32).abs() / (1 + p32.abs())).max())
+        err_cls = float((p16[..., 5:] - p32[..., 5:]).abs().max())
+        same, total, same_cls = 0, 0, 0
+        c16, c32 = c16.tolist(), c32.tolist()
+        for b in range(p16.shape[0]):
+            n = min(c16[b], c32[b])
+            total += max(c16[b], c32[b])
+            same += int((o16[b, :n] == o32[b, :n]).all(-1).sum())
+            # same detection = same class and boxes within a pixel, whatever the rank in the list
+            same_cls += int(((o16[b, :n, 5] == o32[b, :n, 5]) & ((o16[b, :n, :4] - o32[b, :n, :4]).abs().max(-1).values < 1.0)).sum())
+        model.set_precision("bf16")
+    return {"max_rel_err_bf16_vs_fp32": err, "max_abs_err_scores": err_cls, "nms_rows_bit_identical_frac": same / max(total, 1),
+            "nms_rows_same_class_and_box_within_1px_frac": same_cls / max(total, 1), "nms_rows": total,
+            "tolerance_note": "north_star's 1e-4 is met by the fp32 mode (tests/test_gpu_model.py); bf16 is the speed mode"}
+
+
+TRAIN_LOSS = {"yolov6n": dict(use_dfl=False, reg_max=0, iou_type="siou"), "yolov6s": dict(use_dfl=False, reg_max=0, iou_type="giou"),
+              "yolov6m": dict(use_dfl=True, reg_max=16, iou_type="giou"), "yolov6l6": dict(use_dfl=True, reg_max=16, iou_type="giou")}
+
+
+def bench_train(model_name, B, S, steps, warmup, rank, world, dev, graph=True):
+    """One training step of `model_name` on B images per GPU (BASELINE.json config 3 / 4): train-form forward, TAL
+    assignment, VFL + IoU (+ DFL) loss, backward, gradient all-reduce over NCCL when world > 1; the optimizer (fused SGD +
+    EMA) is timed separately and inside the end-to-end number."""
+    from yolov6_b200.loss import ComputeLoss
+    from yolov6_b200.model import build_model
+    from yolov6_b200.optim import FusedSGDEMA
+    from yolov6_b200.step import TrainStep
+    from yolov6_b200.synth import synthetic_targets
+    torch.manual_seed(0)                                  # same initial weights on every rank (DDP broadcasts rank 0's)
+    model = build_model(model_name, 80, dev).train()      # random init of the architecture (initialize_biases etc.)
+    strides = [int(v) for v in model.graph.strides]
+    crit = ComputeLoss(fpn_strides=strides, num_classes=80, ori_img_size=S, warmup_epoch=0, **TRAIN_LOSS[model_name])
+    opt = FusedSGDEMA(model, lr=0.01, momentum=0.937, weight_decay=5e-4)
+    step = TrainStep(model, crit, B, S, S, in_dtype=torch.uint8, max_gt=64, optimizer=None, graph=graph)
+    g = torch.Generator().manual_seed(1 + rank)           # tools/train.py:104 seeds per rank
+    imgs = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8).pin_memory() for _ in range(2)]
+    tgts = [synthetic_targets(B, seed=100 + 10 * rank + i).pin_memory() for i in range(2)]
+    loss_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+    step.load(imgs[0], tgts[0])
+
+    def step_device(i):
+        step.run(epoch_num=0)
+
+    def step_opt(i):
+        opt.upload_hyper()
+        opt.launch()
+
+    def step_e2e(i):
+        step.load(imgs[i & 1], tgts[i & 1])               # H2D: uint8 images + targets from pinned memory
+        out = step.run(epoch_num=0)
+        opt.upload_hyper()
+        opt.launch()
+        loss_host.copy_(out, non_blocking=True)           # D2H: loss / loss items
+
+    ms_dev = timed(step_device, steps, warmup, world, dev)
+    first_loss = [float(v) for v in step.state["out"][:4].tolist()]
+    ar_ms = step.sync.last_ms() if step.sync is not None else 0.0
+    ms_opt = timed(step_opt, steps, 1, world, dev)
+    ms_e2e = timed(step_e2e, steps, warmup, world, dev)
+    model.mark_weights_changed()
+    torch.cuda.synchronize()
+    last_loss = [float(v) for v in loss_host[:4].tolist()]
+    f, b = step.eng.launch_counts()
+    nbytes = step.eng.flat.n_train * 4
+    peaks = load_peaks()
+    gflop_img = 3.0 * GFLOP_PER_IMG[model_name] * (S / (1280.0 if model_name == "yolov6l6" else 640.0)) ** 2
+    achieved = gflop_img * 1e9 * B / (ms_dev * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    return {"model": model_name, "batch_per_gpu": B, "size": S, "value": world * B / (ms_dev * 1e-3), "unit": "images/s",
+            "ms_per_step": ms_dev, "step": "train-form forward + TAL + VFL/GIoU" + ("/DFL" if TRAIN_LOSS[model_name]["use_dfl"] else "") +
+            " loss + backward" + (" + gradient all-reduce" if world > 1 else ""),
+            "optimizer_ms": ms_opt, "optimizer": "fused SGD-nesterov + weight decay + EMA, one kernel (yv6_sgd_ema_step)",
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": B * 3 * S * S + int(tgts[0].numel()) * 4, "d2h_bytes_per_step": 64,
+                    "includes": "H2D of uint8 images + targets, step, optimizer, D2H of the loss"},
+            "allreduce": {"bytes_per_step": nbytes if world > 1 else 0, "buckets": len(step.eng.bucket_range), "dtype": "f32",
+                          "ms_first_bucket_to_done": ar_ms, "world": world},
+            "launches_per_step": 2 + f + b + 8, "graph": bool(graph),
+            "loss_first_step": first_loss, "loss_after_training_steps": last_loss,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "algorithmic_gflop_per_img": gflop_img,
+                         "note": "3 x the deploy-form forward FLOPs (fwd + dgrad + wgrad), SURVEY.md 8d; the train form executes ~9 % more"}}
+
+
+def free_cuda():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     ap.add_argument("--model", default="yolov6s")
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--steps-ref", type=int, default=3)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fp32-mode leg and the other BASELINE configs")
     args = ap.parse_args()
+    if args.size is None:
+        args.size = 1280 if args.model == "yolov6l6" else 640
+    if args.batch is None:
+        args.batch = 32 if args.model != "yolov6l6" else 2
     if args.impl == "reference":
         return run_reference(args)
 
@@ -179,76 +383,71 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    from yolov6_b200.model import build_model
-    from yolov6_b200.nms import nms_batched
-    from yolov6_b200.synth import randomize_
-
-    model = randomize_(build_model(args.model, 80, dev), seed=0)   # seeded synthetic checkpoint
-    model.eval().set_precision(args.precision)
-    eng = model.engine()
-    B, S = args.batch, args.size
-    g = torch.Generator().manual_seed(1 + rank)   # per-rank data like tools/train.py:104 seeds per rank
-    host_u8 = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8).pin_memory() for _ in range(2)]
-    dev_f32 = [h.to(dev).float() / 255 for h in host_u8]   # 157 MB each > 126 MB L2
-
-    from yolov6_b200.pipeline import DetectPipeline
+    W = max(args.warmup, 3)
     use_graph = not args.no_graph
-    if use_graph:
-        # steady state = one CUDA-graph launch per batch (yolov6_b200/pipeline.py); two pipelines with
-        # separate static buffers alternate so that consecutive steps never reuse a cached input
-        pipes_dev = [DetectPipeline(model, B, S, S, host_input=False, **NMS_KW) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)   # H2D of batch i+1 overlaps the kernels of batch i
-        pipes_e2e = [DetectPipeline(model, B, S, S, host_input=True, overlap_h2d=True, copy_stream=copy_stream, **NMS_KW)
-                     for _ in range(2)]
-        for i in range(2):
-            pipes_dev[i].x_dev.copy_(dev_f32[i])
-            pipes_e2e[i].x_host.copy_(host_u8[i])
+    B, S = args.batch, args.size
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    peaks = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    short = max(5, min(args.steps, 20))
 
-        def step_device(i):
-            pipes_dev[i & 1].launch()
-
-        def step_e2e(i):
-            pipes_e2e[i & 1].launch()          # H2D (39 MB u8, copy stream) -> graph: kernels -> D2H detections
-    else:
-        def step_device(i):
-            pred = eng.forward(dev_f32[i & 1])
-            return nms_batched(pred, **NMS_KW)
-
-        def step_e2e(i):
-            x = host_u8[i & 1].to(dev, non_blocking=True)
-            pred = eng.forward(x)
-            out, count, _, _ = nms_batched(pred, **NMS_KW)
-            return out.cpu(), count.cpu()
-
-    def barrier():
+    if args.mode == "train":
+        tr = bench_train(args.model, B, S, args.steps, W, rank, world, dev, graph=use_graph)
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        if rank == 0:
+            line = {"metric": f"images/sec {args.model} {S} bs{B} training step", "value": tr["value"], "unit": "images/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": W, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "bf16 (fp32 master weights, fp32 accumulation)", "data": "synthetic",
+                    "config": {"workload": f"{args.model} {S}x{S} bs{B}/GPU training step: {tr['step']}",
+                               "targets": "synthetic COCO-shaped (Poisson(7.3) boxes per image)", "weights": "random init",
+                               "parallelism": f"dp{world} image-sharded, one gradient all-reduce (sum) per step",
+                               "l2": "activations (> 5 GB per step) exceed the 126 MB L2",
+                               "launch": "CUDA graph segments (TrainStep)" if use_graph else "eager ctypes launches"},
+                    "e2e": tr["e2e"], "gpu_launches": tr["launches_per_step"] * args.steps, "roofline": tr["roofline"],
+                    "train": {k: v for k, v in tr.items() if k not in ("e2e", "roofline", "value", "unit", "ms_per_step")},
+                    "clocks": sampler.summary()}
+            print(json.dumps(line), flush=True)
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / steps
-
-    with torch.no_grad():
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        ms_dev = timed(step_device, args.steps, max(args.warmup, 3))
-        ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
-        sampler.stop_flag = True                # sampled across both timed regions
-        # roofline of the dominant kernel (conv_igemm): CUDA events around every conv launch of 5 steps
-        conv_ms, conv_flop, n_conv = eng.profile_convs(dev_f32[0], steps=5)
+    # ---------------------------------------------------------------- inference headline (BASELINE.json config 2)
+    main_r = bench_infer(args.model, B, S, args.steps, W, rank, world, dev, precision=args.precision, graph=use_graph)
+    model, x0 = main_r.pop("_model"), main_r.pop("_input")
+    modes, check, extra = {}, None, {}
+    if not args.no_extra:
+        check = precision_check(model, x0, dev)
+        other = "fp32" if args.precision == "bf16" else "bf16"
+        del model
+        free_cuda()
+        r2 = bench_infer(args.model, B, S, short, 3, rank, world, dev, precision=other, e2e=False, roofline=False, graph=use_graph)
+        r2.pop("_model"), r2.pop("_input")
+        modes = {args.precision: {"value": main_r["value"], "ms_per_step": main_r["ms_per_step"]},
+                 other: {"value": r2["value"], "ms_per_step": r2["ms_per_step"], "steps": short}}
+        modes["note"] = "fp32 = bf16x3 split operands (fp32-equivalent products, fp32 accumulation): the mode that meets the 1e-4 bar"
+        del r2
+        free_cuda()
+        # the other GPU configurations of BASELINE.json, per-GPU shard sizes, short runs
+        try:
+            t3 = bench_train("yolov6s", 32, 640, short, 3, rank, world, dev, graph=use_graph)
+            extra["config3_yolov6s_bs32_train_step"] = t3
+            free_cuda()
+            t4 = bench_train("yolov6m", 8, 640, short, 3, rank, world, dev, graph=use_graph)
+            extra["config4_yolov6m_bs8_per_gpu_train_step"] = t4
+            free_cuda()
+            r5 = bench_infer("yolov6l6", 2, 1280, short, 3, rank, world, dev, precision="bf16", e2e=True, roofline=True, graph=use_graph)
+            r5.pop("_model"), r5.pop("_input")
+            c5 = r5.pop("conv")
+            r5["roofline"] = {"bound": "tensor", "achieved": c5["flop"] / (c5["ms"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                              "frac": c5["flop"] / (c5["ms"] * 1e-3) / 1e12 / peak_tf, "conv_ms_per_step": c5["ms"], "launches_per_step": c5["launches"]}
+            extra["config5_yolov6l6_1280_bs2_per_gpu_inference"] = r5
+            free_cuda()
+        except Exception as e:  # noqa: BLE001 -- the headline must survive a failure of an auxiliary measurement
+            extra["error"] = f"{type(e).__name__}: {e}"
+    sampler.stop_flag = True
     sampler.join(timeout=2)
 
     if rank != 0:
@@ -256,45 +455,50 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         return
-    peaks = {}
-    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk_path):
-        with open(pk_path) as f:
-            peaks = json.load(f)
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    achieved_tf = conv_flop / (conv_ms * 1e-3) / 1e12
-    nms_launches = 3              # nms_select, nms_sort, nms_greedy
+    conv = main_r["conv"]
+    achieved_tf = conv["flop"] / (conv["ms"] * 1e-3) / 1e12
     traffic = None                # DRAM bytes per conv launch from the committed ncu capture (profiles/)
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+    for tname in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+            break
     line = {
-        "metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC if (args.model, B, S) == ("yolov6s", 32, 640) else f"images/sec {args.model} {S} bs{B}",
+        "value": main_r["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-equivalent)", "data": "synthetic",
         "config": {"workload": f"{args.model} {S}x{S} bs{B}/GPU inference: forward + decode + batched NMS",
                    "nms": NMS_KW, "weights": "seeded random (yolov6_b200/synth.py)", "parallelism": f"dp{world} image-sharded, no collective",
-                   "l2": "inputs (157 MB fp32 per batch, two alternating buffers) exceed the 126 MB L2",
+                   "l2": f"inputs ({B * 3 * S * S * 4 / 1e6:.0f} MB fp32 per batch, two alternating buffers) exceed the 126 MB L2"
+                         if B * 3 * S * S * 4 > 126e6 else "two alternating input buffers; activations of one step exceed the 126 MB L2",
                    "launch": "one CUDA graph per batch (DetectPipeline)" if use_graph else "eager ctypes launches",
                    "e2e_pipeline": "two alternating pipelines; the pinned-host -> device copy of a batch runs on a copy stream and "
                                    "overlaps the kernels of the previous batch; detections are copied back inside the graph"},
-        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * NMS_KW["max_det"] * 6 * 4 + B * 4},
-        "gpu_launches": (eng.launch_count(B, S, S) + nms_launches) * args.steps,
+        "e2e": main_r["e2e"],
+        "gpu_launches": main_r["launches_per_step"] * args.steps,
         "roofline": {"bound": "tensor", "kernel": "yv6::conv_igemm_kernel", "achieved": achieved_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                      "traffic_note": "bytes per conv_igemm launch, ncu dram__bytes_read+write averaged over the step's launches "
-                                     "(profiles/r01_conv_traffic.json); algorithmic activation bytes per launch = "
-                                     f"{eng.conv_bytes_per_launch(B, S, S):.3e}",
+                                     f"(profiles/); algorithmic activation bytes per launch = {conv['bytes_per_launch']:.3e}",
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
-                     "launches_per_step": n_conv, "conv_ms_per_step": conv_ms, "algorithmic_gflop_per_step": conv_flop / 1e9,
+                     "frac_of_burst_peak": achieved_tf / float(peaks.get("bf16_tflops", 1661.3)),
+                     "launches_per_step": conv["launches"], "conv_ms_per_step": conv["ms"], "algorithmic_gflop_per_step": conv["flop"] / 1e9,
                      "model_gflop_per_img": GFLOP_PER_IMG.get(args.model)},
         "clocks": sampler.summary(),
     }
+    if modes:
+        line["modes"] = modes
+    if check:
+        line["precision_check"] = check
+    if extra:
+        line["configs"] = extra
     if not args.no_cpu_baseline and world == 1:
         from oracle import model as om        # CPU-baseline leg: the checker, timed on the host cores
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        from yolov6_b200.model import build_model
+        from yolov6_b200.synth import randomize_
+        sd = {k: v.detach().cpu() for k, v in randomize_(build_model(args.model, 80, torch.device("cpu")), seed=0).state_dict().items()}
         xs = torch.rand(args.ref_batch, 3, S, S, generator=torch.Generator().manual_seed(0))
         cores = pick_threads(lambda: cpu_reference_step(sd, om.CONFIGS[args.model], xs[:1], NMS_KW))
         t0 = time.perf_counter()

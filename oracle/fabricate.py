@@ -68,6 +68,20 @@ def synthetic_predictions(batch, anchors, num_classes, seed=0, clusters=12, img=
     return torch.cat([cxy, wh, torch.ones(batch, anchors, 1), cls], -1).float()
 
 
+def synthetic_predictions_sparse(batch, anchors, num_classes, seed=0, density=0.012, clusters=12, img=640.0):
+    """Like `synthetic_predictions`, but only a fraction `density` of the (anchor, class) scores is above the Evaler's
+    conf 0.03 (the rest sits at ~1e-3): ~6000 candidates per 8400-anchor image, the load of the benchmark workload."""
+    g = torch.Generator().manual_seed(2500 + seed)
+    centers = torch.rand(batch, clusters, 2, generator=g) * (img - 40) + 20
+    which = torch.randint(0, clusters, (batch, anchors), generator=g)
+    cxy = torch.gather(centers, 1, which[..., None].expand(batch, anchors, 2)) + torch.randn(batch, anchors, 2, generator=g) * 6
+    wh = torch.rand(batch, anchors, 2, generator=g) * 80 + 10
+    hot = torch.rand(batch, anchors, num_classes, generator=g) < density
+    cls = torch.where(hot, torch.rand(batch, anchors, num_classes, generator=g) ** 2 * 0.9 + 0.03,
+                      torch.rand(batch, anchors, num_classes, generator=g) * 2e-3)
+    return torch.cat([cxy, wh, torch.ones(batch, anchors, 1), cls], -1).float()
+
+
 def synthetic_head_outputs(batch, sizes, num_classes, reg_ch, seed=0):
     """Seeded train-form head outputs: cls [B,A,nc] post-sigmoid, reg [B,A,reg_ch] (ltrb distances in
     stride units when reg_ch == 4, DFL logits otherwise)."""

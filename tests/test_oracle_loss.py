@@ -57,3 +57,26 @@ def test_preprocess_pads_and_scales():
     assert out[1].tolist() == [[-1, 0, 0, 0, 0]] * 2
     np.testing.assert_allclose(out[0, 0].numpy(), [3, 256, 192, 384, 448], rtol=1e-6)
     assert oloss.preprocess_targets(torch.zeros(0, 6), 2, torch.tensor([640.0] * 4)).shape == (2, 0, 5)
+
+
+def test_loss_at_640_batch_32_matches_reference():
+    """BASELINE.json config 3's loss: 640x640, batch 32, A = 8400, COCO-shaped targets (make_golden_configs.py)."""
+    g = golden_npz("configs.npz")
+    B, img, strides, nc = 32, 640, [8, 16, 32], 80
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = fab.synthetic_head_outputs(B, sizes, nc, 4, seed=60)
+    targets = oloss.synthetic_targets(B, seed=61, num_classes=nc)
+    chk = fab.checksum(ps) + fab.checksum(pd) + fab.checksum(targets)
+    assert abs(chk - float(g["loss640_in_checksum"])) <= 1e-9 * abs(chk), "RNG drift"
+    ps.requires_grad_(True)
+    pd.requires_grad_(True)
+    loss, items, asg = oloss.compute_loss(sizes, ps, pd, targets, strides=strides, num_classes=nc, ori_img_size=img, warmup_epoch=0,
+                                          epoch_num=0, use_dfl=False, reg_max=0, iou_type="giou", return_assign=True)
+    g_ps, g_pd = torch.autograd.grad(loss, [ps, pd])
+    fg = asg["fg"].numpy()
+    assert np.array_equal(np.packbits(fg), g["loss640_fg"])
+    assert np.array_equal(asg["labels"].numpy()[fg], g["loss640_labels_fg"].astype(np.int64))
+    assert abs(loss.item() - float(g["loss640_loss"])) <= 1e-10 * abs(loss.item())
+    np.testing.assert_allclose(items.double().numpy(), g["loss640_items"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(g_pd[asg["fg"]].double().numpy(), g["loss640_grad_distri_fg"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(g_ps.double().abs().sum(-1)[:, ::64].numpy(), g["loss640_grad_scores_rowabs"], rtol=1e-9, atol=1e-12)

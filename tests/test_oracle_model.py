@@ -90,3 +90,17 @@ def test_oracle_train_mode_matches_reference(name, batch, size):
         if k.startswith("grad::"):
             n = k[6:]
             np.testing.assert_allclose(sd64[n].grad.numpy().reshape(g[k].shape), g[k], rtol=1e-7, atol=1e-9 * (1 + np.abs(g[k]).max()))
+
+
+@pytest.mark.parametrize("name,B,size,step", [("yolov6s", 4, 640, 16), ("yolov6l6", 1, 1280, 32)])
+def test_oracle_matches_reference_at_benchmark_size(name, B, size, step):
+    """BASELINE.json configs 2 / 5: 640x640 (A = 8400) and 1280x1280 (A = 34000) goldens of make_golden_configs.py."""
+    g = golden_npz("configs.npz")
+    sd = fab.fabricate_state_dict(golden_keys(name), seed=0)
+    x = fab.synthetic_images(B, size, size, seed=40)
+    assert abs(fab.checksum(x) - float(g[f"{name}_x_checksum"])) < 1e-9 * abs(float(g[f"{name}_x_checksum"])), "input RNG drift"
+    with torch.no_grad():
+        out = om.forward(sd, om.CONFIGS[name], x).double().numpy()
+    assert rel_err(out[:, ::step], g[f"{name}_rows"].astype(np.float64)) < 1e-5
+    A = out.shape[1]
+    assert float((np.abs(out.sum(1) - g[f"{name}_colsum"]) / (A + g[f"{name}_abs_colsum"])).max()) < 1e-5

@@ -2,7 +2,7 @@
 non_max_suppression outputs stored by tests/golden/make_golden.py."""
 import numpy as np
 
-from conftest import golden_json, golden_npz
+from conftest import golden_json, golden_npz, same_up_to_score_ties
 from oracle import fabricate as fab
 from oracle import nms as onms
 
@@ -63,3 +63,20 @@ def test_nms_oracle_extra_regimes_vs_reference():
         got, ref = np.concatenate(out), g[f"c{i}_rows"]
         assert np.array_equal(got[:, 4], ref[:, 4]), f"extra case {i}: confidences differ"
         assert np.array_equal(canon(got), canon(ref)), f"extra case {i}: kept rows differ"
+
+
+def test_oracle_matches_reference_at_eval_batch_settings():
+    """B = 32 / A = 8400 Evaler settings incl. the ~390 k-candidate regime (tests/golden/make_golden_configs.py)."""
+    g = golden_npz("configs.npz")
+    kw = dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)
+    for tag, B, gen in (("sparse", 4, fab.synthetic_predictions_sparse), ("dense", 1, fab.synthetic_predictions)):
+        full_B = 32 if tag == "sparse" else 4
+        p = gen(full_B, 8400, 80, 70)[:B]           # the oracle is slow: first images only
+        out = onms.non_max_suppression(p.numpy(), **kw)
+        counts = g[f"nms_{tag}_counts"]
+        rows = g[f"nms_{tag}_rows"]
+        off = 0
+        for b in range(B):
+            assert out[b].shape[0] == counts[b]
+            assert same_up_to_score_ties(out[b], rows[off:off + counts[b]])
+            off += counts[b]

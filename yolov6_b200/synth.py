@@ -36,3 +36,18 @@ def randomize_(model, seed=0):
             v = torch.randn(shape, generator=g) * 0.1
         t.copy_(v.to(t.device, t.dtype))
     return model
+
+
+def synthetic_targets(batch, seed=1, mean_per_image=7.3, num_classes=80, max_per_image=60):
+    """COCO-shaped synthetic labels (SURVEY.md 8d config 3): per image n ~ clip(Poisson(7.3), 1, 60); cls ~ U{0..nc-1};
+    w, h ~ U(.02, .6); centres uniform such that the box stays inside.  Rows (img, cls, cx, cy, w, h), fp32, normalised --
+    the layout of the reference's collate_fn (yolov6/data/datasets.py:299-304)."""
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for b in range(batch):
+        n = int(torch.poisson(torch.tensor([mean_per_image]), generator=g).clamp(1, max_per_image).item())
+        cls = torch.randint(0, num_classes, (n, 1), generator=g).float()
+        wh = torch.rand(n, 2, generator=g) * 0.58 + 0.02
+        cxy = wh / 2 + torch.rand(n, 2, generator=g) * (1 - wh)
+        rows.append(torch.cat([torch.full((n, 1), float(b)), cls, cxy, wh], 1))
+    return torch.cat(rows).float()
