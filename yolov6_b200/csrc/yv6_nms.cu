@@ -220,6 +220,10 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
 // hold more than `cap` keys (tens of thousands of scores equal to 8 significant bits) is `overflow` raised.
 __device__ __forceinline__ int score_bin(float s) { return (int)((__float_as_uint(s) >> 19) & (kHistBins - 1)); }
 
+constexpr int kOverflowRows = 64;
+template <bool EMIT>
+__device__ __forceinline__ void overflow_row(const NmsParams& p, int b, int a, int lane, int cut);
+
 template <bool EMIT>
 __global__ void __launch_bounds__(256) nms_overflow_pass_kernel(const NmsParams p) {
   const int b = blockIdx.y;
@@ -231,8 +235,14 @@ __global__ void __launch_bounds__(256) nms_overflow_pass_kernel(const NmsParams 
   } else if (p.ws.cand_count[b] <= p.ws.cap) {
     return;
   }
-  const int a = blockIdx.x * 8 + warp;
-  if (a >= p.A) return;
+  // one warp per anchor row, 64 rows per warp: the grid stays small, so the launch costs next to nothing for the
+  // images that did not overflow (every block of such an image returns above)
+  for (int a = (blockIdx.x * 8 + warp) * kOverflowRows, a_end = min(p.A, a + kOverflowRows); a < a_end; ++a)
+    overflow_row<EMIT>(p, b, a, lane, cut);
+}
+
+template <bool EMIT>
+__device__ __forceinline__ void overflow_row(const NmsParams& p, int b, int a, int lane, int cut) {
   const float* row = p.pred + ((int64_t)b * p.A + a) * p.no;
   const float obj = __ldg(row + 4);
   float raw_max = -INFINITY;
@@ -553,7 +563,7 @@ extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int3
   nms_select_kernel<<<grid, kNmsTile, 0, s>>>(p);
   if (p.ws.hist != nullptr) {   // A * nc exceeds the key capacity: keep the max_nms best of an overflowing image (nms.py:90-91)
     YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.hist, 0, sizeof(uint32_t) * (size_t)B * kHistBins, s));
-    dim3 g8((A + 7) / 8, B);
+    dim3 g8((A + 8 * kOverflowRows - 1) / (8 * kOverflowRows), B);
     nms_overflow_pass_kernel<false><<<g8, 256, 0, s>>>(p);
     nms_cutoff_kernel<<<B, 1024, 0, s>>>(p);
     nms_overflow_pass_kernel<true><<<g8, 256, 0, s>>>(p);

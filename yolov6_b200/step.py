@@ -66,13 +66,19 @@ class TrainStep:
 
     def _capture(self, epoch_num):
         nseg = len(self._segments()[0])
-        side = torch.cuda.Stream(device=self.dev)
+        fl = self.eng.flat
+        snap = (fl.pflat.clone(), fl.gflat.clone(), fl.iflat.clone())   # warm-up runs must not train: running statistics,
+        side = torch.cuda.Stream(device=self.dev)                       # batch counters and accumulated gradients are restored
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             for _ in range(2):                      # plans, tensor maps, cudaFuncSetAttribute, allocator warm-up
                 for j in range(nseg):
                     self._segment(j, epoch_num)
         torch.cuda.current_stream(self.dev).wait_stream(side)
+        fl.pflat.copy_(snap[0])
+        fl.gflat.copy_(snap[1])
+        fl.iflat.copy_(snap[2])
+        del snap
         torch.cuda.synchronize(self.dev)
         graphs = []
         pool = None
