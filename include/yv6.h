@@ -96,6 +96,11 @@ typedef struct yv6_conv_desc {
   int32_t pad_w, out_h, out_w;
   int32_t force_groups;     /* epilogue warp groups: 0 auto (4 when BN <= 128, else 2), 2 = force two */
   void* trace;              /* debug: device uint64[16] receiving clock64 stamps of CTA 0's phases, or NULL */
+  /* ABI 2: column stride when it differs from the row stride (0 = `stride`).  A 3x3 stride-2 conv over few channels runs
+   * faster on the "column-pair" view of its input -- [N, H, W/2, 2*Cin], a pure reinterpretation of NHWC memory -- as a
+   * 3x2 kernel with stride (2, 1), pad_w = 1, out_w = W/2: the A rows become contiguous 2*Cin-channel pixels instead of
+   * every other Cin-channel pixel (see yolov6_b200/engine.py). */
+  int32_t stride_w;
 } yv6_conv_desc;
 
 int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);
@@ -158,6 +163,14 @@ int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int32_t A, int3
                     double iou_thres, int32_t agnostic, int32_t multi_label, const uint8_t* class_mask,
                     int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Evaluation post-processing of the batched NMS output: Evaler.scale_coords + box_convert + the top-left
+ * shift of Evaler.convert_to_coco_format (yolov6/core/evaler.py:333-373) for all images in one launch.
+ * det [B,max_det,6] (xyxy, conf, cls) and count [B] as written by yv6_nms_batched; meta [B,6] fp32 = (gain_h, gain_w, pad_x,
+ * pad_y, h0, w0) per image; out [B,max_det,6] = (x_topleft, y_topleft, w, h, conf, cls) in original-image pixels, rows
+ * beyond count[b] zeroed.  fp32 operation order of the reference (identical decimal output). */
+int yv6_eval_boxes(yv6_handle* h, const float* det, const int32_t* count, const float* meta, int32_t B, int32_t max_det,
+                   float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training-side irregular work: target preprocessing, label assignment, fused loss.
@@ -246,6 +259,7 @@ typedef struct yv6_wgrad_desc {
   int32_t kh, kw, stride, pad;
   float* dw;                                            /* fp32 [Cout][kh][kw][Cin]                            */
   int32_t force_ksplit;                                 /* 0 = auto                                            */
+  int32_t force_taps;                                   /* ABI 2: 0 = auto (3x3: one CTA accumulates a filter row), 1 = one tap per CTA */
 } yv6_wgrad_desc;
 int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stream);
 
@@ -319,6 +333,12 @@ int yv6_stem_wgrad(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale
 int yv6_stem_wgrad2(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy3, int64_t dy3_pitch,
                     const void* dy1, int64_t dy1_pitch, int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw3, float* dw1,
                     int32_t zeroed, void* stream);
+
+/* im2col of the 3-channel stem conv (3x3, stride 2, pad 1): patches bf16 [N, Ho, Wo, 32] with channel (r*3+s)*3 + c =
+ * x[n, c, 2ho+r-1, 2wo+s-1] (x as in yv6_stem_fwd: NCHW fp32 or uint8 * in_scale), channels 27..31 zero.  With it the stem's
+ * weight gradient is a 1x1 yv6_conv_wgrad over (patches, dY): dw [Cout][32] fp32. */
+int yv6_stem_im2col(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, int32_t N, int32_t H, int32_t W,
+                    void* patches_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Step-level plumbing of the training engine: everything that the reference does with

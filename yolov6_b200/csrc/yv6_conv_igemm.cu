@@ -42,7 +42,7 @@ struct ConvKParams {
   int32_t BW, BH, BI, rows;
   int32_t tiles_w, tiles_h, tiles_i, tiles_n, num_tiles;
   int32_t N, Ho, Wo, Cout, BN;
-  int32_t taps, kw, stride, pad, pad_w, Cin;   // pad = rows (h), pad_w = columns
+  int32_t taps, kw, stride, stride_w, pad, pad_w, Cin;   // stride / pad = rows (h), stride_w / pad_w = columns
   int32_t cin_blocks, kb_elems, kb_bytes, ksteps;
   int32_t sbo_bytes, layout_type;
   int32_t npairs;
@@ -440,7 +440,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = tap / p.kw, s = tap - r * p.kw;
-          const int cx = t.w0 * p.stride + s - p.pad_w;
+          const int cx = t.w0 * p.stride_w + s - p.pad_w;
           const int cy = t.h0 * p.stride + r - p.pad;
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -789,6 +789,8 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   YV6_REQUIRE(d->Cout > 0, "conv: Cout=%d", d->Cout);
   YV6_REQUIRE(d->kh >= 1 && d->kh <= 3 && d->kw >= 1 && d->kw <= 3, "conv: kernel %dx%d unsupported", d->kh, d->kw);
   YV6_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
+  YV6_REQUIRE(d->stride_w >= 0 && d->stride_w <= 2, "conv: stride_w %d unsupported", d->stride_w);
+  const int stride_w = d->stride_w > 0 ? d->stride_w : d->stride;
   YV6_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "conv: nsplit must be 1 or 3");
   YV6_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0,
               "conv: x / w must be 16-byte aligned");
@@ -801,13 +803,14 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // the parity sub-problems of a stride-2 dgrad, whose far-side reads rely on TMA zero fill)
   const int pad_w = (d->pad_w == YV6_PAD_SAME) ? d->pad : d->pad_w;
   k.Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->kh) / d->stride + 1;
-  k.Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * pad_w - d->kw) / d->stride + 1;
+  k.Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * pad_w - d->kw) / stride_w + 1;
   YV6_REQUIRE(k.Ho > 0 && k.Wo > 0, "conv: empty output");
   k.Cout = d->Cout;
   k.Cin = d->Cin;
   k.taps = d->kh * d->kw;
   k.kw = d->kw;
   k.stride = d->stride;
+  k.stride_w = stride_w;
   k.pad = d->pad;
   k.pad_w = pad_w;
 
@@ -836,12 +839,12 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     k.BW = d->force_bw;
     k.BH = std::max(1, d->force_bh);
     k.BI = std::max(1, d->force_bi);
-    YV6_REQUIRE(k.BW * k.BH * k.BI <= kTileRows && k.BW * d->stride <= 256 && k.BH * d->stride <= 256,
+    YV6_REQUIRE(k.BW * k.BH * k.BI <= kTileRows && k.BW * stride_w <= 256 && k.BH * d->stride <= 256,
                 "conv: forced tile %dx%dx%d invalid", k.BW, k.BH, k.BI);
   } else {
     long best_tiles = -1, best_box_tiles = -1;
     int bestw = 1, besth = 1, besti = 1, boxw = 0, boxh = 0;
-    const int maxbw = std::min(std::min(k.Wo, kTileRows), 256 / d->stride);
+    const int maxbw = std::min(std::min(k.Wo, kTileRows), 256 / stride_w);
     for (int bw = 1; bw <= maxbw; ++bw) {
       const int maxbh = std::min(std::min(k.Ho, kTileRows / bw), 256 / d->stride);
       for (int bh = 1; bh <= maxbh; ++bh) {
@@ -858,7 +861,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     }
     // "warp-box" tiles: 128 rows whose 32-row quarters are boxes of the output (BW | 32 or 32 | BW), which
     // lets every epilogue warp TMA-store its own rows without a block barrier; preferred within 8 % of the best
-    for (int bw = 1; bw <= std::min(kTileRows, 256 / d->stride); bw <<= 1) {
+    for (int bw = 1; bw <= std::min(kTileRows, 256 / stride_w); bw <<= 1) {
       const int bh = kTileRows / bw;
       if (bh * d->stride > 256) continue;
       long tiles = (long)ceil_div(k.Wo, bw) * ceil_div(k.Ho, bh) * d->N;
@@ -880,7 +883,7 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // halo mode: 3x3 stride-1 with 64-channel K blocks and an 8x16 output tile; taken when its fixed tile
   // shape costs at most 25% more tiles than the best free-form box (it moves ~6x fewer A bytes)
   k.halo = 0;
-  if (d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && pad_w == 1 && d->out_h == 0 && d->out_w == 0 &&
+  if (d->kh == 3 && d->kw == 3 && d->stride == 1 && stride_w == 1 && d->pad == 1 && pad_w == 1 && d->out_h == 0 && d->out_w == 0 &&
       d->Cin % 64 == 0 && d->force_bw == 0 && d->force_halo >= 0) {
     const long generic = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
     const long halo_tiles = (long)ceil_div(k.Wo, 8) * ceil_div(k.Ho, 16) * d->N;
@@ -1036,13 +1039,13 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
                                              : (uint64_t)d->N * d->H * d->W * pix;
     YV6_REQUIRE(plane_stride % 16 == 0, "conv: x_plane_stride must be a multiple of 8 elements");
     cuuint64_t strides[4] = {pix, pix * d->W, pix * d->W * d->H, plane_stride};
-    cuuint32_t box[5] = {(cuuint32_t)k.kb_elems, (cuuint32_t)(k.BW * d->stride), (cuuint32_t)(k.BH * d->stride),
+    cuuint32_t box[5] = {(cuuint32_t)k.kb_elems, (cuuint32_t)(k.BW * k.stride_w), (cuuint32_t)(k.BH * d->stride),
                          (cuuint32_t)k.BI, 1};
     if (k.halo) {
       box[1] = kHaloW;
       box[2] = kHaloH;
     }
-    cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)k.stride_w, (cuuint32_t)d->stride, 1, 1};
     CUresult cr = h->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->x), dims,
                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, plan.swz,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

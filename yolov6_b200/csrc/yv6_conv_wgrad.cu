@@ -20,17 +20,21 @@
 namespace yv6 {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgMaxStages = 6;
+constexpr int kWgMaxStages = 8;
+constexpr int kWgMaxTaps = 3;          // filter taps accumulated by one CTA (they share the dY tile)
 
 struct WgParams {
-  int32_t BW, BH, BI;                 // pixel box, BW*BH*BI == 128
+  int32_t BW, BH, PT;                 // pixel box, BW*BH == PT (128 or 64): the K extent of one pipeline stage
   int32_t tiles_w, tiles_h, tiles_i, ptiles;
   int32_t co_tiles, ci_tiles, taps, kw, ksplit;
+  int32_t T, tap_groups;              // taps per unit (1, or 3 = one filter row) and taps / T
   int32_t Cout, Cin, stride, pad;
-  int32_t a_blocks, b_blocks, b_blk_elems, b_blk_bytes;  // 64-wide dY blocks; X blocks of 64/32/16 channels
+  int32_t a_blocks, a_loaded;         // 64-wide dY blocks in the operand layout (2) and the ones TMA really fetches (1 if Cout <= 64)
+  int32_t b_blocks, b_blk_elems, b_blk_bytes;  // X blocks of 64/32/16 channels
   int32_t NT;                         // UMMA N = b_blocks * b_blk_elems (<= 256)
   int32_t b_layout, b_sbo;            // swizzle mode / 8-row group stride of the X blocks
-  int32_t stages, a_stage_bytes, b_stage_bytes;
+  int32_t stages, a_stage_bytes, b_tap_bytes, b_stage_bytes;
+  int32_t tmem_cols;
   float* dw;                          // fp32 [Cout][kh*kw][Cin]
 };
 
@@ -59,7 +63,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.b_stage_bytes);
+  float* sT = reinterpret_cast<float*>(sB + (size_t)p.stages * p.b_stage_bytes);   // epilogue transpose: 4 warps x [32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 4 * 32 * 33);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWgMaxStages;
   uint64_t* done = bars + 2 * kWgMaxStages;
@@ -69,9 +74,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   // unit decode: ks fastest so that concurrently running CTAs read different pixels of the same tensors
   int u = blockIdx.x;
   const int ks = u % p.ksplit; u /= p.ksplit;
-  const int tap = u % p.taps; u /= p.taps;
+  const int tg = u % p.tap_groups; u /= p.tap_groups;
   const int ci_t = u % p.ci_tiles; u /= p.ci_tiles;
   const int co_t = u;
+  const int tap0 = tg * p.T;
   const int per = (p.ptiles + p.ksplit - 1) / p.ksplit;
   const int pt0 = ks * per, pt1 = min(p.ptiles, pt0 + per);
   const int npt = max(0, pt1 - pt0);
@@ -83,15 +89,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t a_blk_bytes = (uint32_t)p.PT * 128u;                  // one 64-channel dY block: PT pixel rows of 128 bytes
 
   if (warp == 0) {
-    const int r = tap / p.kw, sx = tap - r * p.kw;
-    const uint32_t tx = (uint32_t)(p.a_blocks * 128 * 128 + p.b_blocks * 128 * p.b_blk_bytes);
+    const uint32_t tx = (uint32_t)p.a_loaded * a_blk_bytes + (uint32_t)(p.T * p.b_blocks * p.PT * p.b_blk_bytes);
     int stage = 0;
     uint32_t phase = 0;
     for (int pt = pt0; pt < pt1; ++pt) {
@@ -99,15 +105,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int tw = m % p.tiles_w; m /= p.tiles_w;
       const int th = m % p.tiles_h;
       const int ti = m / p.tiles_h;
-      const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
+      const int w0 = tw * p.BW, h0 = th * p.BH;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&full[stage], tx);
-        for (int j = 0; j < p.a_blocks; ++j)
-          wg_tma_4d(sA + (size_t)stage * p.a_stage_bytes + j * 16384, &tmDY, &full[stage], co_t * 128 + j * 64, w0, h0, i0);
-        for (int j = 0; j < p.b_blocks; ++j)
-          wg_tma_4d(sB + (size_t)stage * p.b_stage_bytes + (size_t)j * 128 * p.b_blk_bytes, &tmX, &full[stage],
-                    ci_t * p.NT + j * p.b_blk_elems, w0 * p.stride + sx - p.pad, h0 * p.stride + r - p.pad, i0);
+        for (int j = 0; j < p.a_loaded; ++j)
+          wg_tma_4d(sA + (size_t)stage * p.a_stage_bytes + (size_t)j * a_blk_bytes, &tmDY, &full[stage], co_t * 128 + j * 64, w0, h0, ti);
+        for (int t = 0; t < p.T; ++t) {
+          const int tap = tap0 + t;
+          const int r = tap / p.kw, sx = tap - r * p.kw;
+          uint8_t* dst = sB + (size_t)stage * p.b_stage_bytes + (size_t)t * p.b_tap_bytes;
+          for (int j = 0; j < p.b_blocks; ++j)
+            wg_tma_4d(dst + (size_t)j * p.PT * p.b_blk_bytes, &tmX, &full[stage], ci_t * p.NT + j * p.b_blk_elems,
+                      w0 * p.stride + sx - p.pad, h0 * p.stride + r - p.pad, ti);
+        }
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -115,11 +126,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   } else if (warp == 1) {
     // instruction descriptor: bf16 x bf16 -> fp32, both operands MN-major (bits 15 / 16), M = 128, N = NT
     const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.NT) | (1u << 15) | (1u << 16);
-    const uint64_t da = wg_desc(16384u, 1024u, 2u);
-    const uint64_t db = wg_desc((uint32_t)(128 * p.b_blk_bytes), (uint32_t)p.b_sbo, (uint32_t)p.b_layout);
+    const uint64_t da = wg_desc(a_blk_bytes, 1024u, 2u);
+    const uint64_t db = wg_desc((uint32_t)(p.PT * p.b_blk_bytes), (uint32_t)p.b_sbo, (uint32_t)p.b_layout);
     const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
-    const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)p.b_stage_bytes >> 4;
+    const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)p.b_stage_bytes >> 4, b_tap = (uint32_t)p.b_tap_bytes >> 4;
     const uint32_t a_k = 2048u >> 4, b_k = (uint32_t)(2 * p.b_sbo) >> 4;   // 16 pixels = two 8-row groups
+    const int ksteps = p.PT / 16;
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < npt; ++it) {
@@ -128,8 +140,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const uint64_t ad = da | (uint64_t)(a_base + (uint32_t)stage * a_step);
       const uint64_t bd = db | (uint64_t)(b_base + (uint32_t)stage * b_step);
       if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_base, ad + (uint64_t)(k * a_k), bd + (uint64_t)(k * b_k), idesc, (uint32_t)((it | k) != 0));
+        for (int t = 0; t < p.T; ++t) {
+          const uint64_t bt = bd + (uint64_t)((uint32_t)t * b_tap);
+          const uint32_t acc = tmem_base + (uint32_t)(t * p.NT);
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(acc, ad + (uint64_t)(k * a_k), bt + (uint64_t)(k * b_k), idesc, (uint32_t)((it | k) != 0));
+        }
         umma_commit(&empty[stage]);
       }
       __syncwarp();
@@ -138,21 +155,32 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     if (elect_one()) umma_commit(done);
     __syncwarp();
   } else {
+    // Epilogue: warp q owns TMEM lanes (= output channels) 32q..32q+31.  32x32 blocks go through a per-warp shared-memory
+    // transpose so that every reduction instruction adds 32 CONSECUTIVE floats of one dW row (one 128-byte line) instead of
+    // one float in each of 32 rows.
     const int q = warp & 3;
-    const int co = co_t * 128 + q * 32 + lane;
+    float* tr = sT + q * 32 * 33;
     mbar_wait(done, 0);
     tc_fence_after();
     if (npt > 0) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      float* out = p.dw + ((int64_t)co * p.taps + tap) * p.Cin + ci_t * p.NT;
-      for (int c0 = 0; c0 < p.NT; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (co < p.Cout) {
+      const int co_base = co_t * 128 + q * 32;
+      for (int t = 0; t < p.T; ++t) {
+        const int tap = tap0 + t;
+        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)(t * p.NT + c0), r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (ci_t * p.NT + c0 + j < p.Cin) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int ci = ci_t * p.NT + c0 + lane;
+          if (ci < p.Cin && c0 + lane < p.NT) {
+            float* out = p.dw + ((int64_t)co_base * p.taps + tap) * p.Cin + ci;
+            const int rows = min(32, p.Cout - co_base);
+            for (int row = 0; row < rows; ++row) atomicAdd(out + (int64_t)row * p.taps * p.Cin, tr[row * 33 + lane]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -161,7 +189,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -182,35 +210,48 @@ extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stre
   p.Cout = d->Cout; p.Cin = d->Cin; p.stride = d->stride; p.pad = d->pad;
   p.taps = d->kh * d->kw; p.kw = d->kw;
   p.dw = d->dw;
-  // pixel box: exactly 128 rows (partial boxes are zero filled by TMA, so the K sum stays exact)
-  long best = -1;
-  for (int bw = 1; bw <= 128; bw <<= 1) {
-    const int bh = 128 / bw;
-    if (bw * d->stride > 256 || bh * d->stride > 256) continue;
-    const long t = (long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * d->N;
-    if (best < 0 || t < best || (t == best && bw > p.BW)) { best = t; p.BW = bw; p.BH = bh; }
-  }
-  p.BI = 1;
-  p.tiles_w = (Wo + p.BW - 1) / p.BW; p.tiles_h = (Ho + p.BH - 1) / p.BH; p.tiles_i = d->N;
-  p.ptiles = p.tiles_w * p.tiles_h * p.tiles_i;
-  p.a_blocks = 2;
   p.b_blk_elems = (d->Cin % 64 == 0) ? 64 : (d->Cin % 32 == 0) ? 32 : 16;
   p.b_blk_bytes = p.b_blk_elems * 2;
   p.b_layout = (p.b_blk_bytes == 128) ? 2 : (p.b_blk_bytes == 64) ? 4 : 6;
   p.b_sbo = 8 * p.b_blk_bytes;
-  p.ci_tiles = (d->Cin + 255) / 256;
+  // 3x3: one CTA accumulates the three taps of a filter row -- they share the dY tile, which cuts the L2 -> SM operand
+  // stream per MMA by 1.5x (128 channels) to 2.3x (64 channels); the Cin tile is then at most 128 wide (3 x 128 TMEM columns).
+  p.T = (p.taps == 9 && d->force_taps != 1) ? 3 : 1;
+  const int nt_max = (p.T == 3) ? 128 : 256;
+  p.ci_tiles = (d->Cin + nt_max - 1) / nt_max;
   const int per_tile = (d->Cin + p.ci_tiles - 1) / p.ci_tiles;
   p.b_blocks = (per_tile + p.b_blk_elems - 1) / p.b_blk_elems;
   p.NT = p.b_blocks * p.b_blk_elems;
-  YV6_REQUIRE(p.NT % 16 == 0 && p.NT <= 256, "wgrad: N tile %d", p.NT);
+  YV6_REQUIRE(p.NT % 16 == 0 && p.NT <= nt_max, "wgrad: N tile %d", p.NT);
+  p.tap_groups = p.taps / p.T;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.T * p.NT) p.tmem_cols <<= 1;
+  p.PT = (p.T == 3) ? 64 : 128;
+  // pixel box: exactly PT rows (partial boxes are zero filled by TMA, so the K sum stays exact)
+  long best = -1;
+  for (int bw = 1; bw <= p.PT; bw <<= 1) {
+    const int bh = p.PT / bw;
+    if (bw * d->stride > 256 || bh * d->stride > 256) continue;
+    const long t = (long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * d->N;
+    if (best < 0 || t < best || (t == best && bw > p.BW)) { best = t; p.BW = bw; p.BH = bh; }
+  }
+  p.tiles_w = (Wo + p.BW - 1) / p.BW; p.tiles_h = (Ho + p.BH - 1) / p.BH; p.tiles_i = d->N;
+  p.ptiles = p.tiles_w * p.tiles_h * p.tiles_i;
+  p.a_blocks = 2;
+  p.a_loaded = (d->Cout <= 64) ? 1 : 2;     // rows 64..127 of the accumulator are never stored for Cout <= 64
   p.co_tiles = (d->Cout + 127) / 128;
-  p.a_stage_bytes = p.a_blocks * 16384;
-  p.b_stage_bytes = ((p.b_blocks * 128 * p.b_blk_bytes + 1023) / 1024) * 1024;
-  const int budget = h->max_smem_optin - 2048;
+  p.a_stage_bytes = p.a_blocks * p.PT * 128;
+  p.b_tap_bytes = ((p.b_blocks * p.PT * p.b_blk_bytes + 1023) / 1024) * 1024;
+  p.b_stage_bytes = p.T * p.b_tap_bytes;
+  const int fixed = 1024 /* alignment */ + 4 * 32 * 33 * 4 /* epilogue transpose */ + 512 /* barriers */;
+  const int budget = h->max_smem_optin - fixed;
   p.stages = std::min(kWgMaxStages, budget / (p.a_stage_bytes + p.b_stage_bytes));
   YV6_REQUIRE(p.stages >= 2, "wgrad: not enough shared memory");
-  const int base_units = p.co_tiles * p.ci_tiles * p.taps;
-  p.ksplit = std::max(1, std::min(p.ptiles, (2 * h->num_sms + base_units - 1) / base_units));
+  const int base_units = p.co_tiles * p.ci_tiles * p.tap_groups;
+  // split-K over pixel ranges: fill the SMs twice, but keep at least ~8 pipeline stages of work per CTA -- every extra
+  // split adds one full pass of fp32 reductions over the weight tensor
+  const int min_tiles = 8 * 128 / p.PT;
+  p.ksplit = std::max(1, std::min((p.ptiles + min_tiles - 1) / min_tiles, (2 * h->num_sms + base_units - 1) / base_units));
   if (d->force_ksplit > 0) p.ksplit = std::min(p.ptiles, d->force_ksplit);
   const int units = base_units * p.ksplit;
 
@@ -243,7 +284,7 @@ extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stre
     YV6_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
     h->configured |= YV6_CFG_WGRAD;
   }
-  const size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024 + 512;
+  const size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + fixed;
   conv_wgrad_kernel<<<units, kWgThreads, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;

@@ -493,6 +493,40 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
   if (threadIdx.x == 0) p.out_count[b] = s_kept;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation post-processing of the NMS output, all images at once: Evaler.scale_coords + box_convert + the
+// top-left shift of Evaler.convert_to_coco_format (yolov6/core/evaler.py:333-373), in the reference's fp32
+// operation order (explicit round-to-nearest ops, so the decimal strings the COCO json gets are identical):
+//   x -= pad_x; x /= gain_w; clamp(0, w0)   (same for y with pad_y / gain_h / h0)
+//   xc = (x1 + x2) / 2; w = x2 - x1; x_tl = xc - w / 2
+// meta [B][6] = (gain_h, gain_w, pad_x, pad_y, h0, w0) per image (shapes[i] of the reference's dataloader).
+__global__ void eval_boxes_kernel(const float* __restrict__ det, const int32_t* __restrict__ count, const float* __restrict__ meta,
+                                  int B, int max_det, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * max_det) return;
+  const int b = i / max_det, j = i - b * max_det;
+  float* o = out + (int64_t)i * 6;
+  if (j >= count[b]) {
+    o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f;
+    return;
+  }
+  const float* r = det + (int64_t)i * 6;
+  const float* m = meta + b * 6;
+  const float gh = m[0], gw = m[1], px = m[2], py = m[3], h0 = m[4], w0 = m[5];
+  const float x1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[0], px), gw), 0.f), w0);
+  const float y1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[1], py), gh), 0.f), h0);
+  const float x2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[2], px), gw), 0.f), w0);
+  const float y2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r[3], py), gh), 0.f), h0);
+  const float xc = __fdiv_rn(__fadd_rn(x1, x2), 2.f), yc = __fdiv_rn(__fadd_rn(y1, y2), 2.f);
+  const float w = __fsub_rn(x2, x1), hh = __fsub_rn(y2, y1);
+  o[0] = __fsub_rn(xc, __fdiv_rn(w, 2.f));
+  o[1] = __fsub_rn(yc, __fdiv_rn(hh, 2.f));
+  o[2] = w;
+  o[3] = hh;
+  o[4] = r[4];
+  o[5] = r[5];
+}
+
 static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
 static void nms_layout(int32_t B, int32_t A, int32_t nc, int32_t multi_label, NmsWs* ws, int64_t* total, char* base) {
@@ -580,3 +614,13 @@ extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int3
   return YV6_OK;
 }
 
+
+extern "C" int yv6_eval_boxes(yv6_handle* h, const float* det, const int32_t* count, const float* meta, int32_t B, int32_t max_det,
+                              float* out, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && det && count && meta && out && B > 0 && max_det > 0, "eval_boxes: bad argument");
+  const int total = B * max_det;
+  eval_boxes_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(det, count, meta, B, max_det, out);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}

@@ -585,6 +585,42 @@ __global__ void __launch_bounds__(kTrThreads) stem_wgrad_kernel(const void* x, i
   }
 }
 
+// ---------------------------------------------------------------------------------- stem im2col (for the stem's weight gradient)
+// patches[n, ho, wo, (r*3+s)*3 + c] = x[n, c, 2ho + r - 1, 2wo + s - 1] (zero outside the image), channels 27..31 zero, bf16.
+// The stem's weight gradient is then an ordinary 1x1 wgrad GEMM over (patches, dY) on the tensor cores
+// (K = all output pixels, M = Cout, N = 32), instead of 27 * Cout dot products of length N*Ho*Wo on CUDA cores.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const void* x, int x_u8, float in_scale, int N, int H, int W, __nv_bfloat16* out) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo;
+  for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < total; px += (int64_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(px % Wo), ho = (int)((px / Wo) % Ho), n = (int)(px / ((int64_t)Wo * Ho));
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = 2 * ho - 1 + r;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const int wi = 2 * wo - 1 + sx;
+        if (wi < 0 || wi >= W) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int64_t idx = (((int64_t)n * 3 + c) * H + hi) * W + wi;
+          v[(r * 3 + sx) * 3 + c] = x_u8 ? (float)reinterpret_cast<const uint8_t*>(x)[idx] * in_scale : reinterpret_cast<const float*>(x)[idx];
+        }
+      }
+    }
+    __nv_bfloat16* o = out + px * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
+      st8(o + 8 * j, t);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- table-driven repack
 // dst[d0][d1][d2][d3] (arbitrary strides) (+)= cast(src[d0][d1][d2][d3] (arbitrary, possibly negative strides)).
 // One launch repacks every parameter of the network: fp32 master weights -> bf16 KRSC forward weights, rotated /
@@ -875,6 +911,17 @@ extern "C" int yv6_stem_wgrad2(yv6_handle* h, const void* x, int32_t x_dtype, fl
 extern "C" int yv6_stem_wgrad(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, const void* dy, int64_t dy_pitch,
                               int32_t N, int32_t H, int32_t W, int32_t Cout, float* dw, void* stream) {
   return yv6_stem_wgrad2(h, x, x_dtype, in_scale, dy, dy_pitch, nullptr, 0, N, H, W, Cout, dw, nullptr, 0, stream);
+}
+
+extern "C" int yv6_stem_im2col(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, int32_t N, int32_t H, int32_t W,
+                               void* patches_bf16, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && x && patches_bf16 && N > 0 && H > 0 && W > 0, "stem_im2col: bad argument");
+  const int64_t total = (int64_t)N * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
+  stem_im2col_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, x_dtype == YV6_DT_U8, in_scale, N, H, W,
+                                                                                         reinterpret_cast<__nv_bfloat16*>(patches_bf16));
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
 }
 
 extern "C" int yv6_xform(yv6_handle* h, const yv6_xform_seg* segs_dev, const int32_t* chunk_seg_dev, const int32_t* chunk_first_dev,

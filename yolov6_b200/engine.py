@@ -40,6 +40,7 @@ class InferEngine:
         self.nsplit = 3 if precision == "fp32" else 1
         self.handle = _lib.handle(device.index or 0)
         self.lib = _lib.lib()
+        self.fuse_siblings = True
         self.weights = {}     # op index -> dict(w=..., bias=..., alpha=...)
         self._plans = {}      # (N, H, W, dtype) -> plan, least recently used first; bounded (rect-shaped evaluation
         self.max_plans = 4    # would otherwise keep one full activation set per distinct shape)
@@ -47,9 +48,27 @@ class InferEngine:
         self._pack(state_dict)
 
     # ------------------------------------------------------------------ weight packing
+    def _siblings(self):
+        """Pairs of convs that read the same tensor with the same geometry and can run as ONE launch over the
+        concatenated output channels: the cls / reg branches of the decoupled head (effidehead.py:79-84)."""
+        pairs = {}
+        ops = self.g.ops
+        for i, a in enumerate(ops):
+            if a.kind != "conv" or not a.name.startswith("detect.cls_convs."):
+                continue
+            for j in range(i + 1, min(i + 3, len(ops))):
+                b = ops[j]
+                if (b.kind == "conv" and b.name == a.name.replace("cls_convs", "reg_convs") and b.src == a.src and
+                        (b.k, b.s, b.act, b.cout, b.cin) == (a.k, a.s, a.act, a.cout, a.cin) and a.res is None and b.res is None and
+                        a.dst.c_off == 0 and b.dst.c_off == 0 and a.cout % 64 == 0):
+                    pairs[i] = j
+        return pairs
+
     def _pack(self, sd):
         sd = {k: v.detach().cpu() for k, v in sd.items()}
         dev = self.device
+        self.sibling = self._siblings() if self.fuse_siblings else {}
+        self.sibling_second = {j: i for i, j in self.sibling.items()}
         for i, op in enumerate(self.g.ops):
             if op.kind == "pool":
                 continue
@@ -65,11 +84,28 @@ class InferEngine:
                     wi = wi.float().to(dev)
                     packed.append(_split3(wi).contiguous() if self.nsplit == 3 else wi.to(torch.bfloat16).contiguous())
                 ent["w"] = packed
+                if op.kind == "conv" and op.k == 3 and op.s == 2 and op.cin <= 32:
+                    # column-pair view (see _plan): [Cout][3][2][2*Cin]; tap 0 = input columns (2j-2 | 2j-1), tap 1 = (2j | 2j+1)
+                    w33 = ws[0].float()
+                    wf = torch.zeros(op.cout, 3, 2, 2 * op.cin)
+                    wf[:, :, 0, op.cin:] = w33[:, :, 0]
+                    wf[:, :, 1, :op.cin] = w33[:, :, 1]
+                    wf[:, :, 1, op.cin:] = w33[:, :, 2]
+                    wf = wf.to(dev)
+                    ent["w_pair"] = _split3(wf).contiguous() if self.nsplit == 3 else wf.to(torch.bfloat16).contiguous()
                 bias = torch.zeros((op.cout + 255) // 256 * 256, dtype=torch.float32, device=dev)
                 bias[:op.cout] = b.float().to(dev)
                 ent["bias"] = bias
             ent["alpha"] = float(sd[op.alpha]) if (op.alpha and op.res is not None) else 1.0
             self.weights[i] = ent
+        for i, j in self.sibling.items():      # one conv with 2 x Cout output channels: [cls branch | reg branch]
+            (wa, ba), (wb, bb) = fold_op(sd, self.g.ops[i]), fold_op(sd, self.g.ops[j])
+            wf = torch.cat([wa, wb], 0).float().to(dev)
+            c2 = wf.shape[0]
+            bias = torch.zeros((c2 + 255) // 256 * 256, dtype=torch.float32, device=dev)
+            bias[:c2] = torch.cat([ba, bb]).float().to(dev)
+            self.weights[i]["w_fused"] = _split3(wf).contiguous() if self.nsplit == 3 else wf.to(torch.bfloat16).contiguous()
+            self.weights[i]["bias_fused"] = bias
 
     # ------------------------------------------------------------------ per-shape plan
     def _plan(self, N, H, W, in_dtype):
@@ -87,7 +123,7 @@ class InferEngine:
         maxs = max(g.strides)
         if H % maxs or W % maxs:
             raise RuntimeError(f"input {H}x{W} must be a multiple of the largest stride {maxs}")
-        plan = {"bufs": [], "calls": []}
+        plan = {"bufs": [], "calls": [], "conv_info": []}
         for b in g.bufs:
             h, w = H >> b.level, W >> b.level
             shape = (P, N, h, w, b.c_total) if P == 3 else (N, h, w, b.c_total)
@@ -105,11 +141,29 @@ class InferEngine:
         plan["lvl_s"] = (C.c_float * len(sizes))(*[float(s) for s in g.strides])
         plan["image"] = None
 
+        # sibling convs write one [.., 2C] buffer; their consumers read its two channel halves
+        redirect = {}       # graph buffer index -> (fused tensor, channel offset, channel pitch)
+        plan["fused_bufs"] = []
+        for i, j in self.sibling.items():
+            a, b2 = g.ops[i], g.ops[j]
+            lvl = g.bufs[a.dst.buf].level
+            h, w = H >> lvl, W >> lvl
+            shape = (P, N, h, w, 2 * a.cout) if P == 3 else (N, h, w, 2 * a.cout)
+            fb = torch.zeros(shape, dtype=torch.bfloat16, device=dev)
+            plan["fused_bufs"].append(fb)
+            redirect[a.dst.buf] = (fb, 0, 2 * a.cout)
+            redirect[b2.dst.buf] = (fb, a.cout, 2 * a.cout)
+
         def view(t):
-            buf = plan["bufs"][t.buf]
             b = g.bufs[t.buf]
             h, w = H >> b.level, W >> b.level
-            return buf, h, w, b.c_total
+            if t.buf in redirect:
+                fb, coff, pitch = redirect[t.buf]
+                return fb, h, w, pitch
+            return plan["bufs"][t.buf], h, w, b.c_total
+
+        def coff(t):
+            return t.c_off + (redirect[t.buf][1] if t.buf in redirect else 0)
 
         for i, op in enumerate(g.ops):
             ent = self.weights.get(i)
@@ -128,23 +182,42 @@ class InferEngine:
                 plan["stem"] = d
                 plan["calls"].append(("stem", d))
             elif op.kind in ("conv", "pred", "convT"):
+                if i in self.sibling_second:
+                    continue                      # computed by its sibling's launch
                 sbuf, sh, sw, sct = view(op.src)
                 quads = ent["w"] if op.kind == "convT" else [ent["w"][0]]
+                fused = i in self.sibling
                 for q, wq in enumerate(quads):
                     d = ConvDesc()
-                    d.x = sbuf.data_ptr() + op.src.c_off * 2
+                    d.x = sbuf.data_ptr() + coff(op.src) * 2
                     d.N, d.H, d.W, d.Cin, d.x_c_total = N, sh, sw, op.cin, sct
                     d.x_plane_stride = sbuf.stride(0) if P == 3 else 0
+                    if fused:
+                        wq = ent["w_fused"]
                     d.w = wq.data_ptr()
                     d.w_plane_stride = wq.stride(0) if P == 3 else 0
-                    d.bias = ent["bias"].data_ptr()
-                    d.Cout = op.cout
+                    d.bias = (ent["bias_fused"] if fused else ent["bias"]).data_ptr()
+                    d.Cout = op.cout * (2 if fused else 1)
                     d.kh = d.kw = 1 if op.kind == "convT" else op.k
                     d.stride = 1 if op.kind == "convT" else op.s
                     d.pad = d.kh // 2
                     d.pad_w = _lib.PAD_SAME
                     d.act = ACT_CODES[op.act]
                     d.nsplit = P
+                    oh, ow = (sh + 2 * d.pad - d.kh) // d.stride + 1, (sw + 2 * d.pad - d.kw) // d.stride + 1
+                    plan["conv_info"].append(dict(name=op.name if op.kind != "convT" else f"{op.name}[{q}]", cin=op.cin, cout=op.cout,
+                                                  k=d.kh, s=d.stride, ho=oh, wo=ow, h=sh, w=sw,
+                                                  flops=2.0 * N * oh * ow * d.Cout * op.cin * d.kh * d.kw,
+                                                  y_f32=op.kind == "pred"))
+                    if "w_pair" in ent and op.src.c_off == 0 and sct == op.cin and sw % 2 == 0:
+                        # 3x3 stride-2 conv over <= 32 channels: 64-byte pixels fetched with an element stride of 2 keep the
+                        # TMA unit, not the tensor pipe, busy (ERBlock_2.0 of YOLOv6-S: 170 us for 0.9 GFLOP/img).  On the
+                        # column-pair view of the same memory, [N, H, W/2, 2*Cin], it is a 3x2 conv with stride (2, 1):
+                        # contiguous 2*Cin-channel rows, 4/3 of the MACs (the extra quarter multiplies zero weights).
+                        d.W, d.Cin, d.x_c_total = sw // 2, 2 * op.cin, 2 * op.cin
+                        d.w = ent["w_pair"].data_ptr()
+                        d.w_plane_stride = ent["w_pair"].stride(0) if P == 3 else 0
+                        d.kw, d.stride_w, d.pad_w, d.out_w = 2, 1, 1, sw // 2
                     if op.kind == "pred":
                         which, lvl = op.head
                         out = plan[which]
@@ -162,11 +235,11 @@ class InferEngine:
                             d.y = dbuf.data_ptr() + ((dy * dw + dx) * dct + op.dst.c_off) * 2
                             d.y_img_stride, d.y_h_stride, d.y_w_stride = dh * dw * dct, 2 * dw * dct, 2 * dct
                         else:
-                            d.y = dbuf.data_ptr() + op.dst.c_off * 2
+                            d.y = dbuf.data_ptr() + (coff(op.dst) if not fused else 0) * 2
                             d.y_img_stride, d.y_h_stride, d.y_w_stride = dh * dw * dct, dw * dct, dct
                     if op.res is not None:
                         rbuf, rh, rw, rct = view(op.res)
-                        d.res = rbuf.data_ptr() + op.res.c_off * 2
+                        d.res = rbuf.data_ptr() + coff(op.res) * 2
                         d.res_img_stride, d.res_h_stride, d.res_w_stride = rh * rw * rct, rw * rct, rct
                         d.res_plane_stride = rbuf.stride(0) if P == 3 else 0
                         d.alpha = ent["alpha"]
@@ -240,11 +313,7 @@ class InferEngine:
         torch.cuda.synchronize()
         sp = _lib.stream_ptr(stream)
         convs = [d for kind, d in plan["calls"] if kind == "conv"]
-        flops = 0.0
-        for d in convs:
-            ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
-            wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
-            flops += 2.0 * d.N * ho * wo * d.Cout * d.Cin * d.kh * d.kw
+        flops = sum(ci["flops"] for ci in plan["conv_info"])     # algorithmic (the column-pair view's zero taps do not count)
         # one event pair around the back-to-back conv launches of a forward (launch gaps between the
         # kernels are part of the step, so they stay in the denominator)
         total_ms = 0.0
@@ -263,13 +332,9 @@ class InferEngine:
         slice once (bf16), weights once."""
         plan = self._plan(N, H, W, torch.float32)
         tot, n = 0.0, 0
-        for kind, d in plan["calls"]:
-            if kind != "conv":
-                continue
-            ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
-            wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
-            ysz = 4 if d.y_dtype == DT_F32 else 2
-            tot += d.N * (d.H * d.W * d.Cin * 2 + ho * wo * d.Cout * ysz) + d.Cout * d.kh * d.kw * d.Cin * 2
+        for ci in plan["conv_info"]:
+            ysz = 4 if ci["y_f32"] else 2
+            tot += N * (ci["h"] * ci["w"] * ci["cin"] * 2 + ci["ho"] * ci["wo"] * ci["cout"] * ysz) + ci["cout"] * ci["k"] ** 2 * ci["cin"] * 2
             n += 1
         return tot / max(n, 1)
 
@@ -282,15 +347,10 @@ class InferEngine:
         torch.cuda.synchronize()
         sp = _lib.stream_ptr(stream)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
-        names = []
-        for op in self.g.ops:
-            if op.kind in ("conv", "pred"):
-                names.append(op.name)
-            elif op.kind == "convT":
-                names.extend([f"{op.name}[{q}]" for q in range(4)])
         rows = []
         convs = [d for kind, d in plan["calls"] if kind == "conv"]
-        for name, d in zip(names, convs):
+        for ci, d in zip(plan["conv_info"], convs):
+            name = ci["name"]
             ts = []
             for _ in range(iters):
                 flush.zero_()
@@ -302,12 +362,11 @@ class InferEngine:
                 ts.append(e0.elapsed_time(e1))
             ts.sort()
             ms = ts[len(ts) // 2]
-            ho = (d.H + 2 * d.pad - d.kh) // d.stride + 1
-            wo = (d.W + 2 * d.pad - d.kw) // d.stride + 1
-            fl = 2.0 * d.N * ho * wo * d.Cout * d.Cin * d.kh * d.kw
-            by = 2.0 * d.N * (d.H * d.W * d.Cin + ho * wo * d.Cout)
+            ho, wo = ci["ho"], ci["wo"]
+            fl = ci["flops"]
+            by = 2.0 * d.N * (ci["h"] * ci["w"] * ci["cin"] + ho * wo * ci["cout"])
             out = (C.c_int32 * 10)()
             _lib.check(self.lib.yv6_conv_plan(self.handle, C.byref(d), out))
-            rows.append(dict(name=name, cin=d.Cin, cout=d.Cout, k=d.kh, s=d.stride, hw=f"{ho}x{wo}", ms=ms,
+            rows.append(dict(name=name, cin=ci["cin"], cout=ci["cout"], k=ci["k"], s=ci["s"], hw=f"{ho}x{wo}", ms=ms,
                              tflops=fl / ms / 1e9, gbs=by / ms / 1e6, plan=list(out)))
         return rows

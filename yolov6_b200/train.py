@@ -167,8 +167,8 @@ class TrainEngine:
                 for b, (prefix, k) in enumerate(br):
                     if k == 0:
                         continue
-                    if op.kind == "stem":
-                        ztake((i, "dw", b), 4 * op.cout * (27 if k == 3 else 3))
+                    if op.kind == "stem":      # 1x1 wgrad over the im2col patches: [Cout][32] (27 taps + 5 zero columns)
+                        ztake((i, "dw", b), 4 * op.cout * 32)
                     else:
                         ztake((i, "dw", b), 4 * op.cout * k * k * op.cin)
         self.zero_arena = torch.zeros(ztot, dtype=torch.uint8, device=dev)
@@ -303,11 +303,11 @@ class TrainEngine:
             bn = prefix + (".bn" if k else "")
             if k:
                 if op.kind == "stem":
-                    if k == 3:      # dw3 [Cout][(r*3+s)*3 + c] -> [Cout][c][r][s]
-                        segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co, 3, 9], [27, 9, 1], [27, 1, 3],
+                    if k == 3:      # dw [Cout][32]: column (r*3+s)*3 + c -> [Cout][c][r][s]
+                        segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co, 3, 9], [27, 9, 1], [32, 1, 3],
                                          XF_F32, XF_F32))
-                    else:
-                        segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co * 3], [1], [1], XF_F32, XF_F32))
+                    else:           # the 1x1 stride-2 branch sees the centre tap (r = s = 1): columns 12..14
+                        segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b) + 4 * 12, [co, 3], [3, 1], [32, 1], XF_F32, XF_F32))
                 else:
                     kk = k * k      # dw [Cout][kk][Cin] -> [Cout][Cin][kk]
                     segs.append(_seg(fl.grad_ptr(prefix + ".conv.weight"), z(i, "dw", b), [co, ci, kk], [ci * kk, kk, 1],
@@ -542,11 +542,12 @@ class TrainEngine:
             fwd.append(("apply", d))
             calls.append(("dbg", (i, gdst[..., op.dst.c_off:op.dst.c_off + op.cout])))
             calls.append(("bn_bwd", d))
-            if op.kind == "stem":
-                dy3 = dcs[0]
-                dy1 = dcs[1] if nb > 1 else None
-                calls.append(("stem_wgrad", (self.x_static.data_ptr(), x_dt, 1.0 / 255.0, dy3.data_ptr(), op.cout, _p(dy1), op.cout, N, H, W,
-                                             op.cout, z(i, "dw", 0), z(i, "dw", 1) if nb > 1 else 0, 1)))
+            if op.kind == "stem":       # im2col once, then one tensor-core wgrad GEMM per branch
+                patches = bf(n, ho, wo, 32)
+                self._stem_patches = patches
+                calls.append(("im2col", (self.x_static.data_ptr(), x_dt, 1.0 / 255.0, N, H, W, patches.data_ptr())))
+                for b in range(nb):
+                    calls.append(("wgrad", self._wgrad_desc(patches, 0, 32, dcs[b], 0, op.cout, 1, 1, z(i, "dw", b))))
             else:
                 src, gsrc = view(op.src)
                 for b, ent in enumerate(br):
@@ -648,8 +649,8 @@ class TrainEngine:
                 chk(lib.yv6_head_grad_prep(h, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], sp))
             elif kind == "pool_bwd":
                 chk(lib.yv6_maxpool5_bwd(h, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8].data_ptr(), d[9], d[10], d[11], sp))
-            elif kind == "stem_wgrad":
-                chk(lib.yv6_stem_wgrad2(h, *d, sp))
+            elif kind == "im2col":
+                chk(lib.yv6_stem_im2col(h, *d, sp))
             elif kind == "bucket":
                 self.grad_tables[d].launch(lib, h, accumulate, sp)
                 if self.bucket_hook is not None:
