@@ -294,6 +294,7 @@ typedef struct yv6_bn_desc {
    * counter one uint32, coef [nb][2][C] fp32.  zeroed != 0: the caller already zeroed s1, work, counter and dalpha
    * (the training engine clears one arena per step instead of four memsets per block). */
   double* work; uint32_t* counter; float* coef; int32_t zeroed;
+  int32_t dres_assign;                                  /* != 0: dres = alpha * dy (first writer of that gradient slice) instead of += */
 } yv6_bn_desc;
 int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* stream);
 

@@ -85,7 +85,7 @@ class BnDesc(C.Structure):
         ("res", C.c_void_p), ("res_pitch", C.c_int64), ("res_alpha", C.c_float),
         ("dres", C.c_void_p), ("dres_pitch", C.c_int64), ("dalpha", C.c_void_p),
         ("res_alpha_dev", C.c_void_p),
-        ("work", C.c_void_p), ("counter", C.c_void_p), ("coef", C.c_void_p), ("zeroed", C.c_int32),
+        ("work", C.c_void_p), ("counter", C.c_void_p), ("coef", C.c_void_p), ("zeroed", C.c_int32), ("dres_assign", C.c_int32),
     ]
 
 

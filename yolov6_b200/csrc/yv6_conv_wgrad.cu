@@ -46,6 +46,14 @@ __device__ __forceinline__ void wg_tma_4d(void* dst, const CUtensorMap* m, uint6
       : "memory");
 }
 
+// L2 prefetch of a box (no shared-memory destination): issued a few pipeline depths ahead so that the loads that fill the
+// stages hit L2 -- the shared-memory ring alone (~200 KB) does not cover DRAM latency at the rate the MMAs consume operands
+__device__ __forceinline__ void wg_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // MN-major operand descriptor: LBO = bytes between channel blocks, SBO = bytes between 8-pixel-row groups
 __device__ __forceinline__ uint64_t wg_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -71,12 +79,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // unit decode: ks fastest so that concurrently running CTAs read different pixels of the same tensors
+  // unit decode: tap group fastest, then channel tiles, then the pixel range -- CTAs that run at the same time read the SAME
+  // pixels of dY / X for different taps / channel tiles, so each operand byte is fetched from DRAM once and then served by L2
   int u = blockIdx.x;
-  const int ks = u % p.ksplit; u /= p.ksplit;
   const int tg = u % p.tap_groups; u /= p.tap_groups;
   const int ci_t = u % p.ci_tiles; u /= p.ci_tiles;
-  const int co_t = u;
+  const int co_t = u % p.co_tiles; u /= p.co_tiles;
+  const int ks = u;
   const int tap0 = tg * p.T;
   const int per = (p.ptiles + p.ksplit - 1) / p.ksplit;
   const int pt0 = ks * per, pt1 = min(p.ptiles, pt0 + per);
@@ -100,6 +109,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const uint32_t tx = (uint32_t)p.a_loaded * a_blk_bytes + (uint32_t)(p.T * p.b_blocks * p.PT * p.b_blk_bytes);
     int stage = 0;
     uint32_t phase = 0;
+    const int r_mid = (tap0 + p.T / 2) / p.kw, s_mid = (tap0 + p.T / 2) % p.kw;   // the middle tap's box stands for all T of them
+    auto prefetch = [&](int pt) {
+      int m = pt;
+      const int tw = m % p.tiles_w; m /= p.tiles_w;
+      const int th = m % p.tiles_h;
+      const int ti = m / p.tiles_h;
+      const int w0 = tw * p.BW, h0 = th * p.BH;
+      for (int j = 0; j < p.a_loaded; ++j) wg_prefetch_4d(&tmDY, co_t * 128 + j * 64, w0, h0, ti);
+      for (int j = 0; j < p.b_blocks; ++j)
+        wg_prefetch_4d(&tmX, ci_t * p.NT + j * p.b_blk_elems, w0 * p.stride + s_mid - p.pad, h0 * p.stride + r_mid - p.pad, ti);
+    };
+    const int ahead = 2 * p.stages;
+    if (elect_one())
+      for (int pt = pt0; pt < min(pt1, pt0 + ahead); ++pt) prefetch(pt);
+    __syncwarp();
     for (int pt = pt0; pt < pt1; ++pt) {
       int m = pt;
       const int tw = m % p.tiles_w; m /= p.tiles_w;
@@ -108,6 +132,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int w0 = tw * p.BW, h0 = th * p.BH;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
+        if (pt + ahead < pt1) prefetch(pt + ahead);
         mbar_expect_tx(&full[stage], tx);
         for (int j = 0; j < p.a_loaded; ++j)
           wg_tma_4d(sA + (size_t)stage * p.a_stage_bytes + (size_t)j * a_blk_bytes, &tmDY, &full[stage], co_t * 128 + j * 64, w0, h0, ti);
@@ -240,7 +265,9 @@ extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stre
   p.a_blocks = 2;
   p.a_loaded = (d->Cout <= 64) ? 1 : 2;     // rows 64..127 of the accumulator are never stored for Cout <= 64
   p.co_tiles = (d->Cout + 127) / 128;
-  p.a_stage_bytes = p.a_blocks * p.PT * 128;
+  // Cout <= 64: only the first 64-channel block exists; the MMA still reads M = 128 rows, the upper 64 from whatever follows in
+  // shared memory (the next stage / the X tiles) -- they land in accumulator rows that are never stored
+  p.a_stage_bytes = p.a_loaded * p.PT * 128;
   p.b_tap_bytes = ((p.b_blocks * p.PT * p.b_blk_bytes + 1023) / 1024) * 1024;
   p.b_stage_bytes = p.T * p.b_tap_bytes;
   const int fixed = 1024 /* alignment */ + 4 * 32 * 33 * 4 /* epilogue transpose */ + 512 /* barriers */;
@@ -248,10 +275,10 @@ extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stre
   p.stages = std::min(kWgMaxStages, budget / (p.a_stage_bytes + p.b_stage_bytes));
   YV6_REQUIRE(p.stages >= 2, "wgrad: not enough shared memory");
   const int base_units = p.co_tiles * p.ci_tiles * p.tap_groups;
-  // split-K over pixel ranges: fill the SMs twice, but keep at least ~8 pipeline stages of work per CTA -- every extra
+  // split-K over pixel ranges: one wave of CTAs, at least ~8 pipeline stages of work each -- every extra
   // split adds one full pass of fp32 reductions over the weight tensor
   const int min_tiles = 8 * 128 / p.PT;
-  p.ksplit = std::max(1, std::min((p.ptiles + min_tiles - 1) / min_tiles, (2 * h->num_sms + base_units - 1) / base_units));
+  p.ksplit = std::max(1, std::min((p.ptiles + min_tiles - 1) / min_tiles, (h->num_sms + base_units - 1) / base_units));
   if (d->force_ksplit > 0) p.ksplit = std::min(p.ptiles, d->force_ksplit);
   const int units = base_units * p.ksplit;
 

@@ -287,8 +287,9 @@ struct BwdParams {
   View res;                  // optional shortcut input (y = act(z) + alpha * res)
   float alpha;
   const float* alpha_dev;
-  __nv_bfloat16* dres;       // g(res) += alpha * dy
+  __nv_bfloat16* dres;       // g(res) += alpha * dy  (= when dres_assign)
   int64_t dres_pitch;
+  int dres_assign;
   double* dalpha;            // += sum dy * res
   int nb, act, C;
   int64_t pixels;
@@ -410,9 +411,14 @@ __global__ void __launch_bounds__(kTrThreads, 2) bn_bwd_apply_kernel(const BwdPa
     if (p.dres != nullptr) {
       float old[8];
       __nv_bfloat16* dst = p.dres + px * p.dres_pitch + m.cg * 8;
-      ld8(dst, old);
+      if (p.dres_assign) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) old[j] += alpha * dz[j];
+        for (int j = 0; j < 8; ++j) old[j] = alpha * dz[j];
+      } else {
+        ld8(dst, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) old[j] += alpha * dz[j];
+      }
       st8(dst, old);
     }
 #pragma unroll
@@ -736,8 +742,11 @@ static inline int chan_threads(int C) {
   const int cgs = C / 8;
   return cgs * std::max(1, kTrThreads / cgs);
 }
-static inline unsigned chan_grid(int64_t pixels, int C, int num_sms, int per_sm) {
-  const int rows = std::max(1, kTrThreads / (C / 8));
+static inline unsigned chan_grid(int64_t pixels, int C, int num_sms, int per_sm, int min_iters = 1) {
+  // min_iters: pixels each thread should at least loop over (the reduction kernels pay per-block costs -- shared-memory
+  // column sums, 2C..8C float64 atomics on the same addresses, the last-block pass -- that a small tensor cannot amortise
+  // over hundreds of blocks)
+  const int64_t rows = (int64_t)std::max(1, kTrThreads / (C / 8)) * min_iters;
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((pixels + rows - 1) / rows, (int64_t)num_sms * per_sm));
 }
 static int configure_train(yv6_handle* h) {
@@ -767,7 +776,7 @@ extern "C" int yv6_bn_stats_finalize(yv6_handle* h, const yv6_bn_stats_desc* d, 
     YV6_CHECK_CUDA(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), s));
   }
   const int threads = chan_threads(d->C);
-  const unsigned grid = chan_grid(d->pixels, d->C, h->num_sms, 4);
+  const unsigned grid = chan_grid(d->pixels, d->C, h->num_sms, 4, 16);
   const size_t smem = sizeof(float) * (size_t)(threads / (d->C / 8)) * d->C;
   if (d->nb == 1) bn_stats_multi_kernel<1><<<grid, threads, smem, s>>>(p);
   else if (d->nb == 2) bn_stats_multi_kernel<2><<<grid, threads, smem, s>>>(p);
@@ -793,7 +802,7 @@ extern "C" int yv6_bn_apply_fwd(yv6_handle* h, const yv6_bn_desc* d, void* strea
   p.alpha = d->res_alpha;
   p.alpha_dev = d->res_alpha_dev;
   const int threads = chan_threads(d->C);
-  const unsigned grid = chan_grid(d->pixels, d->C, h->num_sms, 16);
+  const unsigned grid = chan_grid(d->pixels, d->C, h->num_sms, 16, 2);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->nb == 1) bn_apply_fwd_kernel<1><<<grid, threads, 0, s>>>(p);
   else if (d->nb == 2) bn_apply_fwd_kernel<2><<<grid, threads, 0, s>>>(p);
@@ -820,6 +829,7 @@ extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
   p.alpha_dev = d->res_alpha_dev;
   p.dres = d->res ? reinterpret_cast<__nv_bfloat16*>(d->dres) : nullptr;
   p.dres_pitch = d->dres_pitch;
+  p.dres_assign = d->dres_assign;
   p.dalpha = d->res ? d->dalpha : nullptr;
   YV6_REQUIRE(!d->res || (d->dres && d->dalpha), "bn_bwd: shortcut without dres / dalpha");
   p.nb = d->nb; p.act = d->act; p.C = d->C; p.pixels = d->pixels;
@@ -844,7 +854,7 @@ extern "C" int yv6_bn_bwd(yv6_handle* h, const yv6_bn_desc* d, void* stream) {
   }
   const int threads = chan_threads(d->C);
   const size_t smem = sizeof(float) * (size_t)(threads / (d->C / 8)) * d->C;
-  const unsigned grid_r = chan_grid(d->pixels, d->C, h->num_sms, 4), grid_a = chan_grid(d->pixels, d->C, h->num_sms, 16);
+  const unsigned grid_r = chan_grid(d->pixels, d->C, h->num_sms, 4, 16), grid_a = chan_grid(d->pixels, d->C, h->num_sms, 16, 2);
   if (d->nb == 1) {
     bn_bwd_reduce_kernel<1><<<grid_r, threads, smem, s>>>(p);
     bn_bwd_apply_kernel<1><<<grid_a, threads, 0, s>>>(p);

@@ -205,7 +205,7 @@ class InferEngine:
                     d.act = ACT_CODES[op.act]
                     d.nsplit = P
                     oh, ow = (sh + 2 * d.pad - d.kh) // d.stride + 1, (sw + 2 * d.pad - d.kw) // d.stride + 1
-                    plan["conv_info"].append(dict(name=op.name if op.kind != "convT" else f"{op.name}[{q}]", cin=op.cin, cout=op.cout,
+                    plan["conv_info"].append(dict(name=op.name if op.kind != "convT" else f"{op.name}[{q}]", cin=op.cin, cout=int(d.Cout),
                                                   k=d.kh, s=d.stride, ho=oh, wo=ow, h=sh, w=sw,
                                                   flops=2.0 * N * oh * ow * d.Cout * op.cin * d.kh * d.kw,
                                                   y_f32=op.kind == "pred"))

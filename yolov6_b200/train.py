@@ -437,8 +437,9 @@ class TrainEngine:
                     pool_scr = torch.zeros(n * h * w * c, dtype=torch.float32, device=dev)
                 calls.append(("dbg", (i, gbuf[..., :4 * c])))
                 for j in (3, 2, 1):   # y_j = pool(y_{j-1}); slice j of the concat
-                    calls.append(("pool_bwd", (buf.data_ptr() + (j - 1) * c * 2, ct, gbuf.data_ptr() + j * c * 2, ct, n, h, w, c,
-                                               pool_scr, gbuf.data_ptr() + (j - 1) * c * 2, ct, 1)))
+                    calls.append(("pool_bwd", [buf.data_ptr() + (j - 1) * c * 2, ct, gbuf.data_ptr() + j * c * 2, ct, n, h, w, c,
+                                               pool_scr, gbuf.data_ptr() + (j - 1) * c * 2, ct, 1],
+                                  dict(buf=op.dst.buf, off=(j - 1) * c, n=c, full=True)))
                 bwd_rev.append(calls)
                 continue
             Wt = self.wts[i]
@@ -456,7 +457,8 @@ class TrainEngine:
                                       dl.data_ptr()), dl))
                 calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dl, 0, ch, 1, 1, z(i, "dw"))))
                 calls.append(("stats", self._stats_desc([(dl, 0)], chp, N * lh * lw, z(i, "bsum"), z(i, "bcnt"))))
-                calls.append(("conv", self._conv_desc(dl, 0, chp, Wt["wt"], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True)))
+                calls.append(("conv", self._conv_desc(dl, 0, chp, Wt["wt"], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True),
+                              dict(buf=op.src.buf, off=op.src.c_off, n=op.cin, full=True)))
                 bwd_rev.append(calls)
                 continue
             if op.kind == "convT":
@@ -480,7 +482,8 @@ class TrainEngine:
                     dq = dq_pool[q][:need].view(N, sh, sw, op.cout)
                     calls.append(("copy", (dq, gd[:, dy::2, dx::2, :])))               # gradient of quadrant q, dense
                     calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dq, 0, op.cout, 1, 1, z(i, "dw") + 4 * q * op.cout * op.cin)))
-                    calls.append(("conv", self._conv_desc(dq, 0, op.cout, Wt["wt"][q], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True)))
+                    calls.append(("conv", self._conv_desc(dq, 0, op.cout, Wt["wt"][q], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True),
+                                  dict(buf=op.src.buf, off=op.src.c_off, n=op.cin, full=True)))
                 bwd_rev.append(calls)
                 continue
             # ---- BN-ed blocks: stem / rep / cba ----
@@ -541,7 +544,13 @@ class TrainEngine:
                 d.dres, d.dres_pitch, d.dalpha = grbuf.data_ptr() + op.res.c_off * 2, grbuf.shape[3], z(i, "dalpha")
             fwd.append(("apply", d))
             calls.append(("dbg", (i, gdst[..., op.dst.c_off:op.dst.c_off + op.cout])))
-            calls.append(("bn_bwd", d))
+            wr = []      # gradient slices this launch writes besides the scratch tensors
+            for b in range(nb):
+                if br[b]["k"] == 0:
+                    wr.append(dict(buf=op.src.buf, off=op.src.c_off, n=op.cin, full=True, what=("dx", b)))
+            if op.res is not None:
+                wr.append(dict(buf=op.res.buf, off=op.res.c_off, n=op.cout, full=True, what=("dres", 0)))
+            calls.append(("bn_bwd", d, wr))
             if op.kind == "stem":       # im2col once, then one tensor-core wgrad GEMM per branch
                 patches = bf(n, ho, wo, 32)
                 self._stem_patches = patches
@@ -554,8 +563,11 @@ class TrainEngine:
                     if ent["k"] == 0:
                         continue
                     calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dcs[b], 0, op.cout, ent["k"], op.s, z(i, "dw", b))))
-                    for dd in self._dgrad_descs(dcs[b], ent, ent["k"], op.s, gsrc, op.src.c_off, op.cin):
-                        calls.append(("conv", dd))
+                    dds = self._dgrad_descs(dcs[b], ent, ent["k"], op.s, gsrc, op.src.c_off, op.cin)
+                    # a stride-2 3x3 dgrad = four parity convolutions that together cover every pixel; 1x1 stride 2 covers one parity
+                    full = op.s == 1 or ent["k"] == 3
+                    for gi, dd in enumerate(dds):
+                        calls.append(("conv", dd, dict(buf=op.src.buf, off=op.src.c_off, n=op.cin, full=full, group=(i, b), first=gi == 0)))
             bwd_rev.append(calls)
         self.fwd_calls = fwd
         bwd = []
@@ -566,6 +578,54 @@ class TrainEngine:
                 bwd.append(("bucket", k))
         self.bwd_calls = bwd
         self._keep = (dc_pool, pool_scr, dq_pool)
+        self._resolve_first_writers()
+
+    def _resolve_first_writers(self):
+        """Gradient buffers are accumulated into by every consumer of a tensor.  Instead of clearing all of them at the start of
+        the backward pass (one more pass over every activation gradient) the FIRST writer of a channel slice assigns and
+        the later ones accumulate; only buffers whose first writer cannot assign (it covers part of the pixels, or part of
+        a slice that is already partly written) are still cleared."""
+        cov = [np.zeros(b.c_total, dtype=bool) for b in self.g.bufs]
+        need_zero = set()
+        group_decision = {}
+
+        def decide(m):
+            seg = cov[m["buf"]][m["off"]:m["off"] + m["n"]]
+            if m["full"] and not seg.any():
+                assign = True
+            else:
+                assign = False
+                if not seg.all():
+                    need_zero.add(m["buf"])
+            seg[:] = True
+            return assign
+
+        for c in self.bwd_calls:
+            kind = c[0]
+            if kind == "conv" and len(c) > 2:
+                m, d = c[2], c[1]
+                if "group" in m:
+                    if m["first"]:
+                        group_decision[m["group"]] = decide(m)
+                    assign = group_decision[m["group"]]
+                else:
+                    assign = decide(m)
+                if assign:          # y = conv(...) instead of y += conv(...): no residual read
+                    d.res, d.alpha = 0, 0.0
+            elif kind == "bn_bwd":
+                d = c[1]
+                for m in c[2]:
+                    assign = decide(m)
+                    if m["what"][0] == "dx":
+                        d.accumulate[m["what"][1]] = 0 if assign else 1
+                    else:
+                        d.dres_assign = 1 if assign else 0
+            elif kind == "pool_bwd":
+                c[1][11] = 0 if decide(c[2]) else 1
+        for i, cv in enumerate(cov):        # slices nobody writes are read as zero gradients
+            if not cv.all():
+                need_zero.add(i)
+        self.zero_gbufs = [self.gbufs[i] for i in sorted(need_zero)]
 
     # ================================================================== execution
     def launch_counts(self):
@@ -630,7 +690,7 @@ class TrainEngine:
         lib, h, chk = self.lib, self.h, _lib.check
         sp = _lib.stream_ptr()
         if first == 0:
-            for gb in self.gbufs:
+            for gb in self.zero_gbufs:
                 gb.zero_()
         calls = self.bwd_calls if last is None else self.bwd_calls[:last]
         for c in calls[first:]:
