@@ -337,9 +337,10 @@ int yv6_stem_wgrad2(yv6_handle* h, const void* x, int32_t x_dtype, float in_scal
 
 /* im2col of the 3-channel stem conv (3x3, stride 2, pad 1): patches bf16 [N, Ho, Wo, 32] with channel (r*3+s)*3 + c =
  * x[n, c, 2ho+r-1, 2wo+s-1] (x as in yv6_stem_fwd: NCHW fp32 or uint8 * in_scale), channels 27..31 zero.  With it the stem's
- * weight gradient is a 1x1 yv6_conv_wgrad over (patches, dY): dw [Cout][32] fp32. */
+ * weight gradient is a 1x1 yv6_conv_wgrad over (patches, dY): dw [Cout][32] fp32.  patches_lo (optional) receives the bf16
+ * rounding residual of the patches; a second wgrad over it restores the fp32 image in the gradient. */
 int yv6_stem_im2col(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, int32_t N, int32_t H, int32_t W,
-                    void* patches_bf16, void* stream);
+                    void* patches_bf16, void* patches_lo_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Step-level plumbing of the training engine: everything that the reference does with

@@ -182,7 +182,12 @@ def test_train_step_matches_reference_op_by_op(name, size, batch):
             assert e < 1e-2, f"{op.name}: forward rel err {e:.3e}"
             (y * _nchw(dbg["gdst"])).sum().backward()
             for pname, leaf in leaves:   # per-channel BN sums over few pixels feel single relu-mask flips (z ~ 0 in fp32 vs float64)
-                check_param(pname, leaf.grad, 1e-2 if leaf.dim() == 4 else 3e-2)
+                tol = 1e-2 if leaf.dim() == 4 else 3e-2
+                if op.kind == "stem" and leaf.dim() == 4:
+                    # dW = sum_px dc * x with sum_px dc = 0 (BatchNorm backward) and x = 0.5 +- 0.29: the image mean cancels, what is
+                    # left competes with the bf16 rounding of dc (2^-9 each, independent) -- measured 0.6e-2 .. 1.1e-2 on 3 x Cout numbers
+                    tol = 2e-2
+                check_param(pname, leaf.grad, tol)
             if op.res is not None:
                 sl(ref_g, op.res, op.cout).add_(res.grad.permute(0, 2, 3, 1))
         if src is not None:

@@ -13,6 +13,7 @@
 // pixel tiles (8 tcgen05.mma per 128-pixel tile) and adds the result to dW with fp32 reductions
 // (split-K over the pixel ranges).  warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
 #include <algorithm>
+#include <cstdlib>
 
 #include "yv6_common.cuh"
 #include "yv6_handle.h"
@@ -44,14 +45,6 @@ __device__ __forceinline__ void wg_tma_4d(void* dst, const CUtensorMap* m, uint6
       " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
-}
-
-// L2 prefetch of a box (no shared-memory destination): issued a few pipeline depths ahead so that the loads that fill the
-// stages hit L2 -- the shared-memory ring alone (~200 KB) does not cover DRAM latency at the rate the MMAs consume operands
-__device__ __forceinline__ void wg_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
-               "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
 }
 
 // MN-major operand descriptor: LBO = bytes between channel blocks, SBO = bytes between 8-pixel-row groups
@@ -109,21 +102,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const uint32_t tx = (uint32_t)p.a_loaded * a_blk_bytes + (uint32_t)(p.T * p.b_blocks * p.PT * p.b_blk_bytes);
     int stage = 0;
     uint32_t phase = 0;
-    const int r_mid = (tap0 + p.T / 2) / p.kw, s_mid = (tap0 + p.T / 2) % p.kw;   // the middle tap's box stands for all T of them
-    auto prefetch = [&](int pt) {
-      int m = pt;
-      const int tw = m % p.tiles_w; m /= p.tiles_w;
-      const int th = m % p.tiles_h;
-      const int ti = m / p.tiles_h;
-      const int w0 = tw * p.BW, h0 = th * p.BH;
-      for (int j = 0; j < p.a_loaded; ++j) wg_prefetch_4d(&tmDY, co_t * 128 + j * 64, w0, h0, ti);
-      for (int j = 0; j < p.b_blocks; ++j)
-        wg_prefetch_4d(&tmX, ci_t * p.NT + j * p.b_blk_elems, w0 * p.stride + s_mid - p.pad, h0 * p.stride + r_mid - p.pad, ti);
-    };
-    const int ahead = 2 * p.stages;
-    if (elect_one())
-      for (int pt = pt0; pt < min(pt1, pt0 + ahead); ++pt) prefetch(pt);
-    __syncwarp();
     for (int pt = pt0; pt < pt1; ++pt) {
       int m = pt;
       const int tw = m % p.tiles_w; m /= p.tiles_w;
@@ -132,7 +110,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int w0 = tw * p.BW, h0 = th * p.BH;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
-        if (pt + ahead < pt1) prefetch(pt + ahead);
         mbar_expect_tx(&full[stage], tx);
         for (int j = 0; j < p.a_loaded; ++j)
           wg_tma_4d(sA + (size_t)stage * p.a_stage_bytes + (size_t)j * a_blk_bytes, &tmDY, &full[stage], co_t * 128 + j * 64, w0, h0, ti);
@@ -275,10 +252,12 @@ extern "C" int yv6_conv_wgrad(yv6_handle* h, const yv6_wgrad_desc* d, void* stre
   p.stages = std::min(kWgMaxStages, budget / (p.a_stage_bytes + p.b_stage_bytes));
   YV6_REQUIRE(p.stages >= 2, "wgrad: not enough shared memory");
   const int base_units = p.co_tiles * p.ci_tiles * p.tap_groups;
-  // split-K over pixel ranges: one wave of CTAs, at least ~8 pipeline stages of work each -- every extra
-  // split adds one full pass of fp32 reductions over the weight tensor
+  // split-K over pixel ranges: the kernel is bound by the L2 -> shared-memory operand stream of each CTA (measured: the time
+  // per 64-pixel stage does not depend on how many CTAs run), so it wants exactly two full waves of CTAs -- one unit more than
+  // a multiple of the SM count costs a whole extra wave -- with at least ~8 stages of work each (every extra split adds a
+  // pass of fp32 reductions over the weight tensor)
   const int min_tiles = 8 * 128 / p.PT;
-  p.ksplit = std::max(1, std::min((p.ptiles + min_tiles - 1) / min_tiles, (h->num_sms + base_units - 1) / base_units));
+  p.ksplit = std::max(1, std::min((p.ptiles + min_tiles - 1) / min_tiles, std::max(1, 2 * h->num_sms / base_units)));
   if (d->force_ksplit > 0) p.ksplit = std::min(p.ptiles, d->force_ksplit);
   const int units = base_units * p.ksplit;
 

@@ -595,7 +595,8 @@ __global__ void __launch_bounds__(kTrThreads) stem_wgrad_kernel(const void* x, i
 // patches[n, ho, wo, (r*3+s)*3 + c] = x[n, c, 2ho + r - 1, 2wo + s - 1] (zero outside the image), channels 27..31 zero, bf16.
 // The stem's weight gradient is then an ordinary 1x1 wgrad GEMM over (patches, dY) on the tensor cores
 // (K = all output pixels, M = Cout, N = 32), instead of 27 * Cout dot products of length N*Ho*Wo on CUDA cores.
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const void* x, int x_u8, float in_scale, int N, int H, int W, __nv_bfloat16* out) {
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const void* x, int x_u8, float in_scale, int N, int H, int W, __nv_bfloat16* out,
+                                                          __nv_bfloat16* out_lo) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)N * Ho * Wo;
   for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < total; px += (int64_t)gridDim.x * blockDim.x) {
@@ -623,6 +624,16 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* x, int x_u
     for (int j = 0; j < 4; ++j) {
       const float t[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
       st8(o + 8 * j, t);
+    }
+    if (out_lo != nullptr) {      // residual plane: image = hi + lo to ~2^-17, so the gradient sees the fp32 image, not its bf16 rounding
+      __nv_bfloat16* ol = out_lo + px * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = v[8 * j + k] - __bfloat162float(__float2bfloat16_rn(v[8 * j + k]));
+        st8(ol + 8 * j, t);
+      }
     }
   }
 }
@@ -924,12 +935,13 @@ extern "C" int yv6_stem_wgrad(yv6_handle* h, const void* x, int32_t x_dtype, flo
 }
 
 extern "C" int yv6_stem_im2col(yv6_handle* h, const void* x, int32_t x_dtype, float in_scale, int32_t N, int32_t H, int32_t W,
-                               void* patches_bf16, void* stream) {
+                               void* patches_bf16, void* patches_lo_bf16, void* stream) {
   yv6_device_guard _dev(h);
   YV6_REQUIRE(h && x && patches_bf16 && N > 0 && H > 0 && W > 0, "stem_im2col: bad argument");
   const int64_t total = (int64_t)N * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
   stem_im2col_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, x_dtype == YV6_DT_U8, in_scale, N, H, W,
-                                                                                         reinterpret_cast<__nv_bfloat16*>(patches_bf16));
+                                                                                         reinterpret_cast<__nv_bfloat16*>(patches_bf16),
+                                                                                         reinterpret_cast<__nv_bfloat16*>(patches_lo_bf16));
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }

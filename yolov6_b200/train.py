@@ -552,11 +552,12 @@ class TrainEngine:
                 wr.append(dict(buf=op.res.buf, off=op.res.c_off, n=op.cout, full=True, what=("dres", 0)))
             calls.append(("bn_bwd", d, wr))
             if op.kind == "stem":       # im2col once, then one tensor-core wgrad GEMM per branch
-                patches = bf(n, ho, wo, 32)
-                self._stem_patches = patches
-                calls.append(("im2col", (self.x_static.data_ptr(), x_dt, 1.0 / 255.0, N, H, W, patches.data_ptr())))
+                patches, patches_lo = bf(n, ho, wo, 32), bf(n, ho, wo, 32)     # image = hi + lo (bf16 planes)
+                self._stem_patches = (patches, patches_lo)
+                calls.append(("im2col", (self.x_static.data_ptr(), x_dt, 1.0 / 255.0, N, H, W, patches.data_ptr(), patches_lo.data_ptr())))
                 for b in range(nb):
-                    calls.append(("wgrad", self._wgrad_desc(patches, 0, 32, dcs[b], 0, op.cout, 1, 1, z(i, "dw", b))))
+                    for pl in (patches, patches_lo):
+                        calls.append(("wgrad", self._wgrad_desc(pl, 0, 32, dcs[b], 0, op.cout, 1, 1, z(i, "dw", b))))
             else:
                 src, gsrc = view(op.src)
                 for b, ent in enumerate(br):
