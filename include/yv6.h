@@ -164,6 +164,15 @@ int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int32_t A, int3
                     int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same NMS on the head tensors, without materialising `pred`: cls [B,A,nc] (post-sigmoid) and reg [B,A,reg_ch] as the prediction
+ * convs write them, levels as for yv6_head_decode.  Candidate boxes are decoded on demand with the operation order of
+ * yv6_head_decode, so the kept rows are bit-identical to yv6_head_decode + yv6_nms_batched (objectness is 1, effidehead.py:133-138). */
+int yv6_nms_batched_head(yv6_handle* h, const float* cls, const float* reg, int32_t B, int32_t nc, int32_t reg_ch, int32_t nl,
+                         const int32_t* lvl_h, const int32_t* lvl_w, const float* lvl_stride, float conf_thres, double iou_thres,
+                         int32_t agnostic, int32_t multi_label, const uint8_t* class_mask, int32_t max_det, float* out,
+                         int32_t* out_count, int32_t* out_src, int32_t* overflow, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
 /* Evaluation post-processing of the batched NMS output: Evaler.scale_coords + box_convert + the top-left
  * shift of Evaler.convert_to_coco_format (yolov6/core/evaler.py:333-373) for all images in one launch.
  * det [B,max_det,6] (xyxy, conf, cls) and count [B] as written by yv6_nms_batched; meta [B,6] fp32 = (gain_h, gain_w, pad_x,

@@ -108,3 +108,26 @@ def test_detect_ring_overlapped_copies_match_eager():
             ref = non_max_suppression(m(img.to(dev))[0], **kw)
         for d, r in zip(dets, ref):
             assert torch.equal(d, r.cpu())
+
+
+@pytest.mark.parametrize("name,size,kw", [("yolov6n", 160, dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)),
+                                          ("yolov6m", 128, dict(conf_thres=0.25, iou_thres=0.45, max_det=100)),
+                                          ("yolov6l6", 128, dict(conf_thres=0.05, iou_thres=0.6, multi_label=True, agnostic=True, classes=[0, 1, 2, 5, 7]))])
+def test_nms_on_head_tensors_equals_nms_on_decoded_predictions(name, size, kw):
+    """yv6_nms_batched_head (no [B,A,5+nc] tensor; boxes decoded for candidates only, plain ltrb and DFL heads) returns the
+    rows of yv6_head_decode + yv6_nms_batched bit for bit."""
+    from yolov6_b200.model import build_model
+    from yolov6_b200.nms import nms_batched, nms_batched_head
+    from yolov6_b200.synth import randomize_
+    dev = torch.device("cuda:0")
+    m = randomize_(build_model(name, 80, dev), seed=4).eval()
+    x = torch.rand(3, 3, size, size, generator=torch.Generator().manual_seed(2)).to(dev)
+    eng = m.engine()
+    with torch.no_grad():
+        pred = eng.forward(x).clone()
+        cls, reg, sizes = eng.forward(x, decode=False)
+        a = nms_batched(pred, **kw)
+        b = nms_batched_head(cls, reg, sizes, m.graph.strides, **kw)
+    assert int(a[1].sum()) > 0
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)

@@ -29,6 +29,11 @@ constexpr int kMultiCap = 65536;    // candidate capacity per image in multi-lab
 constexpr int kSortSmemMax = 16384; // keys sorted in shared memory up to this many
 constexpr int kHistBins = 4096;     // overflow pre-selection: bins over bits [30:19] of the (positive) fp32 score
 
+__device__ __forceinline__ float4 xywh2xyxy_rn(float x, float y, float w, float h) {
+  const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);               // nms.py:24-27
+  return make_float4(__fsub_rn(x, hw), __fsub_rn(y, hh), __fadd_rn(x, hw), __fadd_rn(y, hh));
+}
+
 struct NmsWs {
   int32_t* cand_count;   // [B] slots taken (may exceed cap; clamped by the consumers)
   int32_t* overflow;     // [1]
@@ -38,8 +43,18 @@ struct NmsWs {
   int32_t cap, cap2, T;
 };
 
+constexpr int kNmsMaxLevels = 6;
 struct NmsParams {
-  const float* pred;
+  // score rows: `rows` + (b*A + a) * row_pitch; class c at [cls_off + c]; objectness at [4] when has_obj, else 1.0
+  //   pred mode: rows = pred [B,A,5+nc], row_pitch = 5+nc, cls_off = 5, has_obj = 1, boxes = rows[0..3] (xywh)
+  //   head mode: rows = cls  [B,A,nc],   row_pitch = nc,   cls_off = 0, has_obj = 0, boxes decoded from `reg` on demand
+  const float* rows;
+  int32_t row_pitch, cls_off, has_obj;
+  const float* reg;      // head mode: [B,A,R] ltrb distances or DFL logits
+  int32_t R, reg_max, nl;
+  int32_t lvl_off[kNmsMaxLevels + 1];
+  int32_t lvl_w[kNmsMaxLevels];
+  float lvl_stride[kNmsMaxLevels];
   int32_t B, A, nc, no;
   float conf;
   double iou;
@@ -51,11 +66,44 @@ struct NmsParams {
   NmsWs ws;
 };
 
-__device__ __forceinline__ float4 xywh2xyxy_rn(const float* r) {
-  const float x = __ldg(r), y = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
-  const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);               // nms.py:24-27
-  return make_float4(__fsub_rn(x, hw), __fsub_rn(y, hh), __fadd_rn(x, hw), __fadd_rn(y, hh));
+// xyxy box of anchor `anchor` of image b.  Head mode repeats, operation for operation, what head_decode_kernel (yv6_aux.cu:
+// effidehead.py:106-139, general.py:32-43) writes into `pred` and what the pred mode then reads back, so both modes keep the
+// same rows bit for bit.
+__device__ __forceinline__ float4 candidate_box(const NmsParams& p, int b, int anchor) {
+  if (p.has_obj) {
+    const float* r = p.rows + ((int64_t)b * p.A + anchor) * p.row_pitch;
+    return xywh2xyxy_rn(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+  }
+  const float* reg = p.reg + ((int64_t)b * p.A + anchor) * p.R;
+  float d[4];
+  if (p.R == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = __ldg(reg + k);
+  } else {
+    const int nb = p.reg_max + 1;
+    for (int k = 0; k < 4; ++k) {
+      const float* l = reg + k * nb;
+      float mx = -INFINITY;
+      for (int i = 0; i < nb; ++i) mx = fmaxf(mx, __ldg(l + i));
+      float den = 0.f;
+      for (int i = 0; i < nb; ++i) den += expf(__ldg(l + i) - mx);
+      float e = 0.f;
+      for (int i = 0; i < nb; ++i) e = __fadd_rn(e, __fmul_rn(expf(__ldg(l + i) - mx) / den, (float)i));
+      d[k] = e;
+    }
+  }
+  int lvl = 0;
+  while (lvl + 1 < p.nl && anchor >= p.lvl_off[lvl + 1]) ++lvl;
+  const int local = anchor - p.lvl_off[lvl];
+  const float ax = (float)(local % p.lvl_w[lvl]) + 0.5f;
+  const float ay = (float)(local / p.lvl_w[lvl]) + 0.5f;
+  const float st = p.lvl_stride[lvl];
+  const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
+  const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
+  return xywh2xyxy_rn(__fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), st), __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), st),
+                      __fmul_rn(__fsub_rn(x2, x1), st), __fmul_rn(__fsub_rn(y2, y1), st));
 }
+
 
 __device__ __forceinline__ uint64_t make_key(float score, int order) {
   return ((uint64_t)(0xffffffffu - __float_as_uint(score)) << 32) | (uint32_t)order;  // score > 0
@@ -72,7 +120,7 @@ __device__ __forceinline__ void scan_rows(const NmsParams& p, const float* const
                                           RowScan (&r)[R]) {
 #pragma unroll
   for (int q = 0; q < R; ++q) {
-    r[q].obj = ok[q] ? __ldg(row[q] + 4) : 0.f;
+    r[q].obj = ok[q] ? (p.has_obj ? __ldg(row[q] + 4) : 1.f) : 0.f;
     r[q].raw_max = -INFINITY;
     r[q].best = -INFINITY;
     r[q].best_c = 0x7fffffff;
@@ -82,7 +130,7 @@ __device__ __forceinline__ void scan_rows(const NmsParams& p, const float* const
     const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[c] != 0);
     float v[R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) v[q] = ok[q] ? __ldg(row[q] + 5 + c) : -INFINITY;
+    for (int q = 0; q < R; ++q) v[q] = ok[q] ? __ldg(row[q] + p.cls_off + c) : -INFINITY;
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       r[q].raw_max = fmaxf(r[q].raw_max, v[q]);
@@ -122,7 +170,7 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
   uint64_t* keys = p.ws.keys + (int64_t)b * p.ws.cap2;
   const int a0 = blockIdx.x * kNmsTile + warp * 32;
   if (a0 >= p.A) return;
-  const float* img = p.pred + (int64_t)b * p.A * p.no;
+  const float* img = p.rows + (int64_t)b * p.A * p.row_pitch;
   int my_entries = 0;                                                      // lane i: entries of row a0 + i
   for (int i0 = 0; i0 < 32; i0 += R) {
     const float* row[R];
@@ -131,7 +179,7 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       ok[q] = (a0 + i0 + q < p.A);
-      row[q] = img + (int64_t)(a0 + i0 + q) * p.no;
+      row[q] = img + (int64_t)(a0 + i0 + q) * p.row_pitch;
     }
     scan_rows<R>(p, row, ok, lane, r);
 #pragma unroll
@@ -161,7 +209,7 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         ok[q] = __shfl_sync(0xffffffffu, my_entries, i0 + q) != 0;
-        row[q] = img + (int64_t)(a0 + i0 + q) * p.no;
+        row[q] = img + (int64_t)(a0 + i0 + q) * p.row_pitch;
         any = any || ok[q];
       }
       if (!any) continue;  // warp-uniform
@@ -187,13 +235,13 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
     }
     if (!any) continue;  // warp-uniform
 #pragma unroll
-    for (int q = 0; q < R; ++q) obj[q] = ok[q] ? __ldg(img + (int64_t)(a0 + i0 + q) * p.no + 4) : 0.f;
+    for (int q = 0; q < R; ++q) obj[q] = ok[q] ? (p.has_obj ? __ldg(img + (int64_t)(a0 + i0 + q) * p.row_pitch + 4) : 1.f) : 0.f;
     for (int c0 = 0; c0 < p.nc; c0 += 32) {                               // class-ascending within each row
       const int c = c0 + lane;
       const bool cls_ok = (c < p.nc) && ((p.class_mask == nullptr) || (p.class_mask[c] != 0));
       float v[R];
 #pragma unroll
-      for (int q = 0; q < R; ++q) v[q] = (ok[q] && c < p.nc) ? __ldg(img + (int64_t)(a0 + i0 + q) * p.no + 5 + c) : 0.f;
+      for (int q = 0; q < R; ++q) v[q] = (ok[q] && c < p.nc) ? __ldg(img + (int64_t)(a0 + i0 + q) * p.row_pitch + p.cls_off + c) : 0.f;
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         const float sv = __fmul_rn(v[q], obj[q]);
@@ -243,10 +291,10 @@ __global__ void __launch_bounds__(256) nms_overflow_pass_kernel(const NmsParams 
 
 template <bool EMIT>
 __device__ __forceinline__ void overflow_row(const NmsParams& p, int b, int a, int lane, int cut) {
-  const float* row = p.pred + ((int64_t)b * p.A + a) * p.no;
-  const float obj = __ldg(row + 4);
+  const float* row = p.rows + ((int64_t)b * p.A + a) * p.row_pitch;
+  const float obj = p.has_obj ? __ldg(row + 4) : 1.f;
   float raw_max = -INFINITY;
-  for (int c = lane; c < p.nc; c += 32) raw_max = fmaxf(raw_max, __ldg(row + 5 + c));
+  for (int c = lane; c < p.nc; c += 32) raw_max = fmaxf(raw_max, __ldg(row + p.cls_off + c));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) raw_max = fmaxf(raw_max, __shfl_xor_sync(0xffffffffu, raw_max, o));
   if (!((obj > p.conf) && (raw_max > p.conf))) return;                    // nms.py:48
@@ -255,7 +303,7 @@ __device__ __forceinline__ void overflow_row(const NmsParams& p, int b, int a, i
   for (int c0 = 0; c0 < p.nc; c0 += 32) {
     const int c = c0 + lane;
     const bool cls_ok = (c < p.nc) && ((p.class_mask == nullptr) || (p.class_mask[c] != 0));
-    const float sv = (c < p.nc) ? __fmul_rn(__ldg(row + 5 + c), obj) : 0.f;
+    const float sv = (c < p.nc) ? __fmul_rn(__ldg(row + p.cls_off + c), obj) : 0.f;
     const bool hit = cls_ok && (sv > p.conf);
     if (!EMIT) {
       if (hit) atomicAdd(&hist[score_bin(sv)], 1u);
@@ -404,16 +452,16 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
         if (p.multi_label) {
           cls = order - anchor * div;
         } else {                                                         // best class: recompute from the row (exact)
-          const float* row = p.pred + ((int64_t)b * p.A + anchor) * p.no;
-          const float obj = __ldg(row + 4);
+          const float* row = p.rows + ((int64_t)b * p.A + anchor) * p.row_pitch;
+          const float obj = p.has_obj ? __ldg(row + 4) : 1.f;
           float best = -INFINITY;
           cls = 0;
           for (int cc = 0; cc < p.nc; ++cc) {
-            const float sv = __fmul_rn(__ldg(row + 5 + cc), obj);
+            const float sv = __fmul_rn(__ldg(row + p.cls_off + cc), obj);
             if (sv > best) { best = sv; cls = cc; }
           }
         }
-        const float4 raw = xywh2xyxy_rn(p.pred + ((int64_t)b * p.A + anchor) * p.no);
+        const float4 raw = candidate_box(p, b, anchor);
         float4 bx = raw;
         if (!p.agnostic) {
           const float off = __fmul_rn((float)cls, 4096.f);                // nms.py:94
@@ -560,22 +608,18 @@ extern "C" int64_t yv6_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc, int
   return total;
 }
 
-extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int32_t A, int32_t nc, float conf_thres,
-                               double iou_thres, int32_t agnostic, int32_t multi_label, const uint8_t* class_mask,
-                               int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
-                               void* workspace, int64_t workspace_bytes, void* stream) {
-  yv6_device_guard _dev(h);
-  YV6_REQUIRE(h && pred && out && out_count && out_src && workspace, "nms: null argument");
+static int nms_launch(yv6_handle* h, NmsParams& p, int32_t B, int32_t A, int32_t nc, float conf_thres, double iou_thres,
+                      int32_t agnostic, int32_t multi_label, const uint8_t* class_mask, int32_t max_det, float* out,
+                      int32_t* out_count, int32_t* out_src, int32_t* overflow, void* workspace, int64_t workspace_bytes, void* stream) {
+  YV6_REQUIRE(out && out_count && out_src && workspace, "nms: null argument");
   YV6_REQUIRE(B > 0 && A > 0 && nc > 0, "nms: bad shape B=%d A=%d nc=%d", B, A, nc);
   YV6_REQUIRE(conf_thres >= 0.f && conf_thres <= 1.f, "nms: conf_thres must be in [0,1]");       // nms.py:50
   YV6_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, "nms: iou_thres must be in [0,1]");          // nms.py:51
   YV6_REQUIRE(max_det > 0 && max_det <= 4096, "nms: max_det=%d out of range (1..4096)", max_det);
-  NmsParams p;
   int64_t need = 0;
   const int ml = (multi_label && nc > 1) ? 1 : 0;                                                // nms.py:57
   nms_layout(B, A, nc, ml, &p.ws, &need, reinterpret_cast<char*>(workspace));
   YV6_REQUIRE(workspace_bytes >= need, "nms: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
-  p.pred = pred;
   p.B = B;
   p.A = A;
   p.nc = nc;
@@ -614,6 +658,51 @@ extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int3
   return YV6_OK;
 }
 
+extern "C" int yv6_nms_batched(yv6_handle* h, const float* pred, int32_t B, int32_t A, int32_t nc, float conf_thres,
+                               double iou_thres, int32_t agnostic, int32_t multi_label, const uint8_t* class_mask,
+                               int32_t max_det, float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && pred, "nms: null argument");
+  NmsParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = pred;
+  p.row_pitch = nc + 5;
+  p.cls_off = 5;
+  p.has_obj = 1;
+  return nms_launch(h, p, B, A, nc, conf_thres, iou_thres, agnostic, multi_label, class_mask, max_det, out, out_count, out_src, overflow,
+                    workspace, workspace_bytes, stream);
+}
+
+extern "C" int yv6_nms_batched_head(yv6_handle* h, const float* cls, const float* reg, int32_t B, int32_t nc, int32_t reg_ch, int32_t nl,
+                                    const int32_t* lvl_h, const int32_t* lvl_w, const float* lvl_stride, float conf_thres,
+                                    double iou_thres, int32_t agnostic, int32_t multi_label, const uint8_t* class_mask, int32_t max_det,
+                                    float* out, int32_t* out_count, int32_t* out_src, int32_t* overflow, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && cls && reg && lvl_h && lvl_w && lvl_stride, "nms_head: null argument");
+  YV6_REQUIRE(nl >= 1 && nl <= kNmsMaxLevels && reg_ch >= 4 && reg_ch % 4 == 0, "nms_head: nl=%d reg_ch=%d", nl, reg_ch);
+  NmsParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = cls;
+  p.row_pitch = nc;
+  p.cls_off = 0;
+  p.has_obj = 0;
+  p.reg = reg;
+  p.R = reg_ch;
+  p.reg_max = reg_ch / 4 - 1;
+  p.nl = nl;
+  int A = 0;
+  for (int l = 0; l < nl; ++l) {
+    p.lvl_off[l] = A;
+    p.lvl_w[l] = lvl_w[l];
+    p.lvl_stride[l] = lvl_stride[l];
+    A += lvl_h[l] * lvl_w[l];
+  }
+  p.lvl_off[nl] = A;
+  return nms_launch(h, p, B, A, nc, conf_thres, iou_thres, agnostic, multi_label, class_mask, max_det, out, out_count, out_src, overflow,
+                    workspace, workspace_bytes, stream);
+}
 
 extern "C" int yv6_eval_boxes(yv6_handle* h, const float* det, const int32_t* count, const float* meta, int32_t B, int32_t max_det,
                               float* out, void* stream) {

@@ -260,9 +260,10 @@ class InferEngine:
         """Kernels launched per forward for this shape (convs + stem + pools + decode)."""
         return len(self._plan(N, H, W, in_dtype)["calls"]) + 1
 
-    def forward(self, x, stream=None):
+    def forward(self, x, stream=None, decode=True):
         """x: [N,3,H,W] CUDA tensor, fp32 in [0,1] or uint8.  Returns pred [N,A,5+nc] fp32 (a buffer owned
-        by the engine, overwritten by the next call with the same shape)."""
+        by the engine, overwritten by the next call with the same shape).  decode=False stops after the head convs and
+        returns (cls [N,A,nc], reg [N,A,R], level sizes): the serving pipeline feeds them to the NMS kernels directly."""
         if x.device != self.device:
             raise RuntimeError(f"input on {x.device}, engine on {self.device}")
         if x.dtype not in (torch.float32, torch.uint8):
@@ -283,6 +284,8 @@ class InferEngine:
             else:
                 chk(lib.yv6_sppf_pool(h, C.c_void_p(d[0]), d[1], d[2], d[3], d[4], d[5], d[6], d[7], sp))
         g = self.g
+        if not decode:
+            return plan["cls"], plan["reg"], plan["sizes"]
         chk(lib.yv6_head_decode(h, C.c_void_p(plan["cls"].data_ptr()), C.c_void_p(plan["reg"].data_ptr()),
                                 C.c_void_p(plan["pred"].data_ptr()), N, g.num_classes, 4 * (g.reg_max + 1),
                                 len(g.strides), plan["lvl_h"], plan["lvl_w"], plan["lvl_s"], sp))

@@ -14,7 +14,7 @@ instead of their sum.
 """
 import torch
 
-from .nms import nms_batched, workspace_bytes
+from .nms import nms_batched_head, workspace_bytes
 
 
 class DetectPipeline:
@@ -50,8 +50,10 @@ class DetectPipeline:
     def _body(self):
         if self.host_input and not self.overlap_h2d:
             self.x_dev.copy_(self.x_host, non_blocking=True)
-        pred = self.eng.forward(self.x_dev)
-        out, count, src, overflow = nms_batched(pred, workspace=self.nms_ws, **self.kw)
+        # the [B, A, 5+nc] prediction tensor of Detect.forward (effidehead.py:131-139) is never materialised here: the NMS
+        # kernels scan the class scores where the cls_pred convs wrote them and decode boxes for the candidates only
+        cls, reg, sizes = self.eng.forward(self.x_dev, decode=False)
+        out, count, src, overflow = nms_batched_head(cls, reg, sizes, self.model.graph.strides, workspace=self.nms_ws, **self.kw)
         self.out_dev, self.count_dev = out, count
         if self.host_input:
             self.out_host.copy_(out, non_blocking=True)
