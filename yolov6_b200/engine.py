@@ -10,6 +10,7 @@ Precision modes: "bf16" (bf16 operands, fp32 accumulate) and "fp32" (bf16x3 spli
 equivalent products, used for the 1e-4 parity bar of BASELINE.json).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -41,6 +42,8 @@ class InferEngine:
         self.handle = _lib.handle(device.index or 0)
         self.lib = _lib.lib()
         self.fuse_siblings = True
+        self.n_lanes = int(os.environ.get("YV6_LANES", "4"))   # streams the launches of one forward are spread over (1 = serial)
+        self._side = None
         self.weights = {}     # op index -> dict(w=..., bias=..., alpha=...)
         self._plans = {}      # (N, H, W, dtype) -> plan, least recently used first; bounded (rect-shaped evaluation
         self.max_plans = 4    # would otherwise keep one full activation set per distinct shape)
@@ -123,7 +126,7 @@ class InferEngine:
         maxs = max(g.strides)
         if H % maxs or W % maxs:
             raise RuntimeError(f"input {H}x{W} must be a multiple of the largest stride {maxs}")
-        plan = {"bufs": [], "calls": [], "conv_info": []}
+        plan = {"bufs": [], "calls": [], "conv_info": [], "deps": []}
         for b in g.bufs:
             h, w = H >> b.level, W >> b.level
             shape = (P, N, h, w, b.c_total) if P == 3 else (N, h, w, b.c_total)
@@ -165,6 +168,10 @@ class InferEngine:
         def coff(t):
             return t.c_off + (redirect[t.buf][1] if t.buf in redirect else 0)
 
+        def span(t):
+            """(tensor identity, first channel, end channel) of a graph tensor slice: the unit of the dependency analysis."""
+            return (id(view(t)[0]), coff(t), coff(t) + t.c)
+
         for i, op in enumerate(g.ops):
             ent = self.weights.get(i)
             if op.kind == "stem":
@@ -181,6 +188,7 @@ class InferEngine:
                 d.nsplit = P
                 plan["stem"] = d
                 plan["calls"].append(("stem", d))
+                plan["deps"].append(dict(reads=[], writes=[span(op.dst)]))
             elif op.kind in ("conv", "pred", "convT"):
                 if i in self.sibling_second:
                     continue                      # computed by its sibling's launch
@@ -244,11 +252,59 @@ class InferEngine:
                         d.res_plane_stride = rbuf.stride(0) if P == 3 else 0
                         d.alpha = ent["alpha"]
                     plan["calls"].append(("conv", d))
+                    reads = [span(op.src)] + ([span(op.res)] if op.res is not None else [])
+                    if op.kind == "pred":
+                        writes = [(("head",) + tuple(op.head), 0, 1)]
+                    elif fused:
+                        writes = [(id(dbuf), 0, 2 * op.cout)]
+                    else:
+                        writes = [span(op.dst)]
+                    plan["deps"].append(dict(reads=reads, writes=writes))
             elif op.kind == "pool":
                 buf, h, w, ct = view(op.dst)
                 plan["calls"].append(("pool", (buf.data_ptr(), N, h, w, op.cin, ct, P, buf.stride(0) if P == 3 else 0)))
+                plan["deps"].append(dict(reads=[(id(buf), 0, op.cin)], writes=[(id(buf), op.cin, 4 * op.cin)]))
+        self._schedule(plan)
         self._plans[key] = plan
         return plan
+
+    def _schedule(self, plan):
+        """Assigns every launch to one of a few streams from its data dependencies (channel slices of the activation buffers):
+        a chain keeps its stream, an op whose producers' streams have moved on takes the least recently used one and waits on
+        events.  The backbone stays one chain; the branches of BiFusion (transpose-conv quadrants, cv1, cv2 + downsample), of
+        CSPSPPF and the three head levels run side by side -- these launches are tens of CTAs and a few microseconds each, and
+        their launch-to-first-MMA latency and drain overlap instead of adding up.  Inside a captured CUDA graph the events
+        become plain graph edges."""
+        K = self.n_lanes
+        deps = plan["deps"]
+        n = len(deps)
+        writers = {}
+        lane, waits = [0] * n, [[] for _ in range(n)]
+        last_on = [-1] * K
+        for i, dp in enumerate(deps):
+            prod = set()
+            for key, lo, hi in dp["reads"]:
+                for wlo, whi, j in writers.get(key, ()):
+                    if wlo < hi and lo < whi:
+                        prod.add(j)
+            chain = [lane[j] for j in prod if last_on[lane[j]] == j]
+            if chain:
+                s = min(chain)
+            elif not prod:
+                s = 0
+            else:
+                s = min(range(K), key=lambda t: last_on[t])
+            lane[i] = s
+            waits[i] = sorted(j for j in prod if lane[j] != s)
+            last_on[s] = i
+            for key, lo, hi in dp["writes"]:
+                writers.setdefault(key, []).append((lo, hi, i))
+        need = set(j for w in waits for j in w)
+        tails = [last_on[t] for t in range(1, K) if last_on[t] >= 0]
+        need.update(tails)
+        plan["lane"], plan["waits"], plan["tails"] = lane, waits, tails
+        plan["events"] = {j: torch.cuda.Event() for j in need}
+        plan["fork"] = torch.cuda.Event()
 
     def pin(self, N, H, W, in_dtype=torch.float32):
         """Keep the buffers of this shape for the engine's lifetime (they are referenced by a captured CUDA graph)."""
@@ -273,16 +329,40 @@ class InferEngine:
         assert Cin == 3
         plan = self._plan(N, H, W, x.dtype)
         plan["image"] = x  # keep alive while kernels are in flight
-        sp = _lib.stream_ptr(stream)
+        main = stream if stream is not None else torch.cuda.current_stream(self.device)
+        sp = _lib.stream_ptr(main)
         lib, h, chk = self.lib, self.handle, _lib.check
         plan["stem"].x = x.data_ptr()
-        for kind, d in plan["calls"]:
+        lane, waits, events = plan["lane"], plan["waits"], plan["events"]
+        multi = self.n_lanes > 1 and max(lane) > 0
+        if multi:
+            if self._side is None:
+                self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.n_lanes - 1)]
+            streams = [main] + self._side
+            sps = [_lib.stream_ptr(t) for t in streams]
+            plan["fork"].record(main)
+            forked = set()
+        for i, (kind, d) in enumerate(plan["calls"]):
+            if multi:
+                t = lane[i]
+                if t and t not in forked:        # a side stream starts after everything the caller queued before this forward
+                    streams[t].wait_event(plan["fork"])
+                    forked.add(t)
+                for j in waits[i]:
+                    streams[t].wait_event(events[j])
+                sp = sps[t]
             if kind == "conv":
                 chk(lib.yv6_conv_fwd(h, C.byref(d), sp))
             elif kind == "stem":
                 chk(lib.yv6_stem_fwd(h, C.byref(d), sp))
             else:
                 chk(lib.yv6_sppf_pool(h, C.c_void_p(d[0]), d[1], d[2], d[3], d[4], d[5], d[6], d[7], sp))
+            if multi and i in events:
+                events[i].record(streams[lane[i]])
+        if multi:                                  # join: the caller's stream continues after every lane
+            for j in plan["tails"]:
+                main.wait_event(events[j])
+            sp = sps[0]
         g = self.g
         if not decode:
             return plan["cls"], plan["reg"], plan["sizes"]
