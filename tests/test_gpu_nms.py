@@ -111,8 +111,8 @@ def test_detect_ring_overlapped_copies_match_eager():
 
 
 @pytest.mark.parametrize("name,size,kw", [("yolov6n", 160, dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)),
-                                          ("yolov6m", 128, dict(conf_thres=0.25, iou_thres=0.45, max_det=100)),
-                                          ("yolov6l6", 128, dict(conf_thres=0.05, iou_thres=0.6, multi_label=True, agnostic=True, classes=[0, 1, 2, 5, 7]))])
+                                          ("yolov6m", 128, dict(conf_thres=0.001, iou_thres=0.45, max_det=100)),
+                                          ("yolov6l6", 128, dict(conf_thres=0.0005, iou_thres=0.6, multi_label=True, agnostic=True, classes=[0, 1, 2, 5, 7]))])
 def test_nms_on_head_tensors_equals_nms_on_decoded_predictions(name, size, kw):
     """yv6_nms_batched_head (no [B,A,5+nc] tensor; boxes decoded for candidates only, plain ltrb and DFL heads) returns the
     rows of yv6_head_decode + yv6_nms_batched bit for bit."""
@@ -128,6 +128,47 @@ def test_nms_on_head_tensors_equals_nms_on_decoded_predictions(name, size, kw):
         cls, reg, sizes = eng.forward(x, decode=False)
         a = nms_batched(pred, **kw)
         b = nms_batched_head(cls, reg, sizes, m.graph.strides, **kw)
-    assert int(a[1].sum()) > 0
+    print(name, "detections per image:", a[1].tolist())
+    assert int(a[1].sum()) > 0, "the case must produce detections to mean anything"
     for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("spread,expect_fallback", [(4.0, True), (200.0, False)])
+def test_head_mode_topk_prefix_and_its_fallback(spread, expect_fallback):
+    """Head-tensor mode sorts only the best ~2048 candidates first; when suppression is so heavy that they do not yield
+    max_det boxes the full sort + a second greedy pass must take over.  Synthetic head tensors: many candidates, boxes
+    packed into a few clusters (spread 4 px: almost everything is suppressed) or scattered."""
+    import ctypes as C
+    from yolov6_b200 import _lib
+    from yolov6_b200.nms import nms_batched, nms_batched_head
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7)
+    B, nc, sizes, strides = 2, 80, [(40, 40), (20, 20), (10, 10)], [8, 16, 32]
+    A = sum(h * w for h, w in sizes)
+    cls = (torch.rand(B, A, nc, generator=g) ** 3).to(dev).contiguous()             # ~ 47 k scores above 0.05 per image
+    # ltrb distances that pull every box towards one of four cluster centres
+    reg = torch.zeros(B, A, 4)
+    off = 0
+    for (h, w), s in zip(sizes, strides):
+        ys, xs = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
+        cx = (torch.randint(0, 4, (h * w,), generator=g).float() * 60 + 60 + torch.randn(h * w, generator=g) * spread) / s
+        cy = (torch.randint(0, 4, (h * w,), generator=g).float() * 60 + 60 + torch.randn(h * w, generator=g) * spread) / s
+        half = 20.0 / s
+        ax, ay = xs.reshape(-1), ys.reshape(-1)
+        reg[:, off:off + h * w] = torch.stack([ax - (cx - half), ay - (cy - half), (cx + half) - ax, (cy + half) - ay], 1)
+        off += h * w
+    reg = reg.to(dev).contiguous()
+    pred = torch.empty(B, A, 5 + nc, device=dev)
+    lh, lw = (C.c_int32 * 3)(*[h for h, _ in sizes]), (C.c_int32 * 3)(*[w for _, w in sizes])
+    ls = (C.c_float * 3)(*[float(s) for s in strides])
+    _lib.check(_lib.lib().yv6_head_decode(_lib.handle(0), C.c_void_p(cls.data_ptr()), C.c_void_p(reg.data_ptr()), C.c_void_p(pred.data_ptr()),
+                                          B, nc, 4, 3, lh, lw, ls, _lib.stream_ptr()))
+    kw = dict(conf_thres=0.05, iou_thres=0.5, multi_label=True, max_det=300)
+    a = nms_batched(pred, **kw)
+    b = nms_batched_head(cls, reg, sizes, strides, **kw)
+    counts = a[1].tolist()
+    print("spread", spread, "kept per image", counts)
+    assert (min(counts) < 300) == expect_fallback, "the case must (not) exhaust the prefix to test what it claims"
+    for u, v in zip(a[:3], b[:3]):
         assert torch.equal(u, v)

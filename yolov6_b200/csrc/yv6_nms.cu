@@ -27,6 +27,8 @@ constexpr int kNmsTile = 256;       // anchors per block in scan/emit
 constexpr int kMaxNms = 30000;      // nms.py:55
 constexpr int kMultiCap = 65536;    // candidate capacity per image in multi-label mode
 constexpr int kSortSmemMax = 16384; // keys sorted in shared memory up to this many
+constexpr int kTopK = 2048;         // size the sorted prefix aims at
+constexpr int kTopCap = 8192;       // ... and may reach (one histogram bin can hold many keys); beyond it the full sort runs
 constexpr int kHistBins = 4096;     // overflow pre-selection: bins over bits [30:19] of the (positive) fp32 score
 
 __device__ __forceinline__ float4 xywh2xyxy_rn(float x, float y, float w, float h) {
@@ -40,6 +42,12 @@ struct NmsWs {
   uint64_t* keys;        // [B][cap2]
   uint32_t* hist;        // [B][kHistBins] score histogram of the images that overflowed `cap` (null when cap covers A*nc)
   int32_t* cutoff;       // [B] lowest histogram bin that still enters the sort, -1 = image did not overflow
+  // top-K prefix (head mode): the greedy pass stops at max_det kept boxes and normally consumes only the best few hundred
+  // candidates, so only the best ~kTopK keys of an image are sorted first; the full sort runs only if they did not suffice
+  uint32_t* top_hist;    // [B][kHistBins] score histogram of every candidate (filled by nms_select_rows_kernel), or null
+  uint64_t* top_keys;    // [B][kTopCap] sorted prefix
+  int32_t* top_n;        // [B] keys in the prefix; -1 = the prefix IS the whole (fully sorted) list in `keys`
+  int32_t* need_full;    // [B] set by the greedy pass when the prefix ran out before max_det boxes were kept
   int32_t cap, cap2, T;
 };
 
@@ -266,7 +274,86 @@ __global__ void __launch_bounds__(kNmsTile) nms_select_kernel(const NmsParams p)
 // max_nms candidates, (3) re-emit only the candidates of those bins.  The sort then orders them by the full
 // key, so the first 30000 are exactly the 30000 best under the stable order.  Only if the kept bins still
 // hold more than `cap` keys (tens of thousands of scores equal to 8 significant bits) is `overflow` raised.
+
+// bins over bits [30:19] of a positive fp32 score: monotone in the score
 __device__ __forceinline__ int score_bin(float s) { return (int)((__float_as_uint(s) >> 19) & (kHistBins - 1)); }
+
+// ------------------------------------------------------------------------------------------------
+// Candidate selection for the head-tensor mode (rows = cls [B,A,nc], contiguous, objectness 1): each warp stages 32
+// consecutive rows (one contiguous 32*nc*4-byte chunk, 16-byte loads) in shared memory with an odd row pitch and every LANE
+// then walks ONE row from shared memory -- no cross-lane reductions at all (the generic kernel above spends most of its
+// instructions in shuffles: five rounds x four values per row).  Same candidate rule, same keys.
+constexpr int kSelRows = 32;
+__global__ void __launch_bounds__(256) nms_select_rows_kernel(const NmsParams p) {
+  extern __shared__ float sel_smem[];                       // [8 warps][32 rows][pitch]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = p.nc | 1;                               // odd -> lane-per-row reads are bank-conflict free
+  float* tile = sel_smem + (size_t)warp * kSelRows * pitch;
+  const int a0 = (blockIdx.x * 8 + warp) * kSelRows;
+  if (a0 >= p.A) return;
+  const int nrows = min(kSelRows, p.A - a0);
+  const float* src = p.rows + ((int64_t)b * p.A + a0) * p.nc;
+  const int total = nrows * p.nc;                           // floats; row starts are 16-byte aligned (nc % 4 == 0)
+  for (int i = lane * 4; i < total; i += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    const int r = i / p.nc, c = i - r * p.nc;               // nc % 4 == 0: a float4 never straddles two rows
+    float* d = tile + r * pitch + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncwarp();
+  const bool ok = lane < nrows;
+  const float* row = tile + lane * pitch;
+  float raw_max = -INFINITY, best = -INFINITY;
+  int best_c = 0, cnt = 0;
+  if (ok) {
+    for (int c = 0; c < p.nc; ++c) {
+      const float v = row[c];                               // obj = 1: score = v * 1.0f = v (nms.py:69)
+      raw_max = fmaxf(raw_max, v);
+      if (v > best) { best = v; best_c = c; }               // first max (nms.py:79)
+      const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[c] != 0);
+      if (v > p.conf && cls_ok) ++cnt;
+    }
+  }
+  const bool cand = ok && (1.f > p.conf) && (raw_max > p.conf);                 // nms.py:48
+  int entries;
+  if (p.multi_label) {
+    entries = cand ? cnt : 0;                                                   // nms.py:75-77
+  } else {
+    const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[best_c] != 0);
+    entries = (cand && best > p.conf && cls_ok) ? 1 : 0;                        // nms.py:79-84
+  }
+  int incl = entries;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int tot = __shfl_sync(0xffffffffu, incl, 31);
+  if (tot == 0) return;
+  int slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(&p.ws.cand_count[b], tot);
+  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  int slot = slot0 + incl - entries;
+  if (entries == 0) return;
+  uint64_t* keys = p.ws.keys + (int64_t)b * p.ws.cap2;
+  const int a = a0 + lane;
+  uint32_t* th = p.ws.top_hist + (int64_t)b * kHistBins;
+  if (!p.multi_label) {
+    if (slot < p.ws.cap) keys[slot] = make_key(best, a);
+    atomicAdd(&th[score_bin(best)], 1u);
+    return;
+  }
+  for (int c = 0; c < p.nc; ++c) {                                              // class-ascending within the row
+    const float v = row[c];
+    const bool cls_ok = (p.class_mask == nullptr) || (p.class_mask[c] != 0);
+    if (v > p.conf && cls_ok) {
+      if (slot < p.ws.cap) keys[slot] = make_key(v, a * p.nc + c);
+      atomicAdd(&th[score_bin(v)], 1u);
+      ++slot;
+    }
+  }
+}
 
 constexpr int kOverflowRows = 64;
 template <bool EMIT>
@@ -362,25 +449,9 @@ __global__ void __launch_bounds__(1024) nms_cutoff_kernel(const NmsParams p) {
   }
 }
 
-__global__ void __launch_bounds__(1024) nms_sort_kernel(const NmsParams p) {
-  extern __shared__ uint64_t skeys[];
-  const int b = blockIdx.x;
-  const int taken = p.ws.cand_count[b];
-  if (taken > p.ws.cap && threadIdx.x == 0) atomicExch(p.ws.overflow, 1);
-  const int n = min(taken, p.ws.cap);
-  if (n <= 1) return;
-  int P = 2;
-  while (P < n) P <<= 1;
-  uint64_t* g = p.ws.keys + (int64_t)b * p.ws.cap2;
-  const bool in_smem = (P <= kSortSmemMax);
-  uint64_t* k = in_smem ? skeys : g;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const uint64_t v = (i < n) ? g[i] : ~0ull;  // pad sorts last
-    k[i] = v;
-  }
-  __syncthreads();
-  // Bitonic network.  Compare-exchange distances below CH stay inside one warp's chunk of CH keys, so those
-  // passes need only __syncwarp; block barriers are paid for the few long-distance passes alone.
+// Bitonic network over P (power of two) keys by one block.  Compare-exchange distances below CH stay inside one warp's
+// chunk of CH keys, so those passes need only __syncwarp; block barriers are paid for the few long-distance passes alone.
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* k, int P) {
   const int CH = min(P, 256);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int size = 2; size <= P; size <<= 1) {
@@ -410,12 +481,115 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const NmsParams p) {
     }
     __syncthreads();
   }
+}
+
+// Full sort of an image's keys (in place).  FALLBACK = second launch of the top-K scheme: only images whose prefix ran out.
+template <bool FALLBACK>
+__global__ void __launch_bounds__(1024) nms_sort_kernel(const NmsParams p) {
+  extern __shared__ uint64_t skeys[];
+  const int b = blockIdx.x;
+  if (FALLBACK && !p.ws.need_full[b]) return;
+  const int taken = p.ws.cand_count[b];
+  if (!FALLBACK && taken > p.ws.cap && threadIdx.x == 0) atomicExch(p.ws.overflow, 1);
+  const int n = min(taken, p.ws.cap);
+  if (n <= 1) return;
+  int P = 2;
+  while (P < n) P <<= 1;
+  uint64_t* g = p.ws.keys + (int64_t)b * p.ws.cap2;
+  const bool in_smem = (P <= kSortSmemMax);
+  uint64_t* k = in_smem ? skeys : g;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const uint64_t v = (i < n) ? g[i] : ~0ull;  // pad sorts last
+    k[i] = v;
+  }
+  __syncthreads();
+  block_bitonic_sort(k, P);
   if (in_smem)
     for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = k[i];
 }
 
+// Top-K prefix: sorts all keys when there are at most kTopK of them (top_n = -1: `keys` is the sorted list); otherwise picks the
+// lowest score bin such that the bins from it upwards hold >= kTopK keys, gathers exactly those keys and sorts them into
+// `top_keys`.  Every key outside the prefix has a strictly lower score bin, so the prefix is a true prefix of the full order.
+__global__ void __launch_bounds__(1024) nms_topk_sort_kernel(const NmsParams p) {
+  extern __shared__ uint64_t skeys[];
+  __shared__ uint32_t part[1024];
+  __shared__ int s_cut, s_m, s_fill;
+  const int b = blockIdx.x;
+  const int taken = p.ws.cand_count[b];
+  if (taken > p.ws.cap && threadIdx.x == 0) atomicExch(p.ws.overflow, 1);
+  const int n = min(taken, p.ws.cap);
+  uint64_t* g = p.ws.keys + (int64_t)b * p.ws.cap2;
+  if (n <= kTopK) {                     // small image: one full sort, as before
+    if (threadIdx.x == 0) p.ws.top_n[b] = -1;
+    if (n <= 1) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = (i < n) ? g[i] : ~0ull;
+    __syncthreads();
+    block_bitonic_sort(skeys, P);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = skeys[i];
+    return;
+  }
+  constexpr int PER = kHistBins / 1024;
+  const uint32_t* hist = p.ws.top_hist + (int64_t)b * kHistBins;
+  uint32_t mine[PER], tot = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { mine[j] = hist[threadIdx.x * PER + j]; tot += mine[j]; }
+  part[threadIdx.x] = tot;
+  if (threadIdx.x == 0) { s_cut = 0; s_m = 0; s_fill = 0; }
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t add = (threadIdx.x + o < 1024) ? part[threadIdx.x + o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const uint32_t above = (threadIdx.x + 1 < 1024) ? part[threadIdx.x + 1] : 0u;
+  if (above < (uint32_t)kTopK && part[threadIdx.x] >= (uint32_t)kTopK) {
+    uint32_t acc = above;
+    int cut = threadIdx.x * PER;
+    for (int j = PER - 1; j >= 0; --j) {
+      acc += mine[j];
+      if (acc >= (uint32_t)kTopK) { cut = threadIdx.x * PER + j; break; }
+    }
+    s_cut = cut;
+    s_m = (int)acc;
+  }
+  __syncthreads();
+  const int cut = s_cut, m = s_m;
+  // the histogram counts every candidate, the key list may have been truncated to `cap` (then the overflow pass re-emitted the
+  // best >= 30000): m keys are expected above the cut; if they do not fit the prefix buffer, or the lists disagree, sort everything
+  if (m <= 0 || m > kTopCap || taken > p.ws.cap) {
+    if (threadIdx.x == 0) { p.ws.top_n[b] = 0; p.ws.need_full[b] = 1; }
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t key = g[i];
+    const float sc = __uint_as_float(0xffffffffu - (uint32_t)(key >> 32));
+    if (score_bin(sc) >= cut) {
+      const int at = atomicAdd(&s_fill, 1);
+      if (at < kTopCap) skeys[at] = key;
+    }
+  }
+  __syncthreads();
+  const int got = min(s_fill, kTopCap);
+  int P = 2;
+  while (P < got) P <<= 1;
+  for (int i = got + threadIdx.x; i < P; i += blockDim.x) skeys[i] = ~0ull;
+  __syncthreads();
+  block_bitonic_sort(skeys, P);
+  uint64_t* out = p.ws.top_keys + (int64_t)b * kTopCap;
+  for (int i = threadIdx.x; i < got; i += blockDim.x) out[i] = skeys[i];
+  if (threadIdx.x == 0) p.ws.top_n[b] = got;
+}
+
 constexpr int kGreedyThreads = 512;
 
+// MODE 0: sorted `keys` (full list).  MODE 1: top-K scheme, first pass -- the sorted prefix (or the full list when top_n = -1);
+// raises need_full when the prefix is exhausted before max_det boxes are kept.  MODE 2: second pass over the full list, only
+// for the images that raised it.
+template <int MODE>
 __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsParams p) {
   extern __shared__ float4 gsm[];
   float4* kept_box = gsm;                                              // [max_det] offset boxes
@@ -430,8 +604,19 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
   __shared__ int ch_out[64];            // output row of each chunk member, -1 when suppressed
   __shared__ int s_kept;
   const int b = blockIdx.x;
-  const int n = min(min(p.ws.cand_count[b], p.ws.cap), kMaxNms);
+  const int n_all = min(min(p.ws.cand_count[b], p.ws.cap), kMaxNms);
+  int n = n_all;
   const uint64_t* keys = p.ws.keys + (int64_t)b * p.ws.cap2;
+  if (MODE == 1) {
+    const int tn = p.ws.top_n[b];
+    if (tn >= 0) {
+      if (p.ws.need_full[b]) return;         // the prefix could not be built: the second pass does this image
+      n = min(tn, n_all);
+      keys = p.ws.top_keys + (int64_t)b * kTopCap;
+    }
+  } else if (MODE == 2) {
+    if (!p.ws.need_full[b]) return;
+  }
   const int div = p.multi_label ? p.nc : 1;                            // key order = anchor * div + class
   const double thr = p.iou;
   if (threadIdx.x == 0) s_kept = 0;
@@ -538,7 +723,10 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsPar
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) p.out_count[b] = s_kept;
+  if (threadIdx.x == 0) {
+    p.out_count[b] = s_kept;
+    if (MODE == 1 && n < n_all && s_kept < p.max_det) p.ws.need_full[b] = 1;   // prefix exhausted: redo on the full list
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -591,6 +779,10 @@ static void nms_layout(int32_t B, int32_t A, int32_t nc, int32_t multi_label, Nm
   const bool can_overflow = multi_label && (int64_t)A * nc > cap;
   ws->hist = can_overflow ? (uint32_t*)take((int64_t)B * kHistBins * 4) : nullptr;
   ws->cutoff = can_overflow ? (int32_t*)take((int64_t)B * 4) : nullptr;
+  ws->top_hist = (uint32_t*)take((int64_t)B * kHistBins * 4);       // adjacent to top_n / need_full: one memset clears all three
+  ws->top_n = (int32_t*)take((int64_t)B * 4);
+  ws->need_full = (int32_t*)take((int64_t)B * 4);
+  ws->top_keys = (uint64_t*)take((int64_t)B * kTopCap * 8);
   ws->cap = (int32_t)cap;
   ws->cap2 = (int32_t)cap2;
   ws->T = T;
@@ -637,8 +829,20 @@ static int nms_launch(yv6_handle* h, NmsParams& p, int32_t B, int32_t A, int32_t
   cudaStream_t s = (cudaStream_t)stream;
   YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.overflow, 0, 4, s));
   YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.cand_count, 0, sizeof(int32_t) * B, s));
-  dim3 grid(p.ws.T, B);
-  nms_select_kernel<<<grid, kNmsTile, 0, s>>>(p);
+  const bool rows_mode = !p.has_obj && p.row_pitch == nc && nc % 4 == 0 && nc <= 256 && (reinterpret_cast<uintptr_t>(p.rows) & 15) == 0;
+  if (rows_mode) {
+    YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.top_hist, 0, (size_t)(reinterpret_cast<char*>(p.ws.top_keys) - reinterpret_cast<char*>(p.ws.top_hist)), s));
+    const size_t smem = sizeof(float) * 8 * kSelRows * (size_t)(nc | 1);
+    dim3 grid((A + 8 * kSelRows - 1) / (8 * kSelRows), B);
+    if (!(h->configured & YV6_CFG_TRAIN2)) {
+      YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSelRows * 257 * 4));
+      h->configured |= YV6_CFG_TRAIN2;
+    }
+    nms_select_rows_kernel<<<grid, 256, smem, s>>>(p);
+  } else {
+    dim3 grid(p.ws.T, B);
+    nms_select_kernel<<<grid, kNmsTile, 0, s>>>(p);
+  }
   if (p.ws.hist != nullptr) {   // A * nc exceeds the key capacity: keep the max_nms best of an overflowing image (nms.py:90-91)
     YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.hist, 0, sizeof(uint32_t) * (size_t)B * kHistBins, s));
     dim3 g8((A + 8 * kOverflowRows - 1) / (8 * kOverflowRows), B);
@@ -647,13 +851,25 @@ static int nms_launch(yv6_handle* h, NmsParams& p, int32_t B, int32_t A, int32_t
     nms_overflow_pass_kernel<true><<<g8, 256, 0, s>>>(p);
   }
   if (!(h->configured & YV6_CFG_NMS)) {
-    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemMax * 8));
-    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 20));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemMax * 8));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemMax * 8));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopCap * 8));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 20));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 20));
+    YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 20));
     h->configured |= YV6_CFG_NMS;
   }
   const size_t sort_smem = (size_t)std::min<int64_t>(p.ws.cap2, kSortSmemMax) * 8;
-  nms_sort_kernel<<<B, 1024, sort_smem, s>>>(p);
-  nms_greedy_kernel<<<B, kGreedyThreads, (size_t)max_det * 20, s>>>(p);
+  const size_t greedy_smem = (size_t)max_det * 20;
+  if (rows_mode) {      // sorted top-K prefix first; the full sort + second greedy pass only touch images whose prefix ran out
+    nms_topk_sort_kernel<<<B, 1024, kTopCap * 8, s>>>(p);
+    nms_greedy_kernel<1><<<B, kGreedyThreads, greedy_smem, s>>>(p);
+    nms_sort_kernel<true><<<B, 1024, sort_smem, s>>>(p);
+    nms_greedy_kernel<2><<<B, kGreedyThreads, greedy_smem, s>>>(p);
+  } else {
+    nms_sort_kernel<false><<<B, 1024, sort_smem, s>>>(p);
+    nms_greedy_kernel<0><<<B, kGreedyThreads, greedy_smem, s>>>(p);
+  }
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }
