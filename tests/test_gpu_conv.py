@@ -31,6 +31,15 @@ CASES = [
     ("3x3_s2_cin32_many_tiles", 8, 160, 160, 32, 64, 3, 2, "relu", False, 1, False, 0, 0, None),
     ("1x1_many_tiles_res", 8, 96, 96, 64, 64, 1, 1, "silu", False, 1, True, 0, 0, None),
     ("3x3_s2_x3_many_tiles", 6, 96, 96, 32, 32, 3, 2, "relu", False, 3, False, 0, 0, None),
+    # pair mode (two M tiles per weight tile, kernel mode 3): even / odd tile counts, N split, residual, channel slices,
+    # several units per CTA, bf16x3 planes
+    ("pair_c128_40", 2, 40, 40, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, dict(pair=1)),
+    ("pair_c128_odd_tiles", 1, 24, 24, 128, 128, 3, 1, "silu", False, 1, False, 0, 0, dict(pair=1)),
+    ("pair_c256_nsplit_res", 2, 40, 40, 256, 256, 3, 1, "relu", False, 1, True, 0, 0, dict(pair=1)),
+    ("pair_c64_cout128_slices", 3, 23, 17, 64, 128, 3, 1, "relu", False, 1, False, 64, 128, dict(pair=1)),
+    ("pair_persistent", 4, 80, 80, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, dict(pair=1, grid=8)),
+    ("pair_x3", 2, 20, 20, 128, 128, 3, 1, "relu", False, 3, True, 0, 0, dict(pair=1)),
+    ("pair_auto_c128_80", 8, 80, 80, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, None),
 ]
 
 

@@ -501,10 +501,9 @@ extern "C" int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int
   const size_t smem = (size_t)4 * H * W * 8 * sizeof(float);
   YV6_REQUIRE(smem <= (size_t)h->max_smem_optin, "sppf_pool: %dx%d plane does not fit in shared memory", H, W);
   PoolParams p{reinterpret_cast<__nv_bfloat16*>(buf), plane_stride, N, H, W, C, c_total, nsplit == 3 ? 3 : 1};
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (!(h->configured & YV6_CFG_POOL)) {
     YV6_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
-    configured = h->max_smem_optin;
+    h->configured |= YV6_CFG_POOL;
   }
   sppf_pool_kernel<<<(unsigned)(N * (C / 8)), 256, smem, (cudaStream_t)stream>>>(p);
   YV6_CHECK_CUDA(cudaGetLastError());

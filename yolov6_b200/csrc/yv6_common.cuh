@@ -24,6 +24,7 @@ void yv6_set_error(const char* fmt, ...);
     if (_e != cudaSuccess) {                                                          \
       yv6_set_error("%s:%d CUDA error %d (%s) in `%s`", __FILE__, __LINE__, (int)_e,  \
                     cudaGetErrorString(_e), #expr);                                   \
+      (void)cudaGetLastError(); /* a non-sticky error must not be blamed on the next call */ \
       return YV6_ERR_CUDA;                                                            \
     }                                                                                 \
   } while (0)

@@ -60,7 +60,10 @@ struct ConvKParams {
   // halo mode (3x3 stride-1, Cin % 64 == 0): one (BH+2)x(BW+2) input box per channel block feeds all
   // nine taps through UMMA descriptors offset into it; B tiles ride their own ring (or stay resident).
   int32_t halo, a_stages, b_stages, b_resident;
-  int32_t a_region_bytes, b_region_bytes;  // smem carve: [A ring][B ring][2 C buffers][barriers]
+  int32_t a_region_bytes, b_region_bytes;  // smem carve: [A ring][B ring][C buffers][bias][barriers]
+  // pair mode (halo tiles, streamed weights): one schedule unit = TWO consecutive M tiles x one N tile; every weight
+  // tile that arrives in shared memory feeds both accumulators, halving the L2 -> SM weight stream per FLOP.
+  int32_t pair, m_tiles, c_region_bytes;
   int32_t bias_smem;                       // bias[0 .. tiles_n*BN) is staged in shared memory by the epilogue warps
   int32_t res_aligned;                     // residual rows are 16-byte aligned (channel offset / pitches % 8 == 0)
   int32_t fast_act;                        // bf16 outputs: SiLU through tanh.approx (rel. error 2^-11 < bf16 ulp)
@@ -114,6 +117,29 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   t.h0 = th * p.BH;
   t.i0 = ti * p.BI;
   t.n0 = nt * p.BN;
+  return t;
+}
+
+// pair mode: unit -> (M tiles 2u, 2u+1 ; N tile).  A missing second tile (odd tile count) is placed on image N:
+// its TMA loads are zero filled and its TMA stores dropped, so it costs time but needs no special case.
+__device__ __forceinline__ TileCoord decode_unit(const ConvKParams& p, int unit, int sub) {
+  TileCoord t;
+  const int nt = unit % p.tiles_n;
+  int m = (unit / p.tiles_n) * 2 + sub;
+  t.n0 = nt * p.BN;
+  if (m >= p.m_tiles) {
+    t.w0 = 0;
+    t.h0 = 0;
+    t.i0 = p.N;
+    return t;
+  }
+  const int tw = m % p.tiles_w;
+  m /= p.tiles_w;
+  const int th = m % p.tiles_h;
+  const int ti = m / p.tiles_h;
+  t.w0 = tw * p.BW;
+  t.h0 = th * p.BH;
+  t.i0 = ti * p.BI;
   return t;
 }
 
@@ -327,7 +353,8 @@ __device__ __forceinline__ void epi_cols32(const ConvKParams& p, const float* sb
 }
 
 // MODE: 0 = one TMA box per (tap, channel block); 1 = halo input tiles, weights streamed through a ring;
-//       2 = halo input tiles, the layer's weights resident in shared memory.  Compile-time so that each
+//       2 = halo input tiles, the layer's weights resident in shared memory; 3 = mode 1 over PAIRS of M tiles
+//       (two halo tiles and two accumulators per weight tile).  Compile-time so that each
 //       variant carries only its own producer / issue loops (instruction-cache footprint, issue-slot count).
 template <int G, int MODE>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
@@ -339,8 +366,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.a_region_bytes;
   uint8_t* sC = sB + (size_t)p.b_region_bytes;
-  float* sBiasBuf = reinterpret_cast<float*>(sC + kCBufCount * kCBufBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kCBufCount * kCBufBytes + kBiasSmemFloats * sizeof(float));
+  float* sBiasBuf = reinterpret_cast<float*>(sC + (size_t)p.c_region_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + (size_t)p.c_region_bytes + kBiasSmemFloats * sizeof(float));
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -355,6 +382,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   constexpr bool HALO = (MODE != 0);
   constexpr bool BRES = (MODE == 2);
+  constexpr bool PAIR = (MODE == 3);
+  constexpr int SUBS = PAIR ? 2 : 1;          // M tiles (accumulators) per schedule unit
   if (threadIdx.x == 0) YV6_TRACE(0);
 
   if (threadIdx.x == 0) {
@@ -393,22 +422,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t pha = 0, phb = 0;
       bool first = true;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+        const TileCoord t = PAIR ? decode_unit(p, tile, 0) : decode_tile(p, tile);
+        const TileCoord t1 = PAIR ? decode_unit(p, tile, 1) : t;
         int slot = 0;
         for (int pi = 0; pi < p.npairs; ++pi) {
           const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
-            mbar_wait(&a_empty[sa], pha ^ 1);
-            if (pi == 0 && cb == 0 && lane == 0) {
-              if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(12);
-              if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(13);
+#pragma unroll
+            for (int sub = 0; sub < SUBS; ++sub) {
+              const TileCoord& ts = sub ? t1 : t;
+              mbar_wait(&a_empty[sa], pha ^ 1);
+              if (pi == 0 && cb == 0 && sub == 0 && lane == 0) {
+                if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(12);
+                if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(13);
+              }
+              if (elect_one()) {
+                mbar_expect_tx(&a_full[sa], (uint32_t)kHaloBytes);
+                tma_load_5d(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, ts.w0 - 1, ts.h0 - 1, ts.i0, pa);
+              }
+              __syncwarp();
+              if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
             }
-            if (elect_one()) {
-              mbar_expect_tx(&a_full[sa], (uint32_t)kHaloBytes);
-              tma_load_5d(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 - 1, t.i0, pa);
-            }
-            __syncwarp();
-            if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
             for (int tap = 0; tap < 9; ++tap, ++slot) {
               if constexpr (BRES) {
                 if (first && elect_one()) {
@@ -492,11 +526,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SUBS * BN);
         int slot = 0;
         uint32_t started = 0;
         for (int pc = 0; pc < pcs; ++pc) {
           mbar_wait(&a_full[sa], pha);
+          if (PAIR) mbar_wait(&a_full[sa + 1], pha);   // a_stages is even in pair mode: both tiles share a ring phase
           tc_fence_after();
           const uint32_t a0 = a_base + (uint32_t)sa * halo_step;
 #pragma unroll
@@ -514,15 +549,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
               umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
               umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+              if (PAIR) {   // the same weight tile against the second halo tile -> second accumulator
+                const uint64_t ad1 = ad + halo_step;
+                const uint32_t d1 = d_tmem + (uint32_t)BN;
+                umma_bf16(d1, ad1, bd, idesc, started);
+                umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
+                umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
+                umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
+              }
               if (!b_resident) umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             started = 1u;
             if (!b_resident && ++sb == b_stages) { sb = 0; phb ^= 1; }
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);
+          if (elect_one()) {
+            umma_commit(&a_empty[sa]);
+            if (PAIR) umma_commit(&a_empty[sa + 1]);
+          }
           __syncwarp();
-          if (++sa == a_stages) { sa = 0; pha ^= 1; }
+          sa += SUBS;
+          if (sa == a_stages) { sa = 0; pha ^= 1; }
         }
         if (elect_one()) umma_commit(&tfull[acc]);
         __syncwarp();
@@ -576,7 +623,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tq = row / p.BW;
     const int bh = tq % p.BH;
     const int bi = tq / p.BH;
-    constexpr int NBUF = kCBufCount / G;          // staging buffers per group (2 when G = 2, 1 when G = 4)
+    constexpr int NBUF = PAIR ? 1 : kCBufCount / G;   // staging buffers per group (2 when G = 2, 1 when G = 4 or in pair mode)
     uint8_t* gC = sC + group * NBUF * kCBufBytes;
     const bool f32 = (p.y_dtype == YV6_DT_F32);
     const float* sbias = nullptr;
@@ -588,7 +635,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     int cbuf = 0;
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += G * gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tfull[group], acc_phase);
+      tc_fence_after();
+      if (tile == (int)blockIdx.x && q == 0 && lane == 0) YV6_TRACE(5);
+#pragma unroll 1
+      for (int sub = 0; sub < SUBS; ++sub) {
+      const TileCoord t = PAIR ? decode_unit(p, tile, sub) : decode_tile(p, tile);
       const int img = t.i0 + bi, ho = t.h0 + bh, wo = t.w0 + bw;
       const bool valid = (row < p.rows) && (img < p.N) && (ho < p.Ho) && (wo < p.Wo);
       const int64_t off = (int64_t)img * p.y_img_stride + (int64_t)ho * p.y_h_stride +
@@ -598,10 +650,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // straight-line path: single output plane, no residual or a 16-byte aligned bf16 one
       const __nv_bfloat16* res_row = (p.res != nullptr && valid) ? p.res + roff : nullptr;
       const bool fast_tile = (p.out_planes == 1) && (p.res == nullptr || (p.res_planes == 1 && p.res_aligned));
-      mbar_wait(&tfull[group], acc_phase);
-      tc_fence_after();
-      if (tile == (int)blockIdx.x && q == 0 && lane == 0) YV6_TRACE(5);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * p.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((group * SUBS + sub) * p.BN);
       if (p.tma_store == 2) {
         // ---- per-warp stores: the 32 rows of this warp form a box of the output, so each warp stages
         //      its rows (4 KB, swizzled) and issues its own TMA store -- no block-level barrier at all.
@@ -746,6 +795,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (valid && ncol > 0) store_chunk(p, off, n, ncol, v);
         }
       }
+      }  // sub
       tc_fence_before();
       mbar_arrive(&tempty[group]);
       if (q == 0 && lane == 0) {
@@ -895,9 +945,25 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     }
   }
   const long m_tiles = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
+  // Pair mode: halo tiles whose weights cannot stay resident (Cin >= 128 or Cout >= 128) are bound by the L2 -> SM weight
+  // stream (16-32 KB of weights per 23 KB halo tile and tap; measured ~100 clk per M128xN128xK16 MMA against the 64 clk
+  // floor).  Two M tiles per weight tile halve it.  BN is 128 (four accumulators = two units in flight in TMEM), so it
+  // needs Cout % 128 == 0 or Cout <= 128, and enough tile pairs to fill the SMs about as well as single tiles would.
+  k.pair = 0;
+  if (k.halo && d->force_pair >= 0 && d->force_bn == 0 && d->force_stages == 0 && (d->Cout % 128 == 0 || (d->Cout <= 128 && d->Cout % 16 == 0)) &&
+      (d->Cin >= 128 || d->Cout >= 128)) {
+    const int bn = std::min(128, d->Cout);
+    const long tn = ceil_div(d->Cout, bn);
+    const long units = ((m_tiles + 1) / 2) * tn;
+    const long waves_pair = ceil_div((int)units, h->num_sms), waves_single = ceil_div((int)(m_tiles * tn), h->num_sms);
+    // a pair costs ~1.4 single tiles (measured ratio of the L2-bound and the MMA-bound tile time)
+    if (d->force_pair > 0 || waves_pair * 14 <= waves_single * 10) k.pair = 1;
+  }
   // N tiling: BN <= 256, multiple of 16; pick the split whose wave count x tile cost is smallest
   // (a 448-tile layer on 148 SMs runs 4 waves at BN=256 but 7 half-cost waves at BN=128).
-  if (d->force_bn > 0) {
+  if (k.pair) {
+    k.BN = std::min(128, d->Cout);
+  } else if (d->force_bn > 0) {
     YV6_REQUIRE(d->force_bn % 16 == 0 && d->force_bn <= 256, "conv: force_bn must be a multiple of 16 <= 256");
     k.BN = d->force_bn;
   } else {
@@ -927,15 +993,25 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   k.tiles_w = ceil_div(k.Wo, k.BW);
   k.tiles_h = ceil_div(k.Ho, k.BH);
   k.tiles_i = ceil_div(d->N, k.BI);
-  const long nt = (long)k.tiles_w * k.tiles_h * k.tiles_i * k.tiles_n;
-  YV6_REQUIRE(nt < (1l << 30), "conv: too many tiles");
-  k.num_tiles = (int)nt;
+  YV6_REQUIRE(m_tiles * k.tiles_n < (1l << 30), "conv: too many tiles");
+  k.m_tiles = (int)m_tiles;
+  // schedule units: tiles, or (pair of M tiles) x N tile in pair mode
+  k.num_tiles = k.pair ? (int)(((m_tiles + 1) / 2) * k.tiles_n) : (int)(m_tiles * k.tiles_n);
 
   // smem ring(s)
   k.a_stage_bytes = kTileRows * k.kb_bytes;
   k.b_stage_bytes = ((k.BN * k.kb_bytes + 1023) / 1024) * 1024;
-  const int budget = h->max_smem_optin - 1024 - 1024 - kCBufCount * kCBufBytes - kBiasSmemFloats * (int)sizeof(float);
-  if (k.halo) {
+  k.c_region_bytes = (k.pair ? 2 : kCBufCount) * kCBufBytes;   // pair mode: one staging buffer per epilogue group
+  const int budget = h->max_smem_optin - 1024 - 1024 - k.c_region_bytes - kBiasSmemFloats * (int)sizeof(float);
+  if (k.pair) {
+    k.b_resident = 0;
+    k.a_stages = 4;                                            // two units' worth of halo tiles (even: a pair never wraps)
+    k.b_stages = std::min(kMaxBStages, (budget - k.a_stages * kHaloStageBytes) / k.b_stage_bytes);
+    YV6_REQUIRE(k.b_stages >= 2, "conv(pair): not enough shared memory");
+    k.stages = k.b_stages;
+    k.a_region_bytes = k.a_stages * kHaloStageBytes;
+    k.b_region_bytes = k.b_stages * k.b_stage_bytes;
+  } else if (k.halo) {
     const int b_tiles = k.npairs * k.cin_blocks * 9;   // B tiles one output tile consumes
     k.b_resident = (k.tiles_n == 1 && b_tiles <= kMaxBStages && d->force_stages == 0 &&
                     (long)b_tiles * k.b_stage_bytes + 3 * kHaloStageBytes <= budget) ? 1 : 0;
@@ -961,14 +1037,15 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     k.b_region_bytes = stages * k.b_stage_bytes;
   }
   k.trace = reinterpret_cast<unsigned long long*>(d->trace);
-  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + kBiasSmemFloats * sizeof(float) + 1024 + 1024;
+  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + k.c_region_bytes + kBiasSmemFloats * sizeof(float) + 1024 + 1024;
 
   // four groups only pay off when the tile's mainloop is shorter than its epilogue (1x1 / small-K layers)
   const int kblocks_per_tile = k.npairs * k.taps * k.cin_blocks;
   k.groups = (4 * k.BN <= 512 && kblocks_per_tile <= 8 && d->force_groups != 2) ? 4 : 2;
   if (d->force_groups == 4 && 4 * k.BN <= 512) k.groups = 4;
+  if (k.pair) k.groups = 2;                // two groups, each draining the two accumulators of its unit
   int cols = 32;
-  while (cols < k.groups * k.BN) cols *= 2;
+  while (cols < k.groups * (k.pair ? 2 : 1) * k.BN) cols *= 2;
   k.tmem_cols = cols;
 
   k.act = d->act;
@@ -1016,7 +1093,7 @@ extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out
   out8[6] = plan.grid;
   out8[7] = plan.k.num_tiles;
   out8[8] = plan.k.halo;
-  out8[9] = plan.k.halo ? plan.k.a_stages * 100 + plan.k.b_resident : 0;
+  out8[9] = plan.k.halo ? plan.k.a_stages * 100 + plan.k.b_resident + 2 * plan.k.pair : 0;
   return YV6_OK;
 }
 
@@ -1103,16 +1180,16 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
   }
 
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
-  static const KernelFn kernels[2][3] = {
-      {conv_igemm_kernel<2, 0>, conv_igemm_kernel<2, 1>, conv_igemm_kernel<2, 2>},
-      {conv_igemm_kernel<4, 0>, conv_igemm_kernel<4, 1>, conv_igemm_kernel<4, 2>}};
+  static const KernelFn kernels[2][4] = {
+      {conv_igemm_kernel<2, 0>, conv_igemm_kernel<2, 1>, conv_igemm_kernel<2, 2>, conv_igemm_kernel<2, 3>},
+      {conv_igemm_kernel<4, 0>, conv_igemm_kernel<4, 1>, conv_igemm_kernel<4, 2>, conv_igemm_kernel<2, 3>}};
   if (!(h->configured & YV6_CFG_CONV)) {
     for (int g = 0; g < 2; ++g)
-      for (int m = 0; m < 3; ++m)
+      for (int m = 0; m < 4; ++m)
         YV6_CHECK_CUDA(cudaFuncSetAttribute(kernels[g][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
     h->configured |= YV6_CFG_CONV;
   }
-  const int mode = k.halo ? (k.b_resident ? 2 : 1) : 0;
+  const int mode = k.pair ? 3 : k.halo ? (k.b_resident ? 2 : 1) : 0;
   kernels[k.groups == 4 ? 1 : 0][mode]<<<plan.grid, 64 + 128 * k.groups, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;

@@ -19,7 +19,7 @@ struct yv6_handle {
   unsigned configured;             // YV6_CFG_* bits: cudaFuncSetAttribute is per device, so the flags live in the handle
 };
 
-enum { YV6_CFG_CONV = 1u, YV6_CFG_WGRAD = 2u, YV6_CFG_NMS = 4u, YV6_CFG_BN = 8u, YV6_CFG_TRAIN2 = 16u };
+enum { YV6_CFG_CONV = 1u, YV6_CFG_WGRAD = 2u, YV6_CFG_NMS = 4u, YV6_CFG_BN = 8u, YV6_CFG_TRAIN2 = 16u, YV6_CFG_POOL = 32u, YV6_CFG_SELROWS = 64u };
 
 // Every entry point runs on the handle's device whatever the caller's current device is, and leaves the
 // caller's current device untouched (several handles / GPUs in one process, nn.DataParallel-style callers).

@@ -829,14 +829,17 @@ static int nms_launch(yv6_handle* h, NmsParams& p, int32_t B, int32_t A, int32_t
   cudaStream_t s = (cudaStream_t)stream;
   YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.overflow, 0, 4, s));
   YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.cand_count, 0, sizeof(int32_t) * B, s));
-  const bool rows_mode = !p.has_obj && p.row_pitch == nc && nc % 4 == 0 && nc <= 256 && (reinterpret_cast<uintptr_t>(p.rows) & 15) == 0;
+  // the row tile of the lane-per-row kernel must fit the CTA's opt-in shared memory (nc <= 220 on B200; wider heads take the generic kernel)
+  const size_t sel_smem_bytes = sizeof(float) * 8 * kSelRows * (size_t)(nc | 1);
+  const bool rows_mode = !p.has_obj && p.row_pitch == nc && nc % 4 == 0 && sel_smem_bytes <= (size_t)h->max_smem_optin &&
+                         (reinterpret_cast<uintptr_t>(p.rows) & 15) == 0;
   if (rows_mode) {
     YV6_CHECK_CUDA(cudaMemsetAsync(p.ws.top_hist, 0, (size_t)(reinterpret_cast<char*>(p.ws.top_keys) - reinterpret_cast<char*>(p.ws.top_hist)), s));
-    const size_t smem = sizeof(float) * 8 * kSelRows * (size_t)(nc | 1);
+    const size_t smem = sel_smem_bytes;
     dim3 grid((A + 8 * kSelRows - 1) / (8 * kSelRows), B);
-    if (!(h->configured & YV6_CFG_TRAIN2)) {
-      YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSelRows * 257 * 4));
-      h->configured |= YV6_CFG_TRAIN2;
+    if (!(h->configured & YV6_CFG_SELROWS)) {
+      YV6_CHECK_CUDA(cudaFuncSetAttribute(nms_select_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+      h->configured |= YV6_CFG_SELROWS;
     }
     nms_select_rows_kernel<<<grid, 256, smem, s>>>(p);
   } else {
