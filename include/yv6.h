@@ -101,8 +101,10 @@ typedef struct yv6_conv_desc {
    * 3x2 kernel with stride (2, 1), pad_w = 1, out_w = W/2: the A rows become contiguous 2*Cin-channel pixels instead of
    * every other Cin-channel pixel (see yolov6_b200/engine.py). */
   int32_t stride_w;
-  int32_t force_pair;       /* pair mode of the halo mainloop (two M tiles per weight tile): 0 auto, 1 force on (if eligible), -1 off;
-                             * occupies what used to be tail padding, so the struct size is unchanged */
+  int32_t force_pair;       /* CTA pairs (clusters of two CTAs, tcgen05 cta_group::2: one M256 instruction over two M tiles, each CTA
+                             * staging half of the weight tile): 0 = auto (3x3 stride-1 layers over >= 128 input channels),
+                             * 1 = on whenever the layer has >= 2 M tiles, -1 = off.
+                             * Occupies what used to be tail padding: the struct size is unchanged. */
 } yv6_conv_desc;
 
 int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);

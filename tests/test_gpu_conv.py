@@ -31,15 +31,16 @@ CASES = [
     ("3x3_s2_cin32_many_tiles", 8, 160, 160, 32, 64, 3, 2, "relu", False, 1, False, 0, 0, None),
     ("1x1_many_tiles_res", 8, 96, 96, 64, 64, 1, 1, "silu", False, 1, True, 0, 0, None),
     ("3x3_s2_x3_many_tiles", 6, 96, 96, 32, 32, 3, 2, "relu", False, 3, False, 0, 0, None),
-    # pair mode (two M tiles per weight tile, kernel mode 3): even / odd tile counts, N split, residual, channel slices,
-    # several units per CTA, bf16x3 planes
-    ("pair_c128_40", 2, 40, 40, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, dict(pair=1)),
-    ("pair_c128_odd_tiles", 1, 24, 24, 128, 128, 3, 1, "silu", False, 1, False, 0, 0, dict(pair=1)),
-    ("pair_c256_nsplit_res", 2, 40, 40, 256, 256, 3, 1, "relu", False, 1, True, 0, 0, dict(pair=1)),
-    ("pair_c64_cout128_slices", 3, 23, 17, 64, 128, 3, 1, "relu", False, 1, False, 64, 128, dict(pair=1)),
-    ("pair_persistent", 4, 80, 80, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, dict(pair=1, grid=8)),
-    ("pair_x3", 2, 20, 20, 128, 128, 3, 1, "relu", False, 3, True, 0, 0, dict(pair=1)),
-    ("pair_auto_c128_80", 8, 80, 80, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, None),
+    # CTA-pair specifics (cta_group::2): odd tile counts (the missing second tile of the last unit), N split + residual,
+    # channel slices, several units per cluster, bf16x3 planes, a full-size layer
+    ("pair_c128_odd_tiles", 1, 24, 24, 128, 128, 3, 1, "silu", False, 1, False, 0, 0, None),
+    ("pair_c256_nsplit_res", 2, 40, 40, 512, 512, 3, 1, "relu", False, 1, True, 0, 0, None),
+    ("pair_c64_cout128_slices", 3, 23, 17, 64, 128, 3, 1, "relu", False, 1, False, 64, 128, None),
+    ("pair_persistent", 4, 80, 80, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, dict(grid=8)),
+    ("pair_x3", 2, 20, 20, 128, 128, 3, 1, "relu", False, 3, True, 0, 0, None),
+    ("pair_c128_80_bs8", 8, 80, 80, 128, 128, 3, 1, "relu", False, 1, False, 0, 0, None),
+    ("pair_1x1_cout80_f32_many", 8, 80, 80, 64, 80, 1, 1, "sigmoid", True, 1, False, 0, 0, None),
+    ("pair_s2_c128_256", 4, 80, 80, 128, 256, 3, 2, "relu", False, 1, False, 0, 0, None),
 ]
 
 
@@ -53,10 +54,14 @@ def ref_conv(x, w, b, stride, act, res, alpha):
     return y
 
 
+@pytest.mark.parametrize("pair", [1, -1], ids=["cta_pair", "single_cta"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_conv_fwd(case):
+def test_conv_fwd(case, pair):
+    """Every case runs through both kernel families: CTA pairs (tcgen05 cta_group::2, forced on here; auto mode takes them
+    for the 3x3 stride-1 layers over >= 128 channels) and the single-CTA variants."""
     from yolov6_b200 import ops
     name, N, H, W, Cin, Cout, k, stride, act, out_f32, nsplit, use_res, x_extra, y_extra, force = case
+    force = dict(force or {}, pair=pair)
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
     Ct = Cin + x_extra

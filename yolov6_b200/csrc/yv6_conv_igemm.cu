@@ -60,10 +60,13 @@ struct ConvKParams {
   // halo mode (3x3 stride-1, Cin % 64 == 0): one (BH+2)x(BW+2) input box per channel block feeds all
   // nine taps through UMMA descriptors offset into it; B tiles ride their own ring (or stay resident).
   int32_t halo, a_stages, b_stages, b_resident;
-  int32_t a_region_bytes, b_region_bytes;  // smem carve: [A ring][B ring][C buffers][bias][barriers]
-  // pair mode (halo tiles, streamed weights): one schedule unit = TWO consecutive M tiles x one N tile; every weight
-  // tile that arrives in shared memory feeds both accumulators, halving the L2 -> SM weight stream per FLOP.
-  int32_t pair, m_tiles, c_region_bytes;
+  int32_t a_region_bytes, b_region_bytes;  // smem carve: [A ring][B ring][2 C buffers][barriers]
+  // CTA-pair mode (cluster of two CTAs, tcgen05 cta_group::2): one schedule unit = two consecutive M tiles (one per CTA)
+  // x one N tile; every CTA stages its own input tile and HALF of the weight tile (b_rows = BN / 2 rows), one
+  // M256 x BN x K16 instruction issued by the even CTA feeds both accumulators.  Halves the shared-memory traffic of
+  // the weight operand per FLOP, which is what bounds the single-CTA kernel (A + B operand reads plus the TMA fills
+  // exceed 128 B/clk per SM at every BN).
+  int32_t cpair, m_tiles, b_rows;
   int32_t bias_smem;                       // bias[0 .. tiles_n*BN) is staged in shared memory by the epilogue warps
   int32_t res_aligned;                     // residual rows are 16-byte aligned (channel offset / pitches % 8 == 0)
   int32_t fast_act;                        // bf16 outputs: SiLU through tanh.approx (rel. error 2^-11 < bf16 ulp)
@@ -120,12 +123,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   return t;
 }
 
-// pair mode: unit -> (M tiles 2u, 2u+1 ; N tile).  A missing second tile (odd tile count) is placed on image N:
-// its TMA loads are zero filled and its TMA stores dropped, so it costs time but needs no special case.
-__device__ __forceinline__ TileCoord decode_unit(const ConvKParams& p, int unit, int sub) {
+// CTA-pair mode: unit -> (M tile 2u + rank, N tile).  A missing second tile (odd tile count) is placed on image N: its TMA
+// loads are zero filled and its TMA stores dropped, so it needs no special case anywhere.
+__device__ __forceinline__ TileCoord decode_unit(const ConvKParams& p, int unit, int rank) {
   TileCoord t;
   const int nt = unit % p.tiles_n;
-  int m = (unit / p.tiles_n) * 2 + sub;
+  int m = (unit / p.tiles_n) * 2 + rank;
   t.n0 = nt * p.BN;
   if (m >= p.m_tiles) {
     t.w0 = 0;
@@ -353,10 +356,10 @@ __device__ __forceinline__ void epi_cols32(const ConvKParams& p, const float* sb
 }
 
 // MODE: 0 = one TMA box per (tap, channel block); 1 = halo input tiles, weights streamed through a ring;
-//       2 = halo input tiles, the layer's weights resident in shared memory; 3 = mode 1 over PAIRS of M tiles
-//       (two halo tiles and two accumulators per weight tile).  Compile-time so that each
+//       2 = halo input tiles, the layer's weights resident in shared memory.  Compile-time so that each
 //       variant carries only its own producer / issue loops (instruction-cache footprint, issue-slot count).
-template <int G, int MODE>
+//   CP: CTA-pair variant (launched as clusters of two CTAs): see ConvKParams::cpair.
+template <int G, int MODE, bool CP>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
@@ -366,8 +369,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.a_region_bytes;
   uint8_t* sC = sB + (size_t)p.b_region_bytes;
-  float* sBiasBuf = reinterpret_cast<float*>(sC + (size_t)p.c_region_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + (size_t)p.c_region_bytes + kBiasSmemFloats * sizeof(float));
+  float* sBiasBuf = reinterpret_cast<float*>(sC + kCBufCount * kCBufBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kCBufCount * kCBufBytes + kBiasSmemFloats * sizeof(float));
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -382,18 +385,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   constexpr bool HALO = (MODE != 0);
   constexpr bool BRES = (MODE == 2);
-  constexpr bool PAIR = (MODE == 3);
-  constexpr int SUBS = PAIR ? 2 : 1;          // M tiles (accumulators) per schedule unit
+  // schedule: CTA (or CTA pair) takes units unit0, unit0 + ustep, ...; in pair mode this CTA computes M tile `rank` of a unit
+  const int rank = CP ? (int)cluster_ctarank() : 0;
+  const int unit0 = CP ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = CP ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool leader = (rank == 0);
   if (threadIdx.x == 0) YV6_TRACE(0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+    if (!HALO) {   // generic ring (<= kMaxStages); the halo variants have their own rings below, with up to kMaxBStages stages
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
     }
     for (int a = 0; a < G; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], CP ? 8 : 128);    // pair mode: one arrival per epilogue warp of either CTA, on the leader's barrier
     }
     if (HALO) {
       for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -404,9 +412,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
     if (p.tma_store) tma_prefetch_desc(&tmC);
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (CP) tmem_alloc_pair(tmem_ptr, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CP) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) YV6_TRACE(1);
@@ -421,40 +433,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       bool first = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = PAIR ? decode_unit(p, tile, 0) : decode_tile(p, tile);
-        const TileCoord t1 = PAIR ? decode_unit(p, tile, 1) : t;
+      // pair mode: both CTAs fill their own rings; all completion bytes land on the LEADER's full barriers, which the
+      // leader's producer arms with the byte count of both CTAs (a peer's bytes may arrive before the arming: the
+      // transaction count is signed, the phase cannot complete before the leader's own arrival)
+      const uint32_t a_tx = (uint32_t)kHaloBytes * (CP ? 2u : 1u), b_tx = (uint32_t)(p.b_rows * 128) * (CP ? 2u : 1u);
+      const int nrow0 = rank * p.b_rows;                      // this CTA's half of the weight tile's rows
+      for (int tile = unit0; tile < p.num_tiles; tile += ustep) {
+        const TileCoord t = CP ? decode_unit(p, tile, rank) : decode_tile(p, tile);
         int slot = 0;
         for (int pi = 0; pi < p.npairs; ++pi) {
           const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
-#pragma unroll
-            for (int sub = 0; sub < SUBS; ++sub) {
-              const TileCoord& ts = sub ? t1 : t;
-              mbar_wait(&a_empty[sa], pha ^ 1);
-              if (pi == 0 && cb == 0 && sub == 0 && lane == 0) {
-                if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(12);
-                if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(13);
-              }
-              if (elect_one()) {
-                mbar_expect_tx(&a_full[sa], (uint32_t)kHaloBytes);
-                tma_load_5d(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, ts.w0 - 1, ts.h0 - 1, ts.i0, pa);
-              }
-              __syncwarp();
-              if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+            mbar_wait(&a_empty[sa], pha ^ 1);
+            if (pi == 0 && cb == 0 && lane == 0) {
+              if (tile == unit0 + 4 * ustep) YV6_TRACE(12);
+              if (tile == unit0 + 8 * ustep) YV6_TRACE(13);
             }
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&a_full[sa], a_tx);
+              if (CP) tma_load_5d_pair(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 - 1, t.i0, pa);
+              else tma_load_5d(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 - 1, t.i0, pa);
+            }
+            __syncwarp();
+            if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
             for (int tap = 0; tap < 9; ++tap, ++slot) {
               if constexpr (BRES) {
                 if (first && elect_one()) {
-                  mbar_expect_tx(&b_full[slot], (uint32_t)(p.BN * 128));
-                  tma_load_3d(sB + (size_t)slot * p.b_stage_bytes, &tmB, &b_full[slot], tap * p.Cin + cb * 64, t.n0, pb);
+                  if (leader) mbar_expect_tx(&b_full[slot], b_tx);
+                  if (CP) tma_load_3d_pair(sB + (size_t)slot * p.b_stage_bytes, &tmB, &b_full[slot], tap * p.Cin + cb * 64, t.n0 + nrow0, pb);
+                  else tma_load_3d(sB + (size_t)slot * p.b_stage_bytes, &tmB, &b_full[slot], tap * p.Cin + cb * 64, t.n0, pb);
                 }
                 __syncwarp();
               } else {
                 mbar_wait(&b_empty[sb], phb ^ 1);
                 if (elect_one()) {
-                  mbar_expect_tx(&b_full[sb], (uint32_t)(p.BN * 128));
-                  tma_load_3d(sB + (size_t)sb * p.b_stage_bytes, &tmB, &b_full[sb], tap * p.Cin + cb * 64, t.n0, pb);
+                  if (leader) mbar_expect_tx(&b_full[sb], b_tx);
+                  if (CP) tma_load_3d_pair(sB + (size_t)sb * p.b_stage_bytes, &tmB, &b_full[sb], tap * p.Cin + cb * 64, t.n0 + nrow0, pb);
+                  else tma_load_3d(sB + (size_t)sb * p.b_stage_bytes, &tmB, &b_full[sb], tap * p.Cin + cb * 64, t.n0, pb);
                 }
                 __syncwarp();
                 if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
@@ -467,9 +482,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx = (uint32_t)(p.rows * p.kb_bytes + p.BN * p.kb_bytes);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    const uint32_t tx = (uint32_t)(p.rows * p.kb_bytes + p.b_rows * p.kb_bytes) * (CP ? 2u : 1u);
+    const int nrow0 = rank * p.b_rows;
+    for (int tile = unit0; tile < p.num_tiles; tile += ustep) {
+      const TileCoord t = CP ? decode_unit(p, tile, rank) : decode_tile(p, tile);
       for (int pi = 0; pi < p.npairs; ++pi) {
         const int pa = kPairA[6 - p.npairs + pi], pb = kPairB[6 - p.npairs + pi];
         for (int tap = 0; tap < p.taps; ++tap) {
@@ -479,12 +495,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&full[stage], tx);
-              tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], cb * p.kb_elems, cx, cy,
-                          t.i0, pa);
-              tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage],
-                          tap * p.Cin + cb * p.kb_elems, t.n0, pb);
-              if (tile == (int)blockIdx.x && pi == 0 && tap == 0 && cb == 0) YV6_TRACE(2);
+              if (leader) mbar_expect_tx(&full[stage], tx);
+              if (CP) {
+                tma_load_5d_pair(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], cb * p.kb_elems, cx, cy, t.i0, pa);
+                tma_load_3d_pair(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage], tap * p.Cin + cb * p.kb_elems,
+                                 t.n0 + nrow0, pb);
+              } else {
+                tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &full[stage], cb * p.kb_elems, cx, cy,
+                            t.i0, pa);
+                tma_load_3d(sB + (size_t)stage * p.b_stage_bytes, &tmB, &full[stage],
+                            tap * p.Cin + cb * p.kb_elems, t.n0, pb);
+              }
+              if (tile == unit0 && pi == 0 && tap == 0 && cb == 0) YV6_TRACE(2);
             }
             __syncwarp();
             if (++stage == p.stages) {
@@ -496,13 +518,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && leader) {
     // ================================ MMA issuer ================================
     // Warp-convergent loop; the elected lane issues tcgen05.mma / tcgen05.commit.  Descriptors are
     // a constant high word plus (smem address >> 4), advanced by 2 (= 32 bytes) per K=16 step.
-    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.BN);
+    // Pair mode: the leader CTA issues M256 instructions over both CTAs' operands (same shared-memory offsets in
+    // both) and its commits arrive on the barriers of both CTAs.
+    const uint32_t idesc = umma_idesc_bf16(CP ? 256u : 128u, (uint32_t)p.BN);
     const uint64_t desc_const = umma_smem_desc(0, (uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
-    const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
+    const uint32_t a_base = (smem_u32(sA) & 0x3ffffu) >> 4, b_base = (smem_u32(sB) & 0x3ffffu) >> 4;
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accumulate) {
+      if (CP) umma_bf16_pair(d, ad, bd, idesc, accumulate);
+      else umma_bf16(d, ad, bd, idesc, accumulate);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (CP) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)p.b_stage_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
@@ -523,15 +555,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       bool first = true;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += ustep) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SUBS * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         int slot = 0;
         uint32_t started = 0;
         for (int pc = 0; pc < pcs; ++pc) {
           mbar_wait(&a_full[sa], pha);
-          if (PAIR) mbar_wait(&a_full[sa + 1], pha);   // a_stages is even in pair mode: both tiles share a ring phase
           tc_fence_after();
           const uint32_t a0 = a_base + (uint32_t)sa * halo_step;
 #pragma unroll
@@ -545,61 +576,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t ad = desc_a | (uint64_t)(a0 + (uint32_t)((tap / 3) * kHaloW + (tap % 3)) * 8u);
             const uint64_t bd = desc_b | (uint64_t)(b_base + (uint32_t)bs * b_step);
             if (elect_one()) {
-              umma_bf16(d_tmem, ad, bd, idesc, started);
-              umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-              umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-              umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-              if (PAIR) {   // the same weight tile against the second halo tile -> second accumulator
-                const uint64_t ad1 = ad + halo_step;
-                const uint32_t d1 = d_tmem + (uint32_t)BN;
-                umma_bf16(d1, ad1, bd, idesc, started);
-                umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
-                umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
-                umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
-              }
-              if (!b_resident) umma_commit(&b_empty[sb]);
+              mma(d_tmem, ad, bd, started);
+              mma(d_tmem, ad + 2, bd + 2, 1u);
+              mma(d_tmem, ad + 4, bd + 4, 1u);
+              mma(d_tmem, ad + 6, bd + 6, 1u);
+              if (!b_resident) commit(&b_empty[sb]);
             }
             __syncwarp();
             started = 1u;
             if (!b_resident && ++sb == b_stages) { sb = 0; phb ^= 1; }
           }
-          if (elect_one()) {
-            umma_commit(&a_empty[sa]);
-            if (PAIR) umma_commit(&a_empty[sa + 1]);
-          }
+          if (elect_one()) commit(&a_empty[sa]);
           __syncwarp();
-          sa += SUBS;
-          if (sa == a_stages) { sa = 0; pha ^= 1; }
+          if (++sa == a_stages) { sa = 0; pha ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull[acc]);
+        if (elect_one()) commit(&tfull[acc]);
         __syncwarp();
         if (lane == 0) {
-          if (tile == (int)blockIdx.x) YV6_TRACE(4);
-          if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(14);
-          if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(15);
+          if (tile == unit0) YV6_TRACE(4);
+          if (tile == unit0 + 4 * ustep) YV6_TRACE(14);
+          if (tile == unit0 + 8 * ustep) YV6_TRACE(15);
         }
         first = false;
         if (++acc == G) { acc = 0; acc_phase ^= 1; }
       }
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += ustep) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (kb == 0 && tile == (int)blockIdx.x && lane == 0) YV6_TRACE(3);
+        if (kb == 0 && tile == unit0 && lane == 0) YV6_TRACE(3);
         const uint64_t ad = desc_const | (uint64_t)(a_base + (uint32_t)stage * a_step);
         const uint64_t bd = desc_const | (uint64_t)(b_base + (uint32_t)stage * b_step);
         if (elect_one()) {
-          umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(kb != 0));
-          if (ksteps > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          mma(d_tmem, ad, bd, (uint32_t)(kb != 0));
+          if (ksteps > 1) mma(d_tmem, ad + 2, bd + 2, 1u);
           if (ksteps > 2) {
-            umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-            umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            mma(d_tmem, ad + 4, bd + 4, 1u);
+            mma(d_tmem, ad + 6, bd + 6, 1u);
           }
-          umma_commit(&empty[stage]);
+          commit(&empty[stage]);
         }
         __syncwarp();
         if (++stage == nstages) {
@@ -607,12 +626,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tfull[acc]);
+      if (elect_one()) commit(&tfull[acc]);
       __syncwarp();
-      if (tile == (int)blockIdx.x && lane == 0) YV6_TRACE(4);
+      if (tile == unit0 && lane == 0) YV6_TRACE(4);
       if (++acc == G) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ================================ epilogue ================================
     // Two groups of four warps; group g owns TMEM accumulator g, i.e. every second tile of this CTA, so
     // an epilogue may take up to two mainloop times before it stalls the MMA warp.
@@ -623,7 +642,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tq = row / p.BW;
     const int bh = tq % p.BH;
     const int bi = tq / p.BH;
-    constexpr int NBUF = PAIR ? 1 : kCBufCount / G;   // staging buffers per group (2 when G = 2, 1 when G = 4 or in pair mode)
+    constexpr int NBUF = kCBufCount / G;          // staging buffers per group (2 when G = 2, 1 when G = 4)
     uint8_t* gC = sC + group * NBUF * kCBufBytes;
     const bool f32 = (p.y_dtype == YV6_DT_F32);
     const float* sbias = nullptr;
@@ -634,13 +653,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     uint32_t acc_phase = 0;
     int cbuf = 0;
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += G * gridDim.x) {
-      mbar_wait(&tfull[group], acc_phase);
-      tc_fence_after();
-      if (tile == (int)blockIdx.x && q == 0 && lane == 0) YV6_TRACE(5);
-#pragma unroll 1
-      for (int sub = 0; sub < SUBS; ++sub) {
-      const TileCoord t = PAIR ? decode_unit(p, tile, sub) : decode_tile(p, tile);
+    for (int tile = unit0 + group * ustep; tile < p.num_tiles; tile += G * ustep) {
+      const TileCoord t = CP ? decode_unit(p, tile, rank) : decode_tile(p, tile);
       const int img = t.i0 + bi, ho = t.h0 + bh, wo = t.w0 + bw;
       const bool valid = (row < p.rows) && (img < p.N) && (ho < p.Ho) && (wo < p.Wo);
       const int64_t off = (int64_t)img * p.y_img_stride + (int64_t)ho * p.y_h_stride +
@@ -650,7 +664,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // straight-line path: single output plane, no residual or a 16-byte aligned bf16 one
       const __nv_bfloat16* res_row = (p.res != nullptr && valid) ? p.res + roff : nullptr;
       const bool fast_tile = (p.out_planes == 1) && (p.res == nullptr || (p.res_planes == 1 && p.res_aligned));
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((group * SUBS + sub) * p.BN);
+      mbar_wait(&tfull[group], acc_phase);
+      tc_fence_after();
+      if (tile == unit0 && q == 0 && lane == 0) YV6_TRACE(5);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * p.BN);
       if (p.tma_store == 2) {
         // ---- per-warp stores: the 32 rows of this warp form a box of the output, so each warp stages
         //      its rows (4 KB, swizzled) and issues its own TMA store -- no block-level barrier at all.
@@ -795,13 +812,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (valid && ncol > 0) store_chunk(p, off, n, ncol, v);
         }
       }
-      }  // sub
       tc_fence_before();
-      mbar_arrive(&tempty[group]);
+      if (CP) {     // the accumulator of BOTH CTAs is free again once every epilogue warp of the pair has read its lanes
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty[group]);
+      } else {
+        mbar_arrive(&tempty[group]);
+      }
       if (q == 0 && lane == 0) {
-        if (tile == (int)blockIdx.x) YV6_TRACE(6);
-        if (tile == (int)(blockIdx.x + 4 * gridDim.x)) YV6_TRACE(9);
-        if (tile == (int)(blockIdx.x + 8 * gridDim.x)) YV6_TRACE(10);
+        if (tile == unit0) YV6_TRACE(6);
+        if (tile == unit0 + 4 * ustep) YV6_TRACE(9);
+        if (tile == unit0 + 8 * ustep) YV6_TRACE(10);
       }
       acc_phase ^= 1;
     }
@@ -810,10 +831,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CP) cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer can still signal it or issue into it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (CP) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     if (lane == 0) YV6_TRACE(8);
   }
 }
@@ -945,25 +968,9 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     }
   }
   const long m_tiles = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
-  // Pair mode: halo tiles whose weights cannot stay resident (Cin >= 128 or Cout >= 128) are bound by the L2 -> SM weight
-  // stream (16-32 KB of weights per 23 KB halo tile and tap; measured ~100 clk per M128xN128xK16 MMA against the 64 clk
-  // floor).  Two M tiles per weight tile halve it.  BN is 128 (four accumulators = two units in flight in TMEM), so it
-  // needs Cout % 128 == 0 or Cout <= 128, and enough tile pairs to fill the SMs about as well as single tiles would.
-  k.pair = 0;
-  if (k.halo && d->force_pair >= 0 && d->force_bn == 0 && d->force_stages == 0 && (d->Cout % 128 == 0 || (d->Cout <= 128 && d->Cout % 16 == 0)) &&
-      (d->Cin >= 128 || d->Cout >= 128)) {
-    const int bn = std::min(128, d->Cout);
-    const long tn = ceil_div(d->Cout, bn);
-    const long units = ((m_tiles + 1) / 2) * tn;
-    const long waves_pair = ceil_div((int)units, h->num_sms), waves_single = ceil_div((int)(m_tiles * tn), h->num_sms);
-    // a pair costs ~1.4 single tiles (measured ratio of the L2-bound and the MMA-bound tile time)
-    if (d->force_pair > 0 || waves_pair * 14 <= waves_single * 10) k.pair = 1;
-  }
   // N tiling: BN <= 256, multiple of 16; pick the split whose wave count x tile cost is smallest
   // (a 448-tile layer on 148 SMs runs 4 waves at BN=256 but 7 half-cost waves at BN=128).
-  if (k.pair) {
-    k.BN = std::min(128, d->Cout);
-  } else if (d->force_bn > 0) {
+  if (d->force_bn > 0) {
     YV6_REQUIRE(d->force_bn % 16 == 0 && d->force_bn <= 256, "conv: force_bn must be a multiple of 16 <= 256");
     k.BN = d->force_bn;
   } else {
@@ -995,23 +1002,22 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   k.tiles_i = ceil_div(d->N, k.BI);
   YV6_REQUIRE(m_tiles * k.tiles_n < (1l << 30), "conv: too many tiles");
   k.m_tiles = (int)m_tiles;
-  // schedule units: tiles, or (pair of M tiles) x N tile in pair mode
-  k.num_tiles = k.pair ? (int)(((m_tiles + 1) / 2) * k.tiles_n) : (int)(m_tiles * k.tiles_n);
+  // CTA pairs (force_pair: 1 = on whenever there are two M tiles, -1 = off, 0 = auto).  Measured on B200, bs32
+  // (profiles/r02_pair_sweep.md): pairs gain where the weight operand dominates the shared-memory traffic -- 3x3 stride-1
+  // layers over >= 128 input channels (128->128 @80x80: 57.5 -> 52.0 us) -- are neutral on the stride-2 layers and LOSE on
+  // the HBM-bound 1x1 layers (two SMs in lockstep hide less latency; 64->64 @160x160: 50 -> 67 us) and on the
+  // resident-weight 64-channel 3x3 layers (73 -> 93 us), so auto mode takes them only for the first kind.
+  const bool pair_auto = (d->kh == 3 && d->kw == 3 && d->stride == 1 && stride_w == 1 && d->Cin >= 128 && d->Cout <= d->Cin);
+  k.cpair = (m_tiles >= 2 && h->max_clusters > 0 && (d->force_pair > 0 || (d->force_pair == 0 && pair_auto))) ? 1 : 0;
+  k.b_rows = k.cpair ? k.BN / 2 : k.BN;
+  // schedule units: tiles, or (two consecutive M tiles) x N tile for CTA pairs
+  k.num_tiles = k.cpair ? (int)(((m_tiles + 1) / 2) * k.tiles_n) : (int)(m_tiles * k.tiles_n);
 
   // smem ring(s)
   k.a_stage_bytes = kTileRows * k.kb_bytes;
-  k.b_stage_bytes = ((k.BN * k.kb_bytes + 1023) / 1024) * 1024;
-  k.c_region_bytes = (k.pair ? 2 : kCBufCount) * kCBufBytes;   // pair mode: one staging buffer per epilogue group
-  const int budget = h->max_smem_optin - 1024 - 1024 - k.c_region_bytes - kBiasSmemFloats * (int)sizeof(float);
-  if (k.pair) {
-    k.b_resident = 0;
-    k.a_stages = 4;                                            // two units' worth of halo tiles (even: a pair never wraps)
-    k.b_stages = std::min(kMaxBStages, (budget - k.a_stages * kHaloStageBytes) / k.b_stage_bytes);
-    YV6_REQUIRE(k.b_stages >= 2, "conv(pair): not enough shared memory");
-    k.stages = k.b_stages;
-    k.a_region_bytes = k.a_stages * kHaloStageBytes;
-    k.b_region_bytes = k.b_stages * k.b_stage_bytes;
-  } else if (k.halo) {
+  k.b_stage_bytes = ((k.b_rows * k.kb_bytes + 1023) / 1024) * 1024;
+  const int budget = h->max_smem_optin - 1024 - 1024 - kCBufCount * kCBufBytes - kBiasSmemFloats * (int)sizeof(float);
+  if (k.halo) {
     const int b_tiles = k.npairs * k.cin_blocks * 9;   // B tiles one output tile consumes
     k.b_resident = (k.tiles_n == 1 && b_tiles <= kMaxBStages && d->force_stages == 0 &&
                     (long)b_tiles * k.b_stage_bytes + 3 * kHaloStageBytes <= budget) ? 1 : 0;
@@ -1037,15 +1043,14 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
     k.b_region_bytes = stages * k.b_stage_bytes;
   }
   k.trace = reinterpret_cast<unsigned long long*>(d->trace);
-  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + k.c_region_bytes + kBiasSmemFloats * sizeof(float) + 1024 + 1024;
+  plan->smem_bytes = (size_t)k.a_region_bytes + k.b_region_bytes + kCBufCount * kCBufBytes + kBiasSmemFloats * sizeof(float) + 1024 + 1024;
 
   // four groups only pay off when the tile's mainloop is shorter than its epilogue (1x1 / small-K layers)
   const int kblocks_per_tile = k.npairs * k.taps * k.cin_blocks;
   k.groups = (4 * k.BN <= 512 && kblocks_per_tile <= 8 && d->force_groups != 2) ? 4 : 2;
   if (d->force_groups == 4 && 4 * k.BN <= 512) k.groups = 4;
-  if (k.pair) k.groups = 2;                // two groups, each draining the two accumulators of its unit
   int cols = 32;
-  while (cols < k.groups * (k.pair ? 2 : 1) * k.BN) cols *= 2;
+  while (cols < k.groups * k.BN) cols *= 2;
   k.tmem_cols = cols;
 
   k.act = d->act;
@@ -1069,8 +1074,14 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   k.res_plane_stride = d->res_plane_stride;
   k.bias = d->bias;
 
-  plan->grid = std::min(k.num_tiles, h->num_sms);
-  if (d->force_grid > 0) plan->grid = std::min(k.num_tiles, d->force_grid);
+  if (k.cpair) {   // grid counts CTAs: two per unit
+    int clusters = std::min(k.num_tiles, h->max_clusters);
+    if (d->force_grid > 0) clusters = std::min(k.num_tiles, std::max(1, d->force_grid / 2));
+    plan->grid = 2 * clusters;
+  } else {
+    plan->grid = std::min(k.num_tiles, h->num_sms);
+    if (d->force_grid > 0) plan->grid = std::min(k.num_tiles, d->force_grid);
+  }
   return YV6_OK;
 }
 
@@ -1078,9 +1089,48 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
 
 using namespace yv6;
 
+using ConvKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
+static const ConvKernelFn kConvKernels[2][2][3] = {
+    {{conv_igemm_kernel<2, 0, false>, conv_igemm_kernel<2, 1, false>, conv_igemm_kernel<2, 2, false>},
+     {conv_igemm_kernel<4, 0, false>, conv_igemm_kernel<4, 1, false>, conv_igemm_kernel<4, 2, false>}},
+    {{conv_igemm_kernel<2, 0, true>, conv_igemm_kernel<2, 1, true>, conv_igemm_kernel<2, 2, true>},
+     {conv_igemm_kernel<4, 0, true>, conv_igemm_kernel<4, 1, true>, conv_igemm_kernel<4, 2, true>}}};
+
+// Once per device: opt the kernels in to the large dynamic shared memory and ask how many 2-CTA clusters of the conv
+// kernel (one CTA per SM) can be co-resident -- the grid of the pair variants.
+static int conv_configure(yv6_handle* h) {
+  if (h->configured & YV6_CFG_CONV) return YV6_OK;
+  for (int c = 0; c < 2; ++c)
+    for (int g = 0; g < 2; ++g)
+      for (int m = 0; m < 3; ++m)
+        YV6_CHECK_CUDA(cudaFuncSetAttribute(kConvKernels[c][g][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * h->num_sms));
+  cfg.blockDim = dim3(64 + 128 * 2);
+  cfg.dynamicSmemBytes = 200 * 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kConvKernels[1][0][1], &cfg);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    n = 0;                                   // pairs unavailable: the single-CTA variants are used
+  }
+  h->max_clusters = std::min(n, h->num_sms / 2);
+  h->configured |= YV6_CFG_CONV;
+  return YV6_OK;
+}
+
 extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out8) {
   yv6_device_guard _dev(h);
   YV6_REQUIRE(h != nullptr && out8 != nullptr, "conv_plan: null argument");
+  { const int rc0 = conv_configure(h); if (rc0 != YV6_OK) return rc0; }
   ConvPlan plan;
   int rc = plan_conv(h, d, &plan);
   if (rc != YV6_OK) return rc;
@@ -1093,13 +1143,14 @@ extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out
   out8[6] = plan.grid;
   out8[7] = plan.k.num_tiles;
   out8[8] = plan.k.halo;
-  out8[9] = plan.k.halo ? plan.k.a_stages * 100 + plan.k.b_resident + 2 * plan.k.pair : 0;
+  out8[9] = (plan.k.halo ? plan.k.a_stages * 100 + plan.k.b_resident : 0) + 10 * plan.k.cpair;
   return YV6_OK;
 }
 
 extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream) {
   yv6_device_guard _dev(h);
   YV6_REQUIRE(h != nullptr, "conv_fwd: null handle");
+  { const int rc0 = conv_configure(h); if (rc0 != YV6_OK) return rc0; }
   ConvPlan plan;
   int rc = plan_conv(h, d, &plan);
   if (rc != YV6_OK) return rc;
@@ -1139,7 +1190,7 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
     uint64_t plane_stride = (d->nsplit == 3) ? (uint64_t)d->w_plane_stride * 2 : ktot * 2 * d->Cout;
     YV6_REQUIRE(plane_stride % 16 == 0, "conv: w_plane_stride must be a multiple of 8 elements");
     cuuint64_t strides[2] = {ktot * 2, plane_stride};
-    cuuint32_t box[3] = {(cuuint32_t)k.kb_elems, (cuuint32_t)k.BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)k.kb_elems, (cuuint32_t)k.b_rows, 1};   // pair mode: each CTA loads half of the N tile
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult cr = h->encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), dims,
                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, plan.swz,
@@ -1179,18 +1230,24 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
     tmC = tmA;  // unused by the kernel
   }
 
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
-  static const KernelFn kernels[2][4] = {
-      {conv_igemm_kernel<2, 0>, conv_igemm_kernel<2, 1>, conv_igemm_kernel<2, 2>, conv_igemm_kernel<2, 3>},
-      {conv_igemm_kernel<4, 0>, conv_igemm_kernel<4, 1>, conv_igemm_kernel<4, 2>, conv_igemm_kernel<2, 3>}};
-  if (!(h->configured & YV6_CFG_CONV)) {
-    for (int g = 0; g < 2; ++g)
-      for (int m = 0; m < 4; ++m)
-        YV6_CHECK_CUDA(cudaFuncSetAttribute(kernels[g][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
-    h->configured |= YV6_CFG_CONV;
+  const int mode = k.halo ? (k.b_resident ? 2 : 1) : 0;
+  ConvKernelFn fn = kConvKernels[k.cpair][k.groups == 4 ? 1 : 0][mode];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3((unsigned)(64 + 128 * k.groups));
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  if (k.cpair) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
   }
-  const int mode = k.pair ? 3 : k.halo ? (k.b_resident ? 2 : 1) : 0;
-  kernels[k.groups == 4 ? 1 : 0][mode]<<<plan.grid, 64 + 128 * k.groups, plan.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmC, k);
+  YV6_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmC, k));
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }

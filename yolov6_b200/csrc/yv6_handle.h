@@ -17,6 +17,7 @@ struct yv6_handle {
   void* scratch;                   // device scratch for kernels that need counters / partials
   size_t scratch_bytes;
   unsigned configured;             // YV6_CFG_* bits: cudaFuncSetAttribute is per device, so the flags live in the handle
+  int max_clusters;                // co-resident 2-CTA clusters of the conv kernel (one CTA per SM): num_sms / 2 on B200; 0 = pairs unavailable
 };
 
 enum { YV6_CFG_CONV = 1u, YV6_CFG_WGRAD = 2u, YV6_CFG_NMS = 4u, YV6_CFG_BN = 8u, YV6_CFG_TRAIN2 = 16u, YV6_CFG_POOL = 32u, YV6_CFG_SELROWS = 64u };

@@ -43,6 +43,7 @@ class InferEngine:
         self.lib = _lib.lib()
         self.fuse_siblings = True
         self.n_lanes = int(os.environ.get("YV6_LANES", "4"))   # streams the launches of one forward are spread over (1 = serial)
+        self.force_pair = -1 if os.environ.get("YV6_PAIR", "1") == "0" else 0   # A/B switch: single-CTA kernels only
         self._side = None
         self.weights = {}     # op index -> dict(w=..., bias=..., alpha=...)
         self._plans = {}      # (N, H, W, dtype) -> plan, least recently used first; bounded (rect-shaped evaluation
@@ -212,6 +213,7 @@ class InferEngine:
                     d.pad_w = _lib.PAD_SAME
                     d.act = ACT_CODES[op.act]
                     d.nsplit = P
+                    d.force_pair = self.force_pair
                     oh, ow = (sh + 2 * d.pad - d.kh) // d.stride + 1, (sw + 2 * d.pad - d.kw) // d.stride + 1
                     plan["conv_info"].append(dict(name=op.name if op.kind != "convT" else f"{op.name}[{q}]", cin=op.cin, cout=int(d.Cout),
                                                   k=d.kh, s=d.stride, ho=oh, wo=ow, h=sh, w=sw,
