@@ -379,6 +379,85 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(const PoolParams p) {
   }
 }
 
+// bf16 (single plane) variant: a maximum of bf16 values is itself one of them, so the whole pyramid runs on packed
+// bf16x2 values with no rounding anywhere -- bit-identical to the fp32 kernel above.  One CTA per (image, 16 channels):
+// a pixel's 32 bytes are one full DRAM sector (the fp32 kernel's 8-channel slices fetched half-used sectors at a 2 KB
+// stride: 0.6 TB/s), the staged plane and its three row-maximum planes take 4 x H*W*32 bytes of shared memory.
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  *reinterpret_cast<__nv_bfloat162*>(&r.x) = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.x), *reinterpret_cast<__nv_bfloat162*>(&b.x));
+  *reinterpret_cast<__nv_bfloat162*>(&r.y) = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.y), *reinterpret_cast<__nv_bfloat162*>(&b.y));
+  *reinterpret_cast<__nv_bfloat162*>(&r.z) = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.z), *reinterpret_cast<__nv_bfloat162*>(&b.z));
+  *reinterpret_cast<__nv_bfloat162*>(&r.w) = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a.w), *reinterpret_cast<__nv_bfloat162*>(&b.w));
+  return r;
+}
+
+__global__ void __launch_bounds__(256) sppf_pool_bf16_kernel(const PoolParams p) {
+  extern __shared__ uint4 sq[];                 // [4][H*W][2] units of 8 channels: x, rowmax5, rowmax9, rowmax13
+  const int cgs = p.C / 16;
+  const int n = blockIdx.x / cgs, cg = blockIdx.x % cgs;
+  const int HW = p.H * p.W, U = HW * 2;
+  uint4* sx = sq;
+  uint4* r5 = sq + U;
+  uint4* r9 = r5 + U;
+  uint4* r13 = r9 + U;
+  const __nv_bfloat16* src = p.buf + (int64_t)n * HW * p.c_total + cg * 16;
+  for (int u = threadIdx.x; u < U; u += blockDim.x)      // two adjacent threads fetch one pixel's 32-byte sector
+    sx[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(u >> 1) * p.c_total + (u & 1) * 8));
+  __syncthreads();
+  for (int u = threadIdx.x; u < U; u += blockDim.x) {    // horizontal maxima over 5 / 9 / 13 columns (clipped at the border)
+    const int i = u >> 1, half = u & 1;
+    const int h = i / p.W, w = i - h * p.W;
+    uint4 m5 = sx[u], m9, m13;
+#pragma unroll
+    for (int dx = 1; dx <= 2; ++dx) {
+      if (w - dx >= 0) m5 = hmax8(m5, sx[u - 2 * dx]);
+      if (w + dx < p.W) m5 = hmax8(m5, sx[u + 2 * dx]);
+    }
+    m9 = m5;
+#pragma unroll
+    for (int dx = 3; dx <= 4; ++dx) {
+      if (w - dx >= 0) m9 = hmax8(m9, sx[u - 2 * dx]);
+      if (w + dx < p.W) m9 = hmax8(m9, sx[u + 2 * dx]);
+    }
+    m13 = m9;
+#pragma unroll
+    for (int dx = 5; dx <= 6; ++dx) {
+      if (w - dx >= 0) m13 = hmax8(m13, sx[u - 2 * dx]);
+      if (w + dx < p.W) m13 = hmax8(m13, sx[u + 2 * dx]);
+    }
+    (void)half;
+    r5[u] = m5;
+    r9[u] = m9;
+    r13[u] = m13;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = p.buf + (int64_t)n * HW * p.c_total + cg * 16;
+  const int rs = 2 * p.W;                                // units per image row
+  for (int u = threadIdx.x; u < U; u += blockDim.x) {    // vertical maxima of the row maxima, then store the three slices
+    const int i = u >> 1;
+    const int h = i / p.W;
+    uint4 m5 = r5[u], m9 = r9[u], m13 = r13[u];
+#pragma unroll
+    for (int dy = 1; dy <= 6; ++dy) {
+      if (h - dy >= 0) {
+        if (dy <= 2) m5 = hmax8(m5, r5[u - dy * rs]);
+        if (dy <= 4) m9 = hmax8(m9, r9[u - dy * rs]);
+        m13 = hmax8(m13, r13[u - dy * rs]);
+      }
+      if (h + dy < p.H) {
+        if (dy <= 2) m5 = hmax8(m5, r5[u + dy * rs]);
+        if (dy <= 4) m9 = hmax8(m9, r9[u + dy * rs]);
+        m13 = hmax8(m13, r13[u + dy * rs]);
+      }
+    }
+    __nv_bfloat16* o = dst + (int64_t)i * p.c_total + (u & 1) * 8;
+    *reinterpret_cast<uint4*>(o + (int64_t)p.C) = m5;
+    *reinterpret_cast<uint4*>(o + (int64_t)2 * p.C) = m9;
+    *reinterpret_cast<uint4*>(o + (int64_t)3 * p.C) = m13;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // head decode: eval tail of Detect.forward (effidehead.py:106-139), generate_anchors(is_eval)
 // (anchor_generator.py:13-33) and dist2bbox(xywh) (general.py:32-43).  One warp per anchor row:
@@ -504,6 +583,16 @@ extern "C" int yv6_sppf_pool(yv6_handle* h, void* buf, int32_t N, int32_t H, int
   if (!(h->configured & YV6_CFG_POOL)) {
     YV6_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
     h->configured |= YV6_CFG_POOL;
+  }
+  const size_t smem16 = (size_t)4 * H * W * 32;
+  if (nsplit != 3 && C % 16 == 0 && smem16 <= (size_t)h->max_smem_optin) {   // bf16 activations: packed, sector-sized channel slices
+    if (!(h->configured & YV6_CFG_POOL16)) {
+      YV6_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
+      h->configured |= YV6_CFG_POOL16;
+    }
+    sppf_pool_bf16_kernel<<<(unsigned)(N * (C / 16)), 256, smem16, (cudaStream_t)stream>>>(p);
+    YV6_CHECK_CUDA(cudaGetLastError());
+    return YV6_OK;
   }
   sppf_pool_kernel<<<(unsigned)(N * (C / 8)), 256, smem, (cudaStream_t)stream>>>(p);
   YV6_CHECK_CUDA(cudaGetLastError());
