@@ -198,7 +198,7 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
     """Forward + decode + batched NMS of `model_name` on B images of S x S per GPU.  Returns a dict of measurements."""
     from yolov6_b200.model import build_model
     from yolov6_b200.nms import nms_batched
-    from yolov6_b200.pipeline import DetectPipeline
+    from yolov6_b200.pipeline import DetectStream
     from yolov6_b200.synth import randomize_
     model = randomize_(build_model(model_name, 80, dev), seed=0)   # seeded synthetic checkpoint
     model.eval().set_precision(precision)
@@ -210,12 +210,13 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
     if graph:
         # steady state = one CUDA-graph launch per batch (yolov6_b200/pipeline.py); two pipelines with
         # separate static buffers alternate so that consecutive steps never reuse a cached input
-        pipes_dev = [DetectPipeline(model, B, S, S, host_input=False, **NMS_KW) for _ in range(2)]
+        # (DetectStream: the graph of step i runs the network of batch i and, as a parallel branch, the NMS of batch i - 1)
+        stream_dev = DetectStream(model, B, S, S, host_input=False, **NMS_KW)
         for i in range(2):
-            pipes_dev[i].x_dev.copy_(dev_f32[i])
+            stream_dev.x_dev[i].copy_(dev_f32[i])
 
         def step_device(i):
-            pipes_dev[i & 1].launch()
+            stream_dev.launch()
     else:
         def step_device(i):
             pred = eng.forward(dev_f32[i & 1])
@@ -226,14 +227,12 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
         out["value"] = world * B / (ms_dev * 1e-3)
         if e2e:
             if graph:
-                copy_stream = torch.cuda.Stream(device=dev)   # H2D of batch i+1 overlaps the kernels of batch i
-                pipes_e2e = [DetectPipeline(model, B, S, S, host_input=True, overlap_h2d=True, copy_stream=copy_stream, **NMS_KW)
-                             for _ in range(2)]
+                stream_e2e = DetectStream(model, B, S, S, host_input=True, **NMS_KW)   # H2D of batch i+1 overlaps the kernels of batch i
                 for i in range(2):
-                    pipes_e2e[i].x_host.copy_(host_u8[i])
+                    stream_e2e.x_host[i].copy_(host_u8[i])
 
                 def step_e2e(i):
-                    pipes_e2e[i & 1].launch()      # H2D (u8, copy stream) -> graph: kernels -> D2H detections
+                    stream_e2e.launch()            # H2D (u8, copy stream) -> graph: network(i) || NMS(i-1) -> D2H detections
             else:
                 def step_e2e(i):
                     x = host_u8[i & 1].to(dev, non_blocking=True)
@@ -473,9 +472,11 @@ def main():
                    "nms": NMS_KW, "weights": "seeded random (yolov6_b200/synth.py)", "parallelism": f"dp{world} image-sharded, no collective",
                    "l2": f"inputs ({B * 3 * S * S * 4 / 1e6:.0f} MB fp32 per batch, two alternating buffers) exceed the 126 MB L2"
                          if B * 3 * S * S * 4 > 126e6 else "two alternating input buffers; activations of one step exceed the 126 MB L2",
-                   "launch": "one CUDA graph per batch (DetectPipeline)" if use_graph else "eager ctypes launches",
-                   "e2e_pipeline": "two alternating pipelines; the pinned-host -> device copy of a batch runs on a copy stream and "
-                                   "overlaps the kernels of the previous batch; detections are copied back inside the graph"},
+                   "launch": ("one CUDA graph per batch (pipeline.DetectStream): the graph of step i holds the network of batch i and, as a "
+                              "parallel branch, the NMS of batch i-1 (head outputs double-buffered; every step runs one network and one NMS, "
+                              "detections lag one step)") if use_graph else "eager ctypes launches",
+                   "e2e_pipeline": "same graphs; the pinned-host -> device copy of batch i+1 runs on a copy stream under the kernels of batch i; "
+                                   "the detections of batch i-1 are copied to pinned host memory inside the NMS branch of step i"},
         "e2e": main_r["e2e"],
         "gpu_launches": main_r["launches_per_step"] * args.steps,
         "roofline": {"bound": "tensor", "kernel": "yv6::conv_igemm_kernel", "achieved": achieved_tf, "peak": peak_tf,

@@ -110,6 +110,43 @@ def test_detect_ring_overlapped_copies_match_eager():
             assert torch.equal(d, r.cpu())
 
 
+@pytest.mark.parametrize("host_input", [True, False])
+def test_detect_stream_software_pipeline_matches_eager(host_input):
+    """DetectStream: the graph of step i runs the network of batch i and, in parallel, the NMS of batch i - 1 over the
+    other head-output set.  Every batch's detections (collected one step later, the last one after drain()) must equal
+    the eager model + NMS, in order."""
+    from yolov6_b200.model import build_model
+    from yolov6_b200.nms import non_max_suppression
+    from yolov6_b200.pipeline import DetectStream
+    from yolov6_b200.synth import randomize_
+    dev = torch.device("cuda:0")
+    m = randomize_(build_model("yolov6n", 80, dev), seed=3).eval()
+    B, S = 2, 160
+    kw = dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)
+    ds = DetectStream(m, B, S, S, host_input=host_input, **kw)
+    g = torch.Generator().manual_seed(4)
+    imgs = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8) for _ in range(5)]
+    feed = imgs if host_input else [(i.float() / 255).to(dev) for i in imgs]
+    outs = []
+    for x in feed:
+        ds.submit(x)
+        r = ds.collect()
+        if r is not None:
+            outs.append(r)
+    assert ds.collect() is None          # the last batch has not been post-processed yet
+    ds.drain()
+    outs.append(ds.collect())
+    assert len(outs) == len(imgs) and ds.collect() is None
+    total = 0
+    for x, dets in zip(feed, outs):
+        with torch.no_grad():
+            ref = non_max_suppression(m(x.to(dev))[0], **kw)
+        for d, r in zip(dets, ref):
+            total += len(r)
+            assert torch.equal(d.cpu(), r.cpu())
+    assert total > 0
+
+
 @pytest.mark.parametrize("name,size,kw", [("yolov6n", 160, dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)),
                                           ("yolov6m", 128, dict(conf_thres=0.001, iou_thres=0.45, max_det=100)),
                                           ("yolov6l6", 128, dict(conf_thres=0.0005, iou_thres=0.6, multi_label=True, agnostic=True, classes=[0, 1, 2, 5, 7]))])

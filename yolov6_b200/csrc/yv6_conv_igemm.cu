@@ -392,25 +392,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool leader = (rank == 0);
   if (threadIdx.x == 0) YV6_TRACE(0);
 
-  if (threadIdx.x == 0) {
-    if (!HALO) {   // generic ring (<= kMaxStages); the halo variants have their own rings below, with up to kMaxBStages stages
-      for (int s = 0; s < p.stages; ++s) {
-        mbar_init(&full[s], 1);
-        mbar_init(&empty[s], 1);
-      }
+  // Prologue, kept short because ~50 of YOLOv6-S's 73 conv launches run a single wave: the tensor-map fetches start first
+  // (their latency overlaps everything below), the 32 lanes of warp 0 initialise the barrier array side by side (the halo
+  // variants have up to 2 x 40 weight-stage barriers), warp 1 allocates TMEM meanwhile.
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      if (p.tma_store) tma_prefetch_desc(&tmC);
     }
-    for (int a = 0; a < G; ++a) {
-      mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], CP ? 8 : 128);    // pair mode: one arrival per epilogue warp of either CTA, on the leader's barrier
-    }
-    if (HALO) {
-      for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-      for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    constexpr int kBarSlots = 2 * kMaxStages + 2 * kMaxGroups + 2 + 2 * kMaxAStages + 2 * kMaxBStages;
+    constexpr int kTemptyFirst = 2 * kMaxStages + kMaxGroups, kTmemSlot = 2 * kMaxStages + 2 * kMaxGroups;
+    for (int i = lane; i < kBarSlots; i += 32) {
+      if (i == kTmemSlot || i == kTmemSlot + 1) continue;     // the TMEM base address lives here (written by warp 1's alloc)
+      // tempty: every epilogue thread arrives -- pair mode: one arrival per epilogue warp of either CTA, on the leader's barrier
+      const bool is_tempty = (i >= kTemptyFirst && i < kTemptyFirst + kMaxGroups);
+      mbar_init(&bars[i], is_tempty ? (CP ? 8u : 128u) : 1u);
     }
     fence_mbar_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
     if (CP) tmem_alloc_pair(tmem_ptr, (uint32_t)p.tmem_cols);
@@ -826,7 +825,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       acc_phase ^= 1;
     }
-    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the staging buffers must outlive the TMA engine's READS only; the global writes complete with the grid
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (group == 0 && q == 0 && lane == 0) YV6_TRACE(7);
   }
 

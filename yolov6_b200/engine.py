@@ -127,7 +127,7 @@ class InferEngine:
         maxs = max(g.strides)
         if H % maxs or W % maxs:
             raise RuntimeError(f"input {H}x{W} must be a multiple of the largest stride {maxs}")
-        plan = {"bufs": [], "calls": [], "conv_info": [], "deps": []}
+        plan = {"bufs": [], "calls": [], "conv_info": [], "deps": [], "pred_descs": [], "head_set": 0}
         for b in g.bufs:
             h, w = H >> b.level, W >> b.level
             shape = (P, N, h, w, b.c_total) if P == 3 else (N, h, w, b.c_total)
@@ -234,6 +234,7 @@ class InferEngine:
                         ch = out.shape[2]
                         lh, lw = sizes[lvl]
                         d.y = out.data_ptr() + int(offs[lvl]) * ch * 4
+                        plan["pred_descs"].append((d, which, int(offs[lvl]) * ch * 4))
                         d.y_dtype = DT_F32
                         d.y_img_stride, d.y_h_stride, d.y_w_stride = A * ch, lw * ch, ch
                     else:
@@ -253,6 +254,8 @@ class InferEngine:
                         d.res_img_stride, d.res_h_stride, d.res_w_stride = rh * rw * rct, rw * rct, rct
                         d.res_plane_stride = rbuf.stride(0) if P == 3 else 0
                         d.alpha = ent["alpha"]
+                    if "neck_start" not in plan and op.name.startswith("neck."):
+                        plan["neck_start"] = len(plan["calls"])     # first launch after the backbone (pipeline.DetectStream forks here)
                     plan["calls"].append(("conv", d))
                     reads = [span(op.src)] + ([span(op.res)] if op.res is not None else [])
                     if op.kind == "pred":
@@ -318,10 +321,24 @@ class InferEngine:
         """Kernels launched per forward for this shape (convs + stem + pools + decode)."""
         return len(self._plan(N, H, W, in_dtype)["calls"]) + 1
 
-    def forward(self, x, stream=None, decode=True):
+    def _select_head_set(self, plan, k):
+        """Point the pred convs at head-output set k (0 = the default tensors; 1 = a second pair, allocated on first use).
+        The software-pipelined serving loop (pipeline.DetectStream) alternates between the two so that the NMS of batch
+        i - 1 can read one set while the network of batch i writes the other."""
+        if k == plan["head_set"]:
+            return
+        if k == 1 and "cls_alt" not in plan:
+            plan["cls_alt"], plan["reg_alt"] = torch.empty_like(plan["cls"]), torch.empty_like(plan["reg"])
+        for d, which, off in plan["pred_descs"]:
+            d.y = plan[which + ("_alt" if k == 1 else "")].data_ptr() + off
+        plan["head_set"] = k
+
+    def forward(self, x, stream=None, decode=True, head_set=0, hook=None):
         """x: [N,3,H,W] CUDA tensor, fp32 in [0,1] or uint8.  Returns pred [N,A,5+nc] fp32 (a buffer owned
         by the engine, overwritten by the next call with the same shape).  decode=False stops after the head convs and
-        returns (cls [N,A,nc], reg [N,A,R], level sizes): the serving pipeline feeds them to the NMS kernels directly."""
+        returns (cls [N,A,nc], reg [N,A,R], level sizes): the serving pipeline feeds them to the NMS kernels directly;
+        head_set = 1 makes the head convs write the alternate (cls, reg) pair (decode=False only).  hook = (i, fn): fn() is
+        called just before launch number i is enqueued, with the main stream current (used to fork a side branch there)."""
         if x.device != self.device:
             raise RuntimeError(f"input on {x.device}, engine on {self.device}")
         if x.dtype not in (torch.float32, torch.uint8):
@@ -331,6 +348,8 @@ class InferEngine:
         assert Cin == 3
         plan = self._plan(N, H, W, x.dtype)
         plan["image"] = x  # keep alive while kernels are in flight
+        assert head_set == 0 or not decode, "the alternate head set is for decode=False callers"
+        self._select_head_set(plan, head_set)
         main = stream if stream is not None else torch.cuda.current_stream(self.device)
         sp = _lib.stream_ptr(main)
         lib, h, chk = self.lib, self.handle, _lib.check
@@ -345,6 +364,8 @@ class InferEngine:
             plan["fork"].record(main)
             forked = set()
         for i, (kind, d) in enumerate(plan["calls"]):
+            if hook is not None and i == hook[0]:
+                hook[1]()
             if multi:
                 t = lane[i]
                 if t and t not in forked:        # a side stream starts after everything the caller queued before this forward
@@ -367,6 +388,8 @@ class InferEngine:
             sp = sps[0]
         g = self.g
         if not decode:
+            if head_set == 1:
+                return plan["cls_alt"], plan["reg_alt"], plan["sizes"]
             return plan["cls"], plan["reg"], plan["sizes"]
         chk(lib.yv6_head_decode(h, C.c_void_p(plan["cls"].data_ptr()), C.c_void_p(plan["reg"].data_ptr()),
                                 C.c_void_p(plan["pred"].data_ptr()), N, g.num_classes, 4 * (g.reg_max + 1),
