@@ -168,16 +168,21 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def timed(fn, steps, warmup, world, dev):
-    """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events, max over ranks -> ms per step."""
+def timed(fn, steps, warmup, world, dev, farm=None):
+    """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events, max over ranks -> ms per step.
+    farm: the steps run on the farm's own streams; the timing events bracket them through fence() / release()."""
     import torch.distributed as dist
     for i in range(warmup):
         fn(i)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    if farm is not None:
+        farm.release()         # no lane starts a timed step before e0
     for i in range(steps):
         fn(i)
+    if farm is not None:
+        farm.fence()           # e1 follows the last kernel of every lane
     e1.record()
     barrier(world)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -198,7 +203,7 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
     """Forward + decode + batched NMS of `model_name` on B images of S x S per GPU.  Returns a dict of measurements."""
     from yolov6_b200.model import build_model
     from yolov6_b200.nms import nms_batched
-    from yolov6_b200.pipeline import DetectStream
+    from yolov6_b200.pipeline import DetectFarm
     from yolov6_b200.synth import randomize_
     model = randomize_(build_model(model_name, 80, dev), seed=0)   # seeded synthetic checkpoint
     model.eval().set_precision(precision)
@@ -211,9 +216,12 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
         # steady state = one CUDA-graph launch per batch (yolov6_b200/pipeline.py); two pipelines with
         # separate static buffers alternate so that consecutive steps never reuse a cached input
         # (DetectStream: the graph of step i runs the network of batch i and, as a parallel branch, the NMS of batch i - 1)
-        stream_dev = DetectStream(model, B, S, S, host_input=False, **NMS_KW)
-        for i in range(2):
-            stream_dev.x_dev[i].copy_(dev_f32[i])
+        # DetectFarm: `lanes` such pipelines with their own buffers and streams, fed round-robin (independent batches)
+        n_lanes = int(os.environ.get("YV6_FARM", "2"))
+        stream_dev = DetectFarm(model, B, S, S, lanes=n_lanes, host_input=False, **NMS_KW)
+        for ln in stream_dev.lanes:
+            for i in range(2):
+                ln.x_dev[i].copy_(dev_f32[i])
 
         def step_device(i):
             stream_dev.launch()
@@ -222,14 +230,15 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
             pred = eng.forward(dev_f32[i & 1])
             return nms_batched(pred, **NMS_KW)
     with torch.no_grad():
-        ms_dev = timed(step_device, steps, warmup, world, dev)
+        ms_dev = timed(step_device, steps, warmup, world, dev, farm=stream_dev if graph else None)
         out["ms_per_step"] = ms_dev
         out["value"] = world * B / (ms_dev * 1e-3)
         if e2e:
             if graph:
-                stream_e2e = DetectStream(model, B, S, S, host_input=True, **NMS_KW)   # H2D of batch i+1 overlaps the kernels of batch i
-                for i in range(2):
-                    stream_e2e.x_host[i].copy_(host_u8[i])
+                stream_e2e = DetectFarm(model, B, S, S, lanes=n_lanes, host_input=True, **NMS_KW)   # H2D of batch i+1 overlaps the kernels of batch i
+                for ln in stream_e2e.lanes:
+                    for i in range(2):
+                        ln.x_host[i].copy_(host_u8[i])
 
                 def step_e2e(i):
                     stream_e2e.launch()            # H2D (u8, copy stream) -> graph: network(i) || NMS(i-1) -> D2H detections
@@ -238,7 +247,7 @@ def bench_infer(model_name, B, S, steps, warmup, rank, world, dev, precision="bf
                     x = host_u8[i & 1].to(dev, non_blocking=True)
                     o, c, _, _ = nms_batched(eng.forward(x), **NMS_KW)
                     return o.cpu(), c.cpu()
-            ms_e2e = timed(step_e2e, steps, warmup, world, dev)
+            ms_e2e = timed(step_e2e, steps, warmup, world, dev, farm=stream_e2e if graph else None)
             out["e2e"] = {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                           "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * NMS_KW["max_det"] * 6 * 4 + B * 4}
         if roofline:

@@ -147,6 +147,46 @@ def test_detect_stream_software_pipeline_matches_eager(host_input):
     assert total > 0
 
 
+def test_detect_farm_two_independent_lanes_match_eager():
+    """DetectFarm: two DetectStreams with their own engines / buffers / CUDA streams fed round-robin; the batches of the two
+    lanes overlap on the GPU.  Detections per batch must equal the eager model + NMS."""
+    from yolov6_b200.model import build_model
+    from yolov6_b200.nms import non_max_suppression
+    from yolov6_b200.pipeline import DetectFarm
+    from yolov6_b200.synth import randomize_
+    dev = torch.device("cuda:0")
+    m = randomize_(build_model("yolov6n", 80, dev), seed=5).eval()
+    B, S = 2, 160
+    kw = dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)
+    farm = DetectFarm(m, B, S, S, lanes=2, host_input=True, **kw)
+    g = torch.Generator().manual_seed(11)
+    imgs = [(torch.rand(B, 3, S, S, generator=g) * 255).to(torch.uint8) for _ in range(8)]
+    outs, nxt = {}, [0, 1]                   # nxt[lane] = index of the oldest uncollected batch of that lane
+    for j, x in enumerate(imgs):
+        ln = j % 2
+        farm.submit(x)                       # batch j goes to lane j % 2
+        r = farm.lanes[ln].collect()         # the lane's previous batch, post-processed by the step just submitted
+        if r is not None:
+            outs[nxt[ln]] = r
+            nxt[ln] += 2
+    for ln, lane in enumerate(farm.lanes):
+        with torch.cuda.stream(farm.streams[ln]):
+            lane.drain()
+        torch.cuda.synchronize()
+        r = lane.collect()
+        assert r is not None and lane.collect() is None
+        outs[nxt[ln]] = r
+    assert sorted(outs) == list(range(len(imgs)))
+    total = 0
+    for j, x in enumerate(imgs):
+        with torch.no_grad():
+            ref = non_max_suppression(m(x.to(dev))[0], **kw)
+        for d, r in zip(outs[j], ref):
+            total += len(r)
+            assert torch.equal(d, r.cpu())
+    assert total > 0
+
+
 @pytest.mark.parametrize("name,size,kw", [("yolov6n", 160, dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)),
                                           ("yolov6m", 128, dict(conf_thres=0.001, iou_thres=0.45, max_det=100)),
                                           ("yolov6l6", 128, dict(conf_thres=0.0005, iou_thres=0.6, multi_label=True, agnostic=True, classes=[0, 1, 2, 5, 7]))])

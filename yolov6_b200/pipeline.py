@@ -156,7 +156,7 @@ class DetectStream:
     """
 
     def __init__(self, model, batch, height, width, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
-                 multi_label=False, max_det=300, host_input=True):
+                 multi_label=False, max_det=300, host_input=True, engine=None):
         self.model = model.eval()
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -174,7 +174,7 @@ class DetectStream:
         import os
         self.fork_at_neck = os.environ.get("YV6_NMS_FORK", "neck") == "neck"
         self._drained = False
-        self.eng = model.engine()
+        self.eng = engine if engine is not None else model.engine()
         self.eng.pin(batch, height, width, dt)
         A = sum((height // int(s)) * (width // int(s)) for s in model.graph.strides)
         self.nms_ws = torch.empty(workspace_bytes(batch, A, model.graph.num_classes, multi_label), dtype=torch.uint8, device=self.dev)
@@ -301,3 +301,54 @@ class DetectStream:
             return
         self.drain_graphs[(self.steps - 1) & 1].replay()
         self._drained = True
+
+
+class DetectFarm:
+    """`lanes` independent DetectStreams -- each with its own inference engine (own activation buffers) and its own CUDA
+    stream -- fed round-robin.  Batches of different lanes have no dependency on each other, so the GPU runs the tail of
+    one lane's kernel (the CTAs still working on their last tile of a 3.24-wave layer, an exposed epilogue, the launch gap
+    before the next dependent kernel) next to the head of the other lane's kernel: the persistent conv kernels hold one CTA
+    per SM, so the lanes interleave kernel by kernel rather than share SMs, and what one lane leaves idle the other fills.
+    Costs `lanes` x the activation memory (YOLOv6-S bs32: ~2.3 GB per lane).  Per-lane results are those of DetectStream
+    (bit-identical to the serial path); batch order across lanes is the submission order."""
+
+    def __init__(self, model, batch, height, width, lanes=2, **kw):
+        from .engine import InferEngine
+        self.model = model.eval()
+        self.dev = next(model.parameters()).device
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(lanes)]
+        self.lanes = []
+        for i in range(lanes):
+            eng = model.engine() if i == 0 else InferEngine(model.graph, model.state_dict(), self.dev, model.precision)
+            self.lanes.append(DetectStream(model, batch, height, width, engine=eng, **kw))
+        self.n = 0
+        self._ev = [torch.cuda.Event() for _ in range(lanes)]
+        self._go = torch.cuda.Event()
+
+    def lane_of_next(self):
+        return self.lanes[self.n % len(self.lanes)]
+
+    def launch(self):
+        i = self.n % len(self.lanes)
+        with torch.cuda.stream(self.streams[i]):
+            self.lanes[i].launch()
+        self.n += 1
+
+    def submit(self, images):
+        i = self.n % len(self.lanes)
+        with torch.cuda.stream(self.streams[i]):
+            self.lanes[i].submit(images)
+        self.n += 1
+
+    def fence(self):
+        """The current stream waits for everything enqueued on the lanes."""
+        cur = torch.cuda.current_stream(self.dev)
+        for ev, st in zip(self._ev, self.streams):
+            ev.record(st)
+            cur.wait_event(ev)
+
+    def release(self):
+        """The lanes wait for everything enqueued on the current stream (e.g. a timing event)."""
+        self._go.record(torch.cuda.current_stream(self.dev))
+        for st in self.streams:
+            st.wait_event(self._go)
