@@ -28,6 +28,7 @@ gradient all-reduce (core/engine.py:464-466) is a few large NCCL calls that over
 the BN apply / backward kernels (y = act(z) + alpha * x, alpha read from device memory).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -124,6 +125,8 @@ class TrainEngine:
         self.dbg = {}
         self._shape = None
         self.bucket_hook = None     # callable(k) invoked (eager mode) right after bucket k's gradients are unpacked
+        self.overlap_wgrad = os.environ.get("YV6_WGRAD_OVERLAP", "1") != "0"   # weight gradients on a side stream (see backward)
+        self._wg_stream = None
         self._build_state()
 
     # ================================================================== parameter-level state (shape independent)
@@ -422,7 +425,9 @@ class TrainEngine:
         # shared scratch: BN-backward outputs (gradients w.r.t. the raw conv outputs) live only until their dgrad / wgrad ran
         dc_elems = max([N * (H >> g.bufs[op.dst.buf].level) * (W >> g.bufs[op.dst.buf].level) * op.cout
                         for op in g.ops if op.kind in ("conv", "stem")] + [1])
-        dc_pool = [torch.zeros(dc_elems, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        # (two per op parity: the weight gradients of an op run on a side stream while the next op's BN backward refills the other pair)
+        dc_pool = [torch.zeros(dc_elems, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+        bn_ops = 0
         pool_scr, dq_pool = None, None
         fwd, bwd_rev = [], []        # bwd_rev[j] = list of calls of op j (assembled in reverse op order afterwards)
         x_dt = DT_U8 if in_dtype == torch.uint8 else DT_F32
@@ -529,7 +534,7 @@ class TrainEngine:
                     d.dx[b], d.dx_pitch[b], d.accumulate[b] = gsrc.data_ptr() + op.src.c_off * 2, gsrc.shape[3], 1
                     dcs.append(None)
                 else:
-                    dc = dc_pool[len([t for t in dcs if t is not None])][:count * op.cout].view(n, ho, wo, op.cout)
+                    dc = dc_pool[2 * (bn_ops & 1) + len([t for t in dcs if t is not None])][:count * op.cout].view(n, ho, wo, op.cout)
                     d.dx[b], d.dx_pitch[b], d.accumulate[b] = dc.data_ptr(), op.cout, 0
                     dcs.append(dc)
             d.y, d.y_pitch = dst.data_ptr() + op.dst.c_off * 2, dct
@@ -550,20 +555,22 @@ class TrainEngine:
                     wr.append(dict(buf=op.src.buf, off=op.src.c_off, n=op.cin, full=True, what=("dx", b)))
             if op.res is not None:
                 wr.append(dict(buf=op.res.buf, off=op.res.c_off, n=op.cout, full=True, what=("dres", 0)))
-            calls.append(("bn_bwd", d, wr))
+            par = bn_ops & 1
+            bn_ops += 1
+            calls.append(("bn_bwd", d, wr, par))
             if op.kind == "stem":       # im2col once, then one tensor-core wgrad GEMM per branch
                 patches, patches_lo = bf(n, ho, wo, 32), bf(n, ho, wo, 32)     # image = hi + lo (bf16 planes)
                 self._stem_patches = (patches, patches_lo)
                 calls.append(("im2col", (self.x_static.data_ptr(), x_dt, 1.0 / 255.0, N, H, W, patches.data_ptr(), patches_lo.data_ptr())))
                 for b in range(nb):
                     for pl in (patches, patches_lo):
-                        calls.append(("wgrad", self._wgrad_desc(pl, 0, 32, dcs[b], 0, op.cout, 1, 1, z(i, "dw", b))))
+                        calls.append(("wgrad", self._wgrad_desc(pl, 0, 32, dcs[b], 0, op.cout, 1, 1, z(i, "dw", b)), par))
             else:
                 src, gsrc = view(op.src)
                 for b, ent in enumerate(br):
                     if ent["k"] == 0:
                         continue
-                    calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dcs[b], 0, op.cout, ent["k"], op.s, z(i, "dw", b))))
+                    calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dcs[b], 0, op.cout, ent["k"], op.s, z(i, "dw", b)), par))
                     dds = self._dgrad_descs(dcs[b], ent, ent["k"], op.s, gsrc, op.src.c_off, op.cin)
                     # a stride-2 3x3 dgrad = four parity convolutions that together cover every pixel; 1x1 stride 2 covers one parity
                     full = op.s == 1 or ent["k"] == 3
@@ -694,17 +701,51 @@ class TrainEngine:
             for gb in self.zero_gbufs:
                 gb.zero_()
         calls = self.bwd_calls if last is None else self.bwd_calls[:last]
+        # Weight gradients leave the critical path: a wgrad only feeds the gradient buffer, so it runs on a side stream next to
+        # the dgrad of its own op and the (HBM-bound) BatchNorm backward of the next one.  Hazards: its dY operand lives in the
+        # scratch pair of its op's parity (the BN backward two ops later waits for it), the transposed-conv quadrant copies reuse
+        # their scratch (they wait for everything), and a bucket's unpack reads the accumulators (waits for everything).
+        overlap = self.overlap_wgrad
+        main = torch.cuda.current_stream(self.dev)
+        if overlap and self._wg_stream is None:
+            self._wg_stream = torch.cuda.Stream(device=self.dev)
+        side = self._wg_stream
+        ssp = _lib.stream_ptr(side) if overlap else sp
+        pending = []             # (event recorded on the side stream after a wgrad, scratch parity or None)
+
+        def wait_pending(par=-1):
+            keep = []
+            for ev, q in pending:
+                if par == -1 or q == par:
+                    main.wait_event(ev)
+                else:
+                    keep.append((ev, q))
+            pending[:] = keep
+
         for c in calls[first:]:
             kind, d = c[0], c[1]
             if kind == "conv":
                 chk(lib.yv6_conv_fwd(h, C.byref(d), sp))
             elif kind == "wgrad":
-                chk(lib.yv6_conv_wgrad(h, C.byref(d), sp))
+                if overlap:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    chk(lib.yv6_conv_wgrad(h, C.byref(d), ssp))
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    pending.append((done, c[2] if len(c) > 2 else None))
+                else:
+                    chk(lib.yv6_conv_wgrad(h, C.byref(d), sp))
             elif kind == "bn_bwd":
+                if overlap:
+                    wait_pending(c[3])
                 chk(lib.yv6_bn_bwd(h, C.byref(d), sp))
             elif kind == "stats":
                 chk(lib.yv6_bn_stats_finalize(h, C.byref(d), sp))
             elif kind == "copy":
+                if overlap:
+                    wait_pending()
                 d[0].copy_(d[1])
             elif kind == "hgp":
                 chk(lib.yv6_head_grad_prep(h, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], sp))
@@ -713,12 +754,16 @@ class TrainEngine:
             elif kind == "im2col":
                 chk(lib.yv6_stem_im2col(h, *d, sp))
             elif kind == "bucket":
+                if overlap:
+                    wait_pending()
                 self.grad_tables[d].launch(lib, h, accumulate, sp)
                 if self.bucket_hook is not None:
                     self.bucket_hook(d)
             elif kind == "dbg":
                 if self.debug:
                     self.dbg[d[0]] = dict(gdst=d[1].clone())
+        if overlap:
+            wait_pending()      # every call (and every captured graph segment) ends joined
 
     def bucket_call_index(self):
         """Indices into the backward call list right after each bucket's unpack (segment boundaries for graph capture)."""
