@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YV6_ABI_VERSION 2
+#define YV6_ABI_VERSION 3
 
 enum {
   YV6_OK = 0,
@@ -253,9 +253,33 @@ typedef struct yv6_loss_desc {
   double* out;
   void* workspace;
   int64_t workspace_bytes;   /* >= yv6_det_loss_workspace_bytes(B, A) */
+  int32_t norm_gt_zero;      /* ABI 3: 0 = divide the sums by target_scores_sum when it is > 1 (loss.py:168-169, 238-262);
+                              * 1 = when it is > 0, the rule of the fuse_ab loss (loss_fuseab.py:139, 203-206) */
 } yv6_loss_desc;
 int64_t yv6_det_loss_workspace_bytes(int32_t B, int32_t A);
 int yv6_det_loss(yv6_handle* h, const yv6_loss_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fuse_ab: the anchor-aided training branch of the head (effidehead_fuseab.py:94-140, loss_fuseab.py:58-76).
+ * Per level the two extra pred convs (yv6_conv_fwd, fp32 outputs, sigmoid fused on the class branch) write the natural
+ * order raw_cls [B, hw, na*nc] / raw_reg [B, hw, na*4]; na = 3.
+ * yv6_head_ab_pack:  -> rows [row_off + a*hw + p] of cls_ab [B, rows_total, nc] and reg_ab [B, rows_total, 4] =
+ *                    (x_off, y_off, (2 sigmoid(r_w))^2 * anchors_wh[2a], (2 sigmoid(r_h))^2 * anchors_wh[2a+1]); anchors_wh = host
+ *                    float[6], anchors_init of the level / stride (effidehead_fuseab.py:35,117-119).  row_off = 3 * (A of lower levels).
+ * yv6_head_ab_grad:  gradients w.r.t. those tensors -> dense NHWC bf16 gradients w.r.t. the raw conv outputs
+ *                    dl_cls [B, hw, cls_pad], dl_reg [B, hw, reg_pad] (sigmoid backward included, padded channels zero).
+ * yv6_ab_boxes:      reg_ab + cell centres (pixels) + strides -> boxes in pixels (xyxy, for the assigner) and the equivalent
+ *                    (l, t, r, b) distances in stride units, which yv6_det_loss consumes like an anchor-free head's output.
+ * yv6_ab_boxes_bwd:  gradient w.r.t. (l, t, r, b) -> gradient w.r.t. (x_off, y_off, w, h).
+ * ---------------------------------------------------------------------------------------------- */
+int yv6_head_ab_pack(yv6_handle* h, const float* raw_cls, const float* raw_reg, int32_t B, int32_t hw, int32_t na, int32_t nc,
+                     const float* anchors_wh, int32_t row_off, int32_t rows_total, float* cls_ab, float* reg_ab, void* stream);
+int yv6_head_ab_grad(yv6_handle* h, const float* grad_cls_ab, const float* cls_ab, const float* grad_reg_ab, const float* raw_reg,
+                     int32_t B, int32_t hw, int32_t na, int32_t nc, const float* anchors_wh, int32_t row_off, int32_t rows_total,
+                     int32_t cls_pad, int32_t reg_pad, void* dl_cls, void* dl_reg, void* stream);
+int yv6_ab_boxes(yv6_handle* h, const float* reg_ab, const float* anc_points, const float* strides, int32_t B, int32_t A,
+                 float* ltrb, float* boxes_px, void* stream);
+int yv6_ab_boxes_bwd(yv6_handle* h, const float* grad_ltrb, int64_t rows, float* grad_reg_ab, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training of the conv stack (train form): what autograd + cuDNN do for the reference's

@@ -292,6 +292,33 @@ def head_raw(sd, cfg, feats):
     return torch.cat(cls_all, 1), torch.cat(reg_all, 1)
 
 
+AB_ANCHORS_INIT = [[10, 13, 19, 19, 33, 23], [30, 61, 59, 59, 59, 119], [116, 90, 185, 185, 373, 326]]   # configs/yolov6{n,s,m}.py head.anchors_init
+
+
+def head_ab(sd, cfg, feats, anchors_init=None):
+    """Training branch of the fuse_ab head, effidehead_fuseab.py:94-140: besides the anchor-free outputs, per level
+    cls_preds_ab / reg_preds_ab emit na = 3 predictions per pixel, reshaped to (b, na, h, w, .) and flattened to rows
+    (anchor, pixel); reg[..., 2:4] = (2 sigmoid)^2 * anchors_init / stride.  Returns (cls_ab [B,3A,nc], reg_ab [B,3A,4])."""
+    anchors_init = anchors_init or AB_ANCHORS_INIT
+    na = 3
+    cls_all, reg_all = [], []
+    for i, x in enumerate(feats):
+        b, _, h, w = x.shape
+        x = conv_bn_act(sd, f"detect.stems.{i}", x, 1, "silu")
+        cf = conv_bn_act(sd, f"detect.cls_convs.{i}", x, 1, "silu")
+        rf = conv_bn_act(sd, f"detect.reg_convs.{i}", x, 1, "silu")
+        c = F.conv2d(cf, _wq(sd[f"detect.cls_preds_ab.{i}.weight"].to(x.dtype)), sd[f"detect.cls_preds_ab.{i}.bias"].to(x.dtype))
+        r = F.conv2d(rf, _wq(sd[f"detect.reg_preds_ab.{i}.weight"].to(x.dtype)), sd[f"detect.reg_preds_ab.{i}.bias"].to(x.dtype))
+        c = torch.sigmoid(c).reshape(b, na, -1, h, w).permute(0, 1, 3, 4, 2)                 # :112-114
+        r = r.reshape(b, na, -1, h, w).permute(0, 1, 3, 4, 2)                               # :116
+        anc = (torch.tensor(anchors_init[i], dtype=x.dtype) / cfg["strides"][i]).reshape(1, na, 1, 1, 2)   # :35
+        wh = ((r[..., 2:4].sigmoid() * 2) ** 2) * anc                                       # :117
+        r = torch.cat([r[..., :2], wh], -1)
+        cls_all.append(c.flatten(1, 3))
+        reg_all.append(r.flatten(1, 3))
+    return torch.cat(cls_all, 1), torch.cat(reg_all, 1)
+
+
 def eval_anchor_points(sizes, strides, dtype=torch.float32):
     """generate_anchors(is_eval=True, mode='af'), anchor_generator.py:13-33: cell centres (+0.5) in
     grid units and the per-anchor stride column."""
@@ -320,13 +347,16 @@ def decode_eval(cfg, cls, reg, sizes):
     return torch.cat([box, torch.ones(B, A, 1, dtype=reg.dtype), cls], -1)
 
 
-def forward(sd, cfg, x, train_outputs=False):
+def forward(sd, cfg, x, train_outputs=False, fuse_ab=False):
     """Model.forward, yolo.py:33-41.  x: [B,3,H,W] in [0,1].  Eval: [B,A,5+nc].
     train_outputs=True returns the train-mode head tensors (cls post-sigmoid, reg raw) computed
-    with eval-mode BN -- used to pin the loss / assigner inputs."""
+    with eval-mode BN -- used to pin the loss / assigner inputs; with fuse_ab also (cls_ab, reg_ab)."""
     feats = neck(sd, cfg, backbone(sd, cfg, x))
     sizes = [tuple(f.shape[2:]) for f in feats]
     cls, reg = head_raw(sd, cfg, feats)
+    if train_outputs and fuse_ab:
+        cls_ab, reg_ab = head_ab(sd, cfg, feats)
+        return cls, reg, sizes, cls_ab, reg_ab
     if train_outputs:
         return cls, reg, sizes
     return decode_eval(cfg, cls, reg, sizes)

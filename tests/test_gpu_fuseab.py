@@ -1,0 +1,89 @@
+"""GPU parity of the anchor-aided (fuse_ab) loss -- yv6_ab_boxes + yv6_tal_assign(topk 26) + yv6_det_loss + yv6_ab_boxes_bwd behind
+`yolov6_b200.loss_fuseab.ComputeLoss` -- against the reference's goldens (tests/golden/make_golden_fuseab.py) and the oracle,
+and of the whole fuse_ab training step through the drop-in API.  (The head kernels are checked op by op in
+tests/test_gpu_train.py::test_train_step_matches_reference_op_by_op[yolov6n-128-2-True].)
+
+Bars as in test_gpu_loss.py: positives exact; loss / loss_items 1e-5 against the fp32 reference; gradients rtol 2e-4."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_json, golden_keys, golden_npz
+from oracle import fabricate as fab
+from oracle import loss as oloss
+from oracle import loss_fuseab as oab
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", golden_json("fuseab_cases.json"), ids=lambda c: c[0])
+def test_fuseab_loss_matches_reference_golden(case):
+    from yolov6_b200.loss_fuseab import ComputeLoss
+    name, img, B, seed, iou_type, drop = case
+    g = golden_npz("fuseab.npz")
+    strides = [8, 16, 32]
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = oab.synthetic_ab_outputs(B, sizes, 80, seed)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=80), drop)
+    dev = torch.device("cuda:0")
+    psd, pdd = ps.to(dev).requires_grad_(True), pd.to(dev).requires_grad_(True)
+    feats = [torch.zeros(B, 8, h, w, device=dev) for h, w in sizes]
+    cl = ComputeLoss(fpn_strides=strides, num_classes=80, ori_img_size=img, warmup_epoch=0, use_dfl=False, reg_max=0, iou_type=iou_type)
+    loss, items = cl((feats, psd, pdd), targets.to(dev), 0, 1, img, img)
+    loss.backward()
+    ref_loss = float(g[f"{name}_loss"])
+    print(name, "loss", float(loss), "reference", ref_loss)
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
+    np.testing.assert_allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=1e-5, atol=1e-7)
+    fg = cl.last_assignment.fg.bool().cpu().numpy()
+    assert np.array_equal(np.packbits(fg), g[f"{name}_fg_from_grad"]), "positives differ from the reference"
+    fgt = torch.from_numpy(fg)
+    np.testing.assert_allclose(pdd.grad.cpu()[fgt].double().numpy(), g[f"{name}_grad_distri_rows"], rtol=2e-4, atol=1e-7)
+    assert float(pdd.grad.cpu()[~fgt].abs().max()) == 0.0
+    np.testing.assert_allclose(psd.grad.cpu()[fgt].double().numpy(), g[f"{name}_grad_scores_rows"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(psd.grad.cpu().flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=2e-4, atol=1e-8)
+    got_abs, ref_abs = float(psd.grad.double().abs().sum()), float(g[f"{name}_grad_scores_abs"])
+    assert abs(got_abs - ref_abs) <= 1e-4 * ref_abs
+
+
+def test_fuseab_training_step_through_the_dropin_api():
+    """What Trainer.train_in_steps does with --fuse_ab (core/engine.py:161-166): both losses on the five outputs, one backward;
+    every parameter -- including the two extra pred convs per level -- receives a finite gradient, eval mode ignores the branch."""
+    from yolov6_b200.loss import ComputeLoss
+    from yolov6_b200.loss_fuseab import ComputeLoss as ComputeLossAB
+    from yolov6_b200.model import build_model
+    dev = torch.device("cuda:0")
+    sd = fab.fabricate_state_dict(golden_keys("yolov6n_fuseab"), seed=0)
+    for k in sd:
+        if (".cls_preds" in k or ".reg_preds" in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+    m = build_model("yolov6n", 80, dev, fuse_ab=True)
+    m.load_state_dict(sd)
+    m.train()
+    S, B = 128, 2
+    x = fab.synthetic_images(B, S, S, seed=3).to(dev)
+    targets = oloss.synthetic_targets(B, seed=4).to(dev)
+    crit = ComputeLoss(num_classes=80, ori_img_size=S, warmup_epoch=0, use_dfl=False, reg_max=0, iou_type="siou")
+    crit_ab = ComputeLossAB(num_classes=80, ori_img_size=S, warmup_epoch=0, use_dfl=False, reg_max=0, iou_type="siou")
+    preds, _ = m(x)
+    assert len(preds) == 5 and preds[1].shape == (B, 3 * preds[3].shape[1], 80) and preds[2].shape == (B, 3 * preds[3].shape[1], 4)
+    loss, items = crit((preds[0], preds[3], preds[4]), targets, 0, 0, S, S)
+    loss_ab, items_ab = crit_ab(preds[:3], targets, 0, 0, S, S)
+    # the ab loss on the model's own outputs equals the oracle's on the same tensors
+    ref, ref_items = oab.compute_loss_ab([(S // s, S // s) for s in (8, 16, 32)], preds[1].detach().cpu(), preds[2].detach().cpu(),
+                                         targets.cpu(), strides=[8, 16, 32], ori_img_size=S, iou_type="siou")
+    assert abs(float(loss_ab) - float(ref)) <= 1e-5 * abs(float(ref)), (float(loss_ab), float(ref))
+    (loss + loss_ab).backward()
+    torch.cuda.synchronize()
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+    for i in range(3):
+        assert float(m.detect.cls_preds_ab[i].weight.grad.abs().sum()) > 0 and float(m.detect.reg_preds_ab[i].bias.grad.abs().sum()) > 0
+    # eval mode: the anchor-free branch only (effidehead_fuseab.py:141-199) == the same weights in a plain model
+    m.eval()
+    plain = build_model("yolov6n", 80, dev)
+    plain.load_state_dict({k: v for k, v in m.state_dict().items() if "_ab." not in k})
+    plain.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x)[0], plain(x)[0])

@@ -42,8 +42,9 @@ def _q(t):
     return t + (t.to(torch.bfloat16).double() - t).detach()
 
 
-@pytest.mark.parametrize("name,size,batch", [("yolov6n", 128, 4), ("yolov6s", 96, 2), ("yolov6m", 96, 2), ("yolov6l6", 128, 2)])
-def test_train_step_matches_reference_op_by_op(name, size, batch):
+@pytest.mark.parametrize("name,size,batch,fuse_ab", [("yolov6n", 128, 4, False), ("yolov6s", 96, 2, False), ("yolov6m", 96, 2, False),
+                                                     ("yolov6l6", 128, 2, False), ("yolov6n", 128, 2, True)])
+def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
     """Forward against the oracle's train-mode network; backward op by op.
 
     Train-mode BatchNorm over randomly initialised weights is chaotic: the float64 oracle and the same oracle
@@ -56,28 +57,44 @@ def test_train_step_matches_reference_op_by_op(name, size, batch):
     import torch.nn.functional as F
     from yolov6_b200.model import build_model
     dev = torch.device("cuda:0")
-    sd = fab.fabricate_state_dict(golden_keys(name), seed=0)
+    sd = fab.fabricate_state_dict(golden_keys(name + ("_fuseab" if fuse_ab else "")), seed=0)
     for k in sd:      # batch-stat BN makes the features unit-variance; keep the head logits O(1)
-        if (".cls_preds." in k or ".reg_preds." in k) and k.endswith("weight"):
+        if (".cls_preds" in k or ".reg_preds" in k) and k.endswith("weight"):
             sd[k] = sd[k] * 0.1
         if k.endswith(".alpha"):
             sd[k] = sd[k] * 0.75
-    m = build_model(name, 80, dev)
+    m = build_model(name, 80, dev, fuse_ab=fuse_ab)
     m.load_state_dict(sd)
     m.train()
     eng = m.train_engine()
     eng.debug = True
     x = fab.synthetic_images(batch, size, size, seed=11)
     xd = x.to(dev)
-    (feats, cls, reg), _ = m(xd)
     g = torch.Generator().manual_seed(5)
+    if fuse_ab:       # anchor-aided branch (effidehead_fuseab.py:94-140): five training outputs, all of them in the scalar
+        (feats, cls_ab, reg_ab, cls, reg), _ = m(xd)
+    else:
+        (feats, cls, reg), _ = m(xd)
     wc, wr = torch.randn(cls.shape, generator=g).to(dev), torch.randn(reg.shape, generator=g).to(dev)
-    ((cls * wc).sum() + (reg * wr).sum()).backward()
+    L = (cls * wc).sum() + (reg * wr).sum()
+    if fuse_ab:
+        w1, w2 = torch.randn(cls_ab.shape, generator=g).to(dev), torch.randn(reg_ab.shape, generator=g).to(dev)
+        L = L + (cls_ab * w1).sum() + (reg_ab * w2).sum()
+    L.backward()
     torch.cuda.synchronize()
     assert [tuple(f.shape[2:]) for f in feats] == [(size // s, size // s) for s in om.CONFIGS[name]["strides"]]
 
     # ---- forward vs the oracle (bf16-storage train-mode network, float64 arithmetic)
-    ocls, oreg = oracle_forward(name, sd, x)
+    if fuse_ab:
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+        with torch.no_grad(), om.train_mode(), om.bf16_storage():
+            ocls, oreg, _, ocls_ab, oreg_ab = om.forward(sd64, om.CONFIGS[name], x.double(), train_outputs=True, fuse_ab=True)
+        e1 = float((cls_ab.detach().cpu().double() - ocls_ab).pow(2).mean().sqrt())
+        e2 = _rel(reg_ab.detach().cpu(), oreg_ab)
+        print(f"{name} fuse_ab: forward vs oracle: cls_ab rms {e1:.2e}, reg_ab rel L2 {e2:.2e}")
+        assert cls_ab.shape == ocls_ab.shape and reg_ab.shape == oreg_ab.shape and e1 < 2e-2 and e2 < 5e-2
+    else:
+        ocls, oreg = oracle_forward(name, sd, x)
     # (rounding differences between fp32 and float64 accumulation are amplified layer by layer by the
     # batch-statistics BatchNorm, so this end-to-end bar is an RMS one; each op is checked tightly below)
     e_cls = float((cls.detach().cpu().double() - ocls).pow(2).mean().sqrt())
@@ -127,7 +144,28 @@ def test_train_step_matches_reference_op_by_op(name, size, batch):
         src = None
         if op.kind != "stem":
             src = _nchw(sl(eng.bufs, op.src, op.cin)).requires_grad_(True)
-        if op.kind == "pred":                                   # effidehead.py:79-92 (train branch)
+        if op.kind == "pred" and op.head[0].endswith("_ab"):    # effidehead_fuseab.py:108-121: (b, na, h, w, .) rows, box transform
+            which, lvl = op.head
+            na = 3
+            w = _nchw(ctx["w"]).requires_grad_(True)
+            b = P[op.name + ".bias"].detach().double().requires_grad_(True)
+            y = F.conv2d(src, w, b)
+            B_, _, h_, w_ = y.shape
+            lo, hi = na * eng.offs[lvl], na * eng.offs[lvl + 1]
+            if which == "cls_ab":
+                yy = torch.sigmoid(y).reshape(B_, na, -1, h_, w_).permute(0, 1, 3, 4, 2).flatten(1, 3)
+                out, wt = eng.cls_ab, w1
+            else:
+                r = y.reshape(B_, na, -1, h_, w_).permute(0, 1, 3, 4, 2)
+                anc = (torch.tensor(gr.anchors_init[lvl], dtype=torch.float64, device=dev) / gr.strides[lvl]).reshape(1, na, 1, 1, 2)
+                yy = torch.cat([r[..., :2], ((r[..., 2:4].sigmoid() * 2) ** 2) * anc], -1).flatten(1, 3)
+                out, wt = eng.reg_ab, w2
+            worst["fwd"] = max(worst["fwd"], _rel(out[:, lo:hi], yy.detach()))
+            assert _rel(out[:, lo:hi], yy.detach()) < 1e-3, op.name
+            (yy * wt[:, lo:hi].double()).sum().backward()
+            check_param(op.name + ".weight", w.grad)
+            check_param(op.name + ".bias", b.grad)
+        elif op.kind == "pred":                                 # effidehead.py:79-92 (train branch)
             which, lvl = op.head
             w = _nchw(ctx["w"]).requires_grad_(True)
             b = P[op.name + ".bias"].detach().double().requires_grad_(True)

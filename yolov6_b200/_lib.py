@@ -58,7 +58,7 @@ class LossDesc(C.Structure):
         ("iou_type", C.c_int32),
         ("w_cls", C.c_double), ("w_iou", C.c_double), ("w_dfl", C.c_double), ("grad_scale", C.c_double),
         ("grad_scores", C.c_void_p), ("grad_distri", C.c_void_p), ("out", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("norm_gt_zero", C.c_int32),
     ]
 
 
@@ -144,6 +144,12 @@ _SIGNATURES = {
     "yv6_assign_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "yv6_head_ab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yv6_head_ab_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yv6_ab_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yv6_ab_boxes_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "yv6_box_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_void_p, C.c_void_p]),
     "yv6_det_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),

@@ -61,6 +61,8 @@ class Graph:
     bufs: List[Buf] = field(default_factory=list)
     ops: List[Op] = field(default_factory=list)
     feat: List[T] = field(default_factory=list)   # neck outputs (reference `featmaps`, yolo.py:37-39)
+    fuse_ab: bool = False
+    anchors_init: Optional[list] = None           # fuse_ab: per level [w0, h0, w1, h1, w2, h2] in pixels
 
     # -- builders ---------------------------------------------------------------------------
     def buf(self, level, c_total, name=""):
@@ -93,6 +95,7 @@ class Graph:
 
 
 DETECT_DEFAULT_REG_MAX = 16  # effidehead.py:16
+AB_ANCHORS = 3                # build_network passes num_anchors = 3 to the fuse_ab head (yolo.py:125)
 
 
 def make_divisible(x, divisor):
@@ -170,8 +173,9 @@ def _bifusion(g, name, x0, x1, x2, cout):
     return g.conv(name + ".cv3", "cba", T(cat, 0, 3 * cout), cout, 1, 1, "relu")
 
 
-def build_graph(cfg, num_classes=80, name="yolov6"):
-    """cfg: dict with the fields of the reference's `config.model` (see configs.py / config_from_reference)."""
+def build_graph(cfg, num_classes=80, name="yolov6", fuse_ab=False):
+    """cfg: dict with the fields of the reference's `config.model` (see configs.py / config_from_reference).
+    fuse_ab: add the anchor-aided training branch of effidehead_fuseab.py (two more 1x1 pred convs per level)."""
     depth, width = cfg["depth_multiple"], cfg["width_multiple"]
     bb, nk, hd = cfg["backbone"], cfg["neck"], cfg["head"]
     reps = [(max(round(i * depth), 1) if i > 1 else i) for i in bb["num_repeats"] + nk["num_repeats"]]   # yolo.py:66
@@ -260,6 +264,15 @@ def build_graph(cfg, num_classes=80, name="yolov6"):
         rf = g.conv(f"detect.reg_convs.{i}", "cba", st, c, 3, 1, "silu")
         g.ops.append(Op("pred", f"detect.cls_preds.{i}", "plain", cf, None, c, num_classes, 1, 1, "sigmoid", head=("cls", i)))
         g.ops.append(Op("pred", f"detect.reg_preds.{i}", "plain", rf, None, c, reg_ch, 1, 1, None, head=("reg", i)))
+        if fuse_ab:     # effidehead_fuseab.py:44-55,112-118: num_anchors = 3 class / box predictions per pixel, training only
+            g.ops.append(Op("pred", f"detect.cls_preds_ab.{i}", "plain", cf, None, c, num_classes * AB_ANCHORS, 1, 1, "sigmoid", head=("cls_ab", i)))
+            g.ops.append(Op("pred", f"detect.reg_preds_ab.{i}", "plain", rf, None, c, 4 * AB_ANCHORS, 1, 1, None, head=("reg_ab", i)))
+    g.fuse_ab = bool(fuse_ab)
+    if fuse_ab:
+        ai = hd.get("anchors_init")
+        if ai is None or len(ai) != nl or any(len(a) != 2 * AB_ANCHORS for a in ai):
+            raise ValueError("fuse_ab needs cfg.model.head.anchors_init with 3 (w, h) pairs per level (configs/yolov6*.py)")
+        g.anchors_init = [[float(v) for v in a] for a in ai]
     return g
 
 

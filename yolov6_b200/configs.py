@@ -4,6 +4,7 @@ the reference's own mmcv-style Config object (yolov6/utils/config.py) for drop-i
 import copy
 
 _P5_HEAD = dict(type="EffiDeHead", in_channels=[128, 256, 512], num_layers=3, begin_indices=24, anchors=3,
+                anchors_init=[[10, 13, 19, 19, 33, 23], [30, 61, 59, 59, 59, 119], [116, 90, 185, 185, 373, 326]],   # fuse_ab head
                 out_indices=[17, 20, 23], strides=[8, 16, 32], atss_warmup_epoch=0)
 
 CONFIGS = {

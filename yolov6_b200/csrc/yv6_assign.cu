@@ -19,7 +19,7 @@
 
 namespace yv6 {
 
-constexpr int kTopkMax = 16;
+constexpr int kTopkMax = 32;   // 13 in ComputeLoss (loss.py:41), 26 in the fuse_ab loss (loss_fuseab.py:40)
 constexpr int kAssignThreads = 256;
 
 // ------------------------------------------------------------------------------------------------

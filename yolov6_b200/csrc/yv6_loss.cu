@@ -183,6 +183,7 @@ struct LossParams {
   float* grad_scores;     // [B,A,nc]
   float* grad_distri;     // [B,A,R]
   double* partial;        // [4][nblk_max] : tss, cls, iou, dfl partial sums
+  double norm_thr;        // divide by target_scores_sum when it exceeds this: 1 (loss.py:168-169) or 0 (loss_fuseab.py:139, 203-206)
   double* out;            // [8]: loss, w_iou*iou, w_dfl*dfl, w_cls*cls, tss, num_pos, raw sums...
   int32_t nblk_rows, nblk_cls, nblk_box;
 };
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_cls_kernel(const LossParams
   const int warps = blockDim.x >> 5;
   const int64_t rows = (int64_t)p.B * p.A;
   const double tss = p.out[4];
-  const double denom = (tss > 1.0) ? tss : 1.0;                       // loss.py:168-169
+  const double denom = (tss > p.norm_thr) ? tss : 1.0;                       // loss.py:168-169
   const double gscale = p.w_cls * p.grad_scale / denom;
   double acc = 0.0;
   for (int64_t row = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * warps) {
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_box_kernel(const LossParams
     } else {
       const int a = (int)(o % p.A), b = (int)(o / p.A);
       const double tss = p.out[4];
-      const double denom = (tss > 1.0) ? tss : 1.0;
+      const double denom = (tss > p.norm_thr) ? tss : 1.0;
       const double bw = p.norm[o];                                    // bbox_weight = sum_c target_scores
       const float* reg = p.distri + o * p.R;
       const float s = p.strides[a];
@@ -342,7 +343,7 @@ __global__ void loss_final_kernel(const LossParams p) {
     dfl += p.partial[3 * p.nblk_rows + p.nblk_box + i];
   }
   const double tss = p.out[4];
-  const double denom = (tss > 1.0) ? tss : 1.0;
+  const double denom = (tss > p.norm_thr) ? tss : 1.0;
   cls /= denom;
   iou /= denom;
   dfl = p.use_dfl ? dfl / denom : 0.0;
@@ -389,6 +390,7 @@ extern "C" int yv6_det_loss(yv6_handle* h, const yv6_loss_desc* d, void* stream)
   p.B = d->B; p.A = d->A; p.G = d->G; p.nc = d->nc; p.R = d->reg_ch; p.reg_max = d->reg_ch / 4 - 1;
   p.use_dfl = (d->reg_ch > 4); p.iou_type = d->iou_type;
   p.w_cls = d->w_cls; p.w_iou = d->w_iou; p.w_dfl = d->w_dfl; p.grad_scale = d->grad_scale;
+  p.norm_thr = d->norm_gt_zero ? 0.0 : 1.0;
   p.grad_scores = d->grad_scores; p.grad_distri = d->grad_distri;
   p.partial = reinterpret_cast<double*>(d->workspace);
   p.out = d->out;

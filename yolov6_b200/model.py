@@ -73,6 +73,13 @@ class Detect(Node):
         for conv in self.reg_preds:
             conv.bias.data.fill_(1.0)
             conv.weight.data.fill_(0.)
+        if "cls_preds_ab" in self._modules:         # effidehead_fuseab.py:65-87
+            for conv in self.cls_preds_ab:
+                conv.bias.data.fill_(-math.log((1 - self.prior_prob) / self.prior_prob))
+                conv.weight.data.fill_(0.)
+            for conv in self.reg_preds_ab:
+                conv.bias.data.fill_(1.0)
+                conv.weight.data.fill_(0.)
         self.proj.data.copy_(torch.linspace(0, self.reg_max, self.reg_max + 1))
         self.proj_conv.weight.data.copy_(self.proj.view(1, self.reg_max + 1, 1, 1))
 
@@ -82,9 +89,10 @@ class Model(nn.Module):
 
     def __init__(self, config, channels=3, num_classes=None, fuse_ab=False, distill_ns=False):
         super().__init__()
-        if fuse_ab or distill_ns:
-            raise NotImplementedError("fuse_ab / distill_ns heads are outside the hot-path scope (SURVEY.md 8f N3)")
+        if distill_ns:
+            raise NotImplementedError("the distill_ns head (effidehead_distill_ns.py) is not built (SURVEY.md 8f N3, second half)")
         assert channels == 3
+        self.fuse_ab = bool(fuse_ab)
         self.cfg = configs.normalize(config)
         self.num_classes = int(num_classes if num_classes is not None else 80)
         g = self.graph
@@ -92,8 +100,11 @@ class Model(nn.Module):
         self.backbone, self.neck = Node(), Node()
         # build_network passes use_dfl but not reg_max to Detect (yolo.py:130-131)
         self.detect = Detect(self.num_classes, hd["num_layers"], bool(hd["use_dfl"]), arch.DETECT_DEFAULT_REG_MAX)
-        for name in ("stems", "cls_convs", "reg_convs", "cls_preds", "reg_preds"):
+        for name in ("stems", "cls_convs", "reg_convs", "cls_preds", "reg_preds") + (("cls_preds_ab", "reg_preds_ab") if self.fuse_ab else ()):
             self.detect.add_module(name, Node())
+        if self.fuse_ab:        # effidehead_fuseab.py:20-35
+            self.detect.na = arch.AB_ANCHORS
+            self.detect.anchors_init = (torch.tensor(g.anchors_init) / self.detect.stride[:, None]).reshape(hd["num_layers"], arch.AB_ANCHORS, 2)
         self._materialize(g)
         self.stride = self.detect.stride
         self.detect.initialize_biases()
@@ -110,7 +121,7 @@ class Model(nn.Module):
     def graph(self):
         g = self.__dict__.get("_graph")
         if g is None:
-            g = arch.build_graph(self.cfg, self.num_classes)
+            g = arch.build_graph(self.cfg, self.num_classes, fuse_ab=self.__dict__.get("fuse_ab", False))
             self.__dict__["_graph"] = g
         return g
 
@@ -199,8 +210,12 @@ class Model(nn.Module):
             # effidehead.py:72-92); `feats` carry only the level shapes ComputeLoss needs (loss.py:63-68)
             from .train import train_forward
             eng = self.train_engine()
-            cls, reg = train_forward(eng, x)
+            outs = train_forward(eng, x)
             feats = [torch.empty(x.shape[0], 1, h, w, device=x.device) for h, w in eng.sizes]
+            if self.fuse_ab:       # effidehead_fuseab.py:140: (x, cls_ab, reg_ab, cls_af, reg_af); engine.py:161-166 slices it
+                cls, reg, cls_ab, reg_ab = outs
+                return [(feats, cls_ab, reg_ab, cls, reg), feats]
+            cls, reg = outs
             return [(feats, cls, reg), feats]
         export_mode = torch.onnx.is_in_onnx_export() or self.export
         eng = self.engine()

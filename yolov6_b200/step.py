@@ -26,6 +26,9 @@ from .dist import GradSync
 class TrainStep:
     def __init__(self, model, compute_loss, batch, height, width, in_dtype=torch.float32, max_targets=None, max_gt=64,
                  optimizer=None, n_buckets=None, graph=True, group=None):
+        if getattr(model, "fuse_ab", False):
+            raise NotImplementedError("TrainStep (the CUDA-graph fast path) drives the anchor-free loss only; train fuse_ab models through "
+                                      "the compatible path: model(x) -> ComputeLoss + loss_fuseab.ComputeLoss -> backward()")
         self.model = model.train()
         self.loss = compute_loss
         self.dev = next(model.parameters()).device

@@ -420,6 +420,13 @@ class TrainEngine:
         self.reg = torch.empty(N, A, 4 * (g.reg_max + 1), dtype=torch.float32, device=dev)
         self.grad_cls = torch.zeros_like(self.cls)
         self.grad_reg = torch.zeros_like(self.reg)
+        if getattr(g, "fuse_ab", False):      # anchor-aided branch (effidehead_fuseab.py:94-140): 3 anchors per pixel, rows (level, anchor, pixel)
+            from .arch import AB_ANCHORS
+            self.cls_ab = torch.empty(N, AB_ANCHORS * A, g.num_classes, dtype=torch.float32, device=dev)
+            self.reg_ab = torch.empty(N, AB_ANCHORS * A, 4, dtype=torch.float32, device=dev)
+            self.grad_cls_ab = torch.zeros_like(self.cls_ab)
+            self.grad_reg_ab = torch.zeros_like(self.reg_ab)
+            self._ab = {}                     # level -> dict(raw_cls, raw_reg, dl_cls, dl_reg, anchors)
         self.x_static = torch.zeros(N, 3, H, W, dtype=in_dtype, device=dev)   # the stem reads this buffer (graph-stable address)
         view = lambda t: (self.bufs[t.buf], self.gbufs[t.buf])   # noqa: E731
         # shared scratch: BN-backward outputs (gradients w.r.t. the raw conv outputs) live only until their dgrad / wgrad ran
@@ -448,6 +455,31 @@ class TrainEngine:
                 bwd_rev.append(calls)
                 continue
             Wt = self.wts[i]
+            if op.kind == "pred" and op.head[0].endswith("_ab"):
+                # fuse_ab pred conv: natural NHWC output [N, hw, na * ch] (fp32, sigmoid fused on the class branch); the pack /
+                # grad kernels (csrc/yv6_fuseab.cu) move between it and the reference's (level, anchor, pixel) row order
+                from .arch import AB_ANCHORS
+                src, gsrc = view(op.src)
+                which, lvl = op.head
+                lh, lw = self.sizes[lvl]
+                ch, chp = op.cout, (op.cout + 15) // 16 * 16
+                st = self._ab.setdefault(lvl, {})
+                raw = torch.empty(N, lh * lw, ch, dtype=torch.float32, device=dev)
+                dl = bf(N, lh, lw, chp)
+                st["raw_" + which[:3]], st["dl_" + which[:3]] = raw, dl
+                fwd.append(("conv", self._conv_desc(src, op.src.c_off, op.cin, Wt["w"], raw, 0, op.cout, 1, 1, bias=Wt["bias"], act=op.act,
+                                                    y_f32=True, y_strides=(lh * lw * ch, lw * ch, ch), y_elem_off=0)))
+                if which == "reg_ab":          # second of the level's pair in forward order, first in backward order
+                    anc = [v / float(g.strides[lvl]) for v in g.anchors_init[lvl]]          # effidehead_fuseab.py:35
+                    st["anchors"] = (C.c_float * 6)(*anc)
+                    fwd.append(("abp", lvl))
+                    calls.append(("abg", lvl))
+                calls.append(("wgrad", self._wgrad_desc(src, op.src.c_off, op.cin, dl, 0, ch, 1, 1, z(i, "dw"))))
+                calls.append(("stats", self._stats_desc([(dl, 0)], chp, N * lh * lw, z(i, "bsum"), z(i, "bcnt"))))
+                calls.append(("conv", self._conv_desc(dl, 0, chp, Wt["wt"], gsrc, op.src.c_off, op.cin, 1, 1, accumulate=True),
+                              dict(buf=op.src.buf, off=op.src.c_off, n=op.cin, full=True)))
+                bwd_rev.append(calls)
+                continue
             if op.kind == "pred":
                 src, gsrc = view(op.src)
                 which, lvl = op.head
@@ -684,10 +716,28 @@ class TrainEngine:
                 chk(lib.yv6_bn_apply_fwd(h, C.byref(d), sp))
             elif kind == "stem":
                 chk(lib.yv6_stem_fwd(h, C.byref(d), sp))
+            elif kind == "abp":
+                self._ab_call(d, False, sp)
             else:
                 chk(lib.yv6_sppf_pool(h, C.c_void_p(d[0]), d[1], d[2], d[3], d[4], d[5], d[6], d[7], sp))
 
-    def backward(self, grad_cls, grad_reg, accumulate=False, first=0, last=None):
+    def _ab_call(self, lvl, backward, sp):
+        """fuse_ab level `lvl`: natural-order conv outputs -> (cls_ab, reg_ab) rows, or their gradients -> dense bf16 gradients."""
+        from .arch import AB_ANCHORS
+        st = self._ab[lvl]
+        N = self.cls_ab.shape[0]
+        lh, lw = self.sizes[lvl]
+        nc, A3 = self.g.num_classes, self.cls_ab.shape[1]
+        off3 = AB_ANCHORS * self.offs[lvl]
+        if not backward:
+            _lib.check(self.lib.yv6_head_ab_pack(self.h, _p(st["raw_cls"]), _p(st["raw_reg"]), N, lh * lw, AB_ANCHORS, nc, st["anchors"],
+                                                 off3, A3, _p(self.cls_ab), _p(self.reg_ab), sp))
+        else:
+            _lib.check(self.lib.yv6_head_ab_grad(self.h, _p(self.grad_cls_ab), _p(self.cls_ab), _p(self.grad_reg_ab), _p(st["raw_reg"]), N,
+                                                 lh * lw, AB_ANCHORS, nc, st["anchors"], off3, A3, st["dl_cls"].shape[3], st["dl_reg"].shape[3],
+                                                 _p(st["dl_cls"]), _p(st["dl_reg"]), sp))
+
+    def backward(self, grad_cls, grad_reg, accumulate=False, first=0, last=None, grad_cls_ab=None, grad_reg_ab=None):
         """Writes d(loss)/d(parameter) of every trainable parameter into the flat gradient buffer (`accumulate`: adds to it)
         given d(loss)/d(cls), d(loss)/d(reg) ([N,A,*] fp32).  `first`/`last` restrict the run to a slice of the call list
         (graph capture in bucket-sized segments)."""
@@ -695,6 +745,12 @@ class TrainEngine:
             self.grad_cls.copy_(grad_cls)
         if grad_reg is not None and grad_reg.data_ptr() != self.grad_reg.data_ptr():
             self.grad_reg.copy_(grad_reg)
+        if getattr(self.g, "fuse_ab", False) and first == 0:      # a missing gradient of the anchor-aided branch means "no loss on it"
+            for buf, gr in ((self.grad_cls_ab, grad_cls_ab), (self.grad_reg_ab, grad_reg_ab)):
+                if gr is None:
+                    buf.zero_()
+                elif gr.data_ptr() != buf.data_ptr():
+                    buf.copy_(gr)
         lib, h, chk = self.lib, self.h, _lib.check
         sp = _lib.stream_ptr()
         if first == 0:
@@ -747,6 +803,8 @@ class TrainEngine:
                 if overlap:
                     wait_pending()
                 d[0].copy_(d[1])
+            elif kind == "abg":
+                self._ab_call(d, True, sp)
             elif kind == "hgp":
                 chk(lib.yv6_head_grad_prep(h, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], sp))
             elif kind == "pool_bwd":
@@ -779,12 +837,18 @@ class _HeadFn(torch.autograd.Function):
     def forward(ctx, engine, x, *params):
         ctx.engine = engine
         cls, reg = engine.forward(x)
+        if getattr(engine.g, "fuse_ab", False):
+            return cls.clone(), reg.clone(), engine.cls_ab.clone(), engine.reg_ab.clone()
         return cls.clone(), reg.clone()
 
     @staticmethod
-    def backward(ctx, g_cls, g_reg):
+    def backward(ctx, g_cls, g_reg, g_cls_ab=None, g_reg_ab=None):
         eng = ctx.engine
-        eng.backward(g_cls.contiguous().float(), g_reg.contiguous().float())
+        f = lambda t: None if t is None else t.contiguous().float()   # noqa: E731
+        # an output the loss did not use has no gradient: zero (None would mean "the engine's own buffer is already filled")
+        g_cls = torch.zeros_like(eng.grad_cls) if g_cls is None else g_cls
+        g_reg = torch.zeros_like(eng.grad_reg) if g_reg is None else g_reg
+        eng.backward(f(g_cls), f(g_reg), grad_cls_ab=f(g_cls_ab), grad_reg_ab=f(g_reg_ab))
         flat = eng.flat
         g = flat.gflat.clone()          # autograd may keep (steal) what it is given; the flat buffer is reused next step
         grads = []
