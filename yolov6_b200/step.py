@@ -25,12 +25,14 @@ from .dist import GradSync
 
 class TrainStep:
     def __init__(self, model, compute_loss, batch, height, width, in_dtype=torch.float32, max_targets=None, max_gt=64,
-                 optimizer=None, n_buckets=None, graph=True, group=None):
-        if getattr(model, "fuse_ab", False):
-            raise NotImplementedError("TrainStep (the CUDA-graph fast path) drives the anchor-free loss only; train fuse_ab models through "
-                                      "the compatible path: model(x) -> ComputeLoss + loss_fuseab.ComputeLoss -> backward()")
+                 optimizer=None, n_buckets=None, graph=True, group=None, compute_loss_ab=None):
+        self.fuse_ab = bool(getattr(model, "fuse_ab", False))
+        if self.fuse_ab and compute_loss_ab is None:
+            raise ValueError("a fuse_ab model needs compute_loss_ab (yolov6_b200.loss_fuseab.ComputeLoss): core/engine.py:161-166 adds "
+                             "the anchor-aided loss to the anchor-free one")
         self.model = model.train()
         self.loss = compute_loss
+        self.loss_ab = compute_loss_ab
         self.dev = next(model.parameters()).device
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         if n_buckets is None:
@@ -65,6 +67,14 @@ class TrainStep:
             eng.run_forward(sp)
             self.state = self.loss.forward_backward(eng.cls, eng.reg, self.sizes, self.targets, epoch_num, self.H, self.W,
                                                     max_gt=self.max_gt, grad_scores=eng.grad_cls, grad_distri=eng.grad_reg)
+            if self.fuse_ab:      # total_loss += total_loss_ab; loss_items += loss_items_ab (core/engine.py:164-166)
+                st_ab = self.loss_ab.forward_backward(eng.cls_ab, eng.reg_ab, self.sizes, self.targets, epoch_num, self.H, self.W,
+                                                      max_gt=self.max_gt, grad_scores=eng.grad_cls_ab, grad_distri=eng.grad_reg_ab)
+                self.state["out_af"], self.state["out_ab"] = self.state["out"], st_ab["out"]
+                total = self.state["out"].clone()
+                total[:4] += st_ab["out"][:4]
+                self.state["out"] = total
+                self.state["keep_ab"] = st_ab
         eng.backward(None, None, accumulate=self.accumulate, first=firsts[j], last=lasts[j])
 
     def _capture(self, epoch_num):

@@ -745,11 +745,9 @@ class TrainEngine:
             self.grad_cls.copy_(grad_cls)
         if grad_reg is not None and grad_reg.data_ptr() != self.grad_reg.data_ptr():
             self.grad_reg.copy_(grad_reg)
-        if getattr(self.g, "fuse_ab", False) and first == 0:      # a missing gradient of the anchor-aided branch means "no loss on it"
+        if getattr(self.g, "fuse_ab", False) and first == 0:      # None = the engine's own buffers were filled by the loss kernels
             for buf, gr in ((self.grad_cls_ab, grad_cls_ab), (self.grad_reg_ab, grad_reg_ab)):
-                if gr is None:
-                    buf.zero_()
-                elif gr.data_ptr() != buf.data_ptr():
+                if gr is not None and gr.data_ptr() != buf.data_ptr():
                     buf.copy_(gr)
         lib, h, chk = self.lib, self.h, _lib.check
         sp = _lib.stream_ptr()
@@ -848,6 +846,9 @@ class _HeadFn(torch.autograd.Function):
         # an output the loss did not use has no gradient: zero (None would mean "the engine's own buffer is already filled")
         g_cls = torch.zeros_like(eng.grad_cls) if g_cls is None else g_cls
         g_reg = torch.zeros_like(eng.grad_reg) if g_reg is None else g_reg
+        if getattr(eng.g, "fuse_ab", False):
+            g_cls_ab = torch.zeros_like(eng.grad_cls_ab) if g_cls_ab is None else g_cls_ab
+            g_reg_ab = torch.zeros_like(eng.grad_reg_ab) if g_reg_ab is None else g_reg_ab
         eng.backward(f(g_cls), f(g_reg), grad_cls_ab=f(g_cls_ab), grad_reg_ab=f(g_reg_ab))
         flat = eng.flat
         g = flat.gflat.clone()          # autograd may keep (steal) what it is given; the flat buffer is reused next step
