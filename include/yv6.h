@@ -133,6 +133,8 @@ typedef struct yv6_stem_desc {
   int32_t nsplit;           /* 1 or 3                                                           */
   int32_t fp32_math;        /* nsplit == 1 only: 1 = fp32 image / weights on CUDA cores (training), 0 = bf16
                                image / weights on tensor cores (inference)                          */
+  int32_t force_sync_loads; /* ABI 3, tuning: 1 = register-prefetch kernel even where the cp.async ring variant applies
+                               (fp32 images with 16-byte aligned rows) */
 } yv6_stem_desc;
 int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream);
 

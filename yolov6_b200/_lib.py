@@ -46,6 +46,7 @@ class StemDesc(C.Structure):
         ("w", C.c_void_p), ("bias", C.c_void_p),
         ("Cout", C.c_int32), ("act", C.c_int32),
         ("y", C.c_void_p), ("y_plane_stride", C.c_int64), ("nsplit", C.c_int32), ("fp32_math", C.c_int32),
+        ("force_sync_loads", C.c_int32),
     ]
 
 

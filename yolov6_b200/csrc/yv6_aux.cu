@@ -275,6 +275,160 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const StemParams p) {
   }
 }
 
+// fp32 images, asynchronous variant: the register prefetch above keeps 13 KB per CTA (26 KB per SM) of loads in flight, ~60 % of
+// what HBM latency x bandwidth asks for (the kernel ran at 2.6 of 6.5 TB/s).  Here the input patch of a tile is copied global ->
+// shared with cp.async (16-byte groups, zero fill outside the image) into a ring of three fp32 patches; two tiles are always in
+// flight per CTA (56 KB per SM at two resident CTAs) and no register holds prefetched data.  The A fragments are gathered from the
+// fp32 patch and rounded to bf16 on the way (cvt.rn.bf16x2), everything downstream is the kernel above.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int COUT>
+__global__ void __launch_bounds__(256, 2) stem_mma_async_kernel(const StemParams p) {
+  constexpr int TH = 8, TW = 32, PH = 2 * TH + 1, NT = COUT / 8;
+  constexpr int PWP = 72;                                  // fp32 patch row pitch; element j = input column 64 * tw + j - 4
+  constexpr int PATCH = 3 * PH * PWP;                      // floats per stage
+  constexpr int STAGES = 3;
+  constexpr int PITCH = COUT * 2 + 16;
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  float* ring = reinterpret_cast<float*>(stem_smem);
+  uint8_t* stage = stem_smem + (size_t)STAGES * PATCH * sizeof(float);
+  const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
+  const int num_tiles = tiles_w * tiles_h * p.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+  uint32_t bfrag[NT][2][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int k = ks * 16 + h2 * 8 + 2 * t, nn = nt * 8 + g;
+        const float w0 = (k < 27) ? __ldg(p.w + k * COUT + nn) : 0.f;
+        const float w1 = (k + 1 < 27) ? __ldg(p.w + (k + 1) * COUT + nn) : 0.f;
+        __nv_bfloat162 v = __floats2bfloat162_rn(w0, w1);
+        bfrag[nt][ks][h2] = *reinterpret_cast<uint32_t*>(&v);
+      }
+  float bias[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    bias[nt][0] = p.b ? __ldg(p.b + nt * 8 + 2 * t) : 0.f;
+    bias[nt][1] = p.b ? __ldg(p.b + nt * 8 + 2 * t + 1) : 0.f;
+  }
+  int koff[2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = ks * 16 + h2 * 8 + 2 * t + e;
+        const int tap = k / 3, c = k - 3 * tap, r = tap / 3, sx = tap - 3 * r;
+        koff[ks][h2][e] = (k < 27) ? (c * PH + r) * PWP + sx + 3 : -1;   // input column 64 tw + 2 px + sx - 1 -> element 2 px + sx + 3
+      }
+  uint8_t* wstage = stage + warp * 32 * PITCH;
+  const float* X = reinterpret_cast<const float*>(p.x);
+
+  auto issue = [&](int tile, int slot) {     // one commit group per tile (possibly empty past the end: keeps the group count uniform)
+    if (tile < num_tiles) {
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+      const int hi0 = 2 * th * TH - 1, wc0 = 64 * tw;      // first 16-byte group starts at input column 64 tw
+      float* dst0 = ring + (size_t)slot * PATCH;
+      for (int item = threadIdx.x; item < 3 * PH * 17; item += 256) {
+        const int rc = item / 17, q = item - rc * 17;
+        const int row = rc % PH, c = rc / PH;
+        const int hi = hi0 + row;
+        const bool row_ok = (hi >= 0 && hi < p.H);
+        const float* src_row = X + (((int64_t)n * 3 + c) * p.H + (row_ok ? hi : 0)) * p.W;
+        float* d = dst0 + rc * PWP;
+        if (q == 0) {                                        // the single column left of the first group
+          const int col = wc0 - 1;
+          const bool ok = row_ok && col >= 0;
+          cp_async4(d + 3, src_row + (ok ? col : 0), ok ? 4 : 0);
+        } else {
+          const int col = wc0 + 4 * (q - 1);
+          const int nb = row_ok ? max(0, min(16, (p.W - col) * 4)) : 0;
+          cp_async16(d + 4 + 4 * (q - 1), src_row + (nb > 0 ? col : 0), nb);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  issue(blockIdx.x, 0);
+  issue(blockIdx.x + gridDim.x, 1);
+  int slot = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int px0 = tw * TW, py0 = th * TH;
+    cp_async_wait<1>();                                    // this tile's patch has landed (the next one may still be in flight)
+    __syncthreads();                                       // ... for every thread's copies; the slot refilled below was read last iteration
+    issue(tile + 2 * gridDim.x, (slot + 2) % STAGES);
+    const float* P = ring + (size_t)slot * PATCH;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int base0 = (2 * warp) * PWP + 2 * (mt * 16 + g), base1 = base0 + 16;   // pixels g and g + 8
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int o0 = koff[ks][h2][0], o1 = koff[ks][h2][1];
+          const float l0 = o0 >= 0 ? P[base0 + o0] : 0.f, h0 = o1 >= 0 ? P[base0 + o1] : 0.f;
+          const float l1 = o0 >= 0 ? P[base1 + o0] : 0.f, h1 = o1 >= 0 ? P[base1 + o1] : 0.f;
+          __nv_bfloat162 q0 = __floats2bfloat162_rn(l0, h0), q1 = __floats2bfloat162_rn(l1, h1);
+          a[2 * h2 + 0] = *reinterpret_cast<uint32_t*>(&q0);
+          a[2 * h2 + 1] = *reinterpret_cast<uint32_t*>(&q1);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+              : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfrag[nt][ks][0]), "r"(bfrag[nt][ks][1]));
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float v0 = act_apply(acc[mt][nt][0] + bias[nt][0], p.act), v1 = act_apply(acc[mt][nt][1] + bias[nt][1], p.act);
+        const float v2 = act_apply(acc[mt][nt][2] + bias[nt][0], p.act), v3 = act_apply(acc[mt][nt][3] + bias[nt][1], p.act);
+        *reinterpret_cast<__nv_bfloat162*>(wstage + (mt * 16 + g) * PITCH + (nt * 8 + 2 * t) * 2) = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<__nv_bfloat162*>(wstage + (mt * 16 + g + 8) * PITCH + (nt * 8 + 2 * t) * 2) = __floats2bfloat162_rn(v2, v3);
+      }
+    __syncwarp();
+    const int py = py0 + warp;
+    if (py < p.Ho) {
+      const int valid = min(TW, p.Wo - px0);
+      __nv_bfloat16* dst = p.y + (((int64_t)n * p.Ho + py) * p.Wo + px0) * COUT;
+      constexpr int CPP = COUT / 8;
+      for (int i = lane; i < valid * CPP; i += 32) {
+        const int px = i / CPP, part = i - px * CPP;
+        reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(wstage + px * PITCH + part * 16);
+      }
+    }
+    __syncwarp();
+    slot = (slot + 1) % STAGES;
+  }
+  cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------------------------------------
 // SPPF pooling: reference SPPFModule / CSPSPPFModule (common.py:106-112, 150-158):
 //   y1 = pool5(x), y2 = pool5(y1), y3 = pool5(y2), cat([x, y1, y2, y3]).
@@ -553,6 +707,26 @@ extern "C" int yv6_stem_fwd(yv6_handle* h, const yv6_stem_desc* d, void* stream)
     // bf16 activations: tensor-core path (bf16 image / weights, fp32 accumulate)
     const unsigned ntile = (unsigned)(((p.Wo + 31) / 32) * ((p.Ho + 7) / 8) * p.N);
     const unsigned tiles = std::min<unsigned>(ntile, (unsigned)h->num_sms * 2);   // persistent CTAs, two resident per SM (register budget)
+    // fp32 images whose rows are 16-byte aligned: asynchronous shared-memory ring (3 x 14.7 KB patches + the output staging)
+    if (!p.x_u8 && p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (d->Cout == 16 || d->Cout == 32 || d->Cout == 48 || d->Cout == 64) &&
+        d->force_sync_loads == 0) {
+      const size_t smem = (size_t)3 * 3 * 17 * 72 * 4 + (size_t)8 * 32 * (d->Cout * 2 + 16);
+      if (!(h->configured & YV6_CFG_STEM)) {
+        YV6_CHECK_CUDA(cudaFuncSetAttribute(stem_mma_async_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        YV6_CHECK_CUDA(cudaFuncSetAttribute(stem_mma_async_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        YV6_CHECK_CUDA(cudaFuncSetAttribute(stem_mma_async_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        YV6_CHECK_CUDA(cudaFuncSetAttribute(stem_mma_async_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        h->configured |= YV6_CFG_STEM;
+      }
+      switch (d->Cout) {
+        case 16: stem_mma_async_kernel<16><<<tiles, 256, smem, s>>>(p); break;
+        case 32: stem_mma_async_kernel<32><<<tiles, 256, smem, s>>>(p); break;
+        case 48: stem_mma_async_kernel<48><<<tiles, 256, smem, s>>>(p); break;
+        default: stem_mma_async_kernel<64><<<tiles, 256, smem, s>>>(p); break;
+      }
+      YV6_CHECK_CUDA(cudaGetLastError());
+      return YV6_OK;
+    }
     switch (d->Cout) {
       case 16: stem_mma_kernel<16><<<tiles, 256, 0, s>>>(p); break;
       case 32: stem_mma_kernel<32><<<tiles, 256, 0, s>>>(p); break;
