@@ -127,7 +127,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
   } else if (warp == 1) {
     // instruction descriptor: bf16 x bf16 -> fp32, both operands MN-major (bits 15 / 16), M = 128, N = NT
-    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.NT) | (1u << 15) | (1u << 16);
+    // When a tap's X tile is a single channel block (Cin tile <= 64), the T taps of the stage are just consecutive blocks of
+    // one wider MN-major operand (block stride = LBO = one tap tile): ONE instruction of N = T * NT per K step replaces T
+    // instructions of N = NT, so the dY operand is read once instead of T times (64-channel layers are bound by exactly that
+    // shared-memory traffic).  The accumulator columns are the same (tap t at t * NT), so the epilogue does not change.
+    const bool merged = (p.b_blocks == 1 && p.T > 1 && p.T * p.NT <= 256 && p.b_tap_bytes == p.PT * p.b_blk_bytes);
+    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)(merged ? p.T * p.NT : p.NT)) | (1u << 15) | (1u << 16);
     const uint64_t da = wg_desc(a_blk_bytes, 1024u, 2u);
     const uint64_t db = wg_desc((uint32_t)(p.PT * p.b_blk_bytes), (uint32_t)p.b_sbo, (uint32_t)p.b_layout);
     const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
@@ -142,7 +147,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const uint64_t ad = da | (uint64_t)(a_base + (uint32_t)stage * a_step);
       const uint64_t bd = db | (uint64_t)(b_base + (uint32_t)stage * b_step);
       if (elect_one()) {
-        for (int t = 0; t < p.T; ++t) {
+        for (int t = 0; t < (merged ? 1 : p.T); ++t) {
           const uint64_t bt = bd + (uint64_t)((uint32_t)t * b_tap);
           const uint32_t acc = tmem_base + (uint32_t)(t * p.NT);
 #pragma unroll 4
