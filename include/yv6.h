@@ -283,6 +283,16 @@ int yv6_ab_boxes(yv6_handle* h, const float* reg_ab, const float* anc_points, co
                  float* ltrb, float* boxes_px, void* stream);
 int yv6_ab_boxes_bwd(yv6_handle* h, const float* grad_ltrb, int64_t rows, float* grad_reg_ab, void* stream);
 
+/* Self-distillation terms (losses/loss_distill.py:213-222 distill_loss_cls, :351-361 distill_loss_dfl): over `rows` rows of C
+ * fp32 "logits" (student / teacher, contiguous), adds  eff * sum_rows KL(softmax(teacher/T) || softmax(student/T))  to *acc
+ * (device double) and  eff * (softmax(student/T) - softmax(teacher/T)) / T  to grad (fp32, same shape as student; may be NULL).
+ * row_mask (may be NULL): row r takes part iff row_mask[r / rows_per_mask] != 0 (the 4 sides of positive anchors).
+ * eff = scale; if count_ptr != NULL: scale / (rows_per_mask * *count_ptr) (mean over the active rows, count on the device);
+ * if gate_ptr != NULL and *gate_ptr <= 0: 0. */
+int yv6_kl_rows(yv6_handle* h, const float* student, const float* teacher, int64_t rows, int32_t C, float temperature,
+                const uint8_t* row_mask, int32_t rows_per_mask, double scale, const double* count_ptr, const double* gate_ptr,
+                double* acc, float* grad, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Training of the conv stack (train form): what autograd + cuDNN do for the reference's
  * Trainer.train_in_steps (yolov6/core/engine.py:142-176) under ConvModule.forward (conv -> BN(batch

@@ -99,10 +99,11 @@ def decode_pred(pred_distri, anchor_points_s, use_dfl, reg_max):
 
 def compute_loss(sizes, pred_scores, pred_distri, targets, *, strides, num_classes=80, ori_img_size=640,
                  warmup_epoch=0, epoch_num=0, use_dfl=False, reg_max=0, iou_type="giou",
-                 loss_weight=None, return_assign=False):
+                 loss_weight=None, return_assign=False, norm_gt_zero=False):
     """sizes: [(h,w)] per level; pred_scores [B,A,nc] (post-sigmoid), pred_distri [B,A,4*(reg_max+1)];
     targets [n,6].  Returns (loss, loss_items[iou, dfl, cls]) like the reference."""
     lw = loss_weight or {"class": 1.0, "iou": 2.5, "dfl": 0.5}
+    norm_thr = 0 if norm_gt_zero else 1      # loss.py:168-169 divides when the sum exceeds 1, loss_distill.py / loss_fuseab.py when it is > 0
     B = pred_scores.shape[0]
     anchors, anchor_points, n_list, stride_t = assign.train_anchors(sizes, strides, dtype=pred_scores.dtype)
     scale = torch.tensor([ori_img_size] * 4, dtype=pred_scores.dtype)           # loss.py:72
@@ -126,7 +127,7 @@ def compute_loss(sizes, pred_scores, pred_distri, targets, *, strides, num_class
     weight = 0.75 * pred_scores.pow(2.0) * (1 - one_hot) + ts * one_hot
     loss_cls = (F.binary_cross_entropy(pred_scores.float(), ts.float(), reduction="none") * weight).sum()
     tss = ts.sum()
-    if tss > 1:                                                                  # loss.py:168-169
+    if tss > norm_thr:                                                                  # loss.py:168-169
         loss_cls = loss_cls / tss
     # BboxLoss, loss.py:222-263
     num_pos = fg.sum()
@@ -135,7 +136,7 @@ def compute_loss(sizes, pred_scores, pred_distri, targets, *, strides, num_class
         tbp = tb[fg]
         bw = ts.sum(-1)[fg].unsqueeze(-1)
         loss_iou = (iou_loss(pb, tbp, iou_type) * bw).sum()
-        if tss > 1:
+        if tss > norm_thr:
             loss_iou = loss_iou / tss
         if use_dfl:
             pd_pos = pred_distri[fg].view(-1, 4, reg_max + 1)
@@ -148,7 +149,7 @@ def compute_loss(sizes, pred_scores, pred_distri, targets, *, strides, num_class
             ce_l = F.cross_entropy(pd_pos.view(-1, reg_max + 1), tl_.view(-1), reduction="none").view(tl_.shape) * wl
             ce_r = F.cross_entropy(pd_pos.view(-1, reg_max + 1), tr_.view(-1), reduction="none").view(tl_.shape) * wr
             loss_dfl = ((ce_l + ce_r).mean(-1, keepdim=True) * bw).sum()
-            if tss > 1:
+            if tss > norm_thr:
                 loss_dfl = loss_dfl / tss
         else:
             loss_dfl = pred_distri.sum() * 0.0

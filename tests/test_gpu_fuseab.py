@@ -130,3 +130,37 @@ def test_fuseab_train_step_graph_equals_autograd_path():
         assert e < 5e-3, f"{n}: {e:.3e}"         # same kernels; fp32 atomics make the accumulation order differ
     print("fuse_ab TrainStep vs autograd path: worst relative gradient difference", worst)
     assert any("_ab." in n for n in ref)
+
+
+@pytest.mark.parametrize("case", golden_json("distill_cases.json"), ids=lambda c: c[0])
+def test_distill_loss_matches_reference_golden(case):
+    """`yolov6_b200.loss_distill.ComputeLoss` (yv6_det_loss with the > 0 rule + two yv6_kl_rows terms) against the reference's
+    loss_distill.py goldens: loss / items 1e-5, positives exact, gradients rtol 2e-4."""
+    from yolov6_b200.loss_distill import ComputeLoss
+    name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop = case
+    g = golden_npz("distill.npz")
+    strides = [8, 16, 32]
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed)
+    tps, tpd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed + 100)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=80), drop)
+    dev = torch.device("cuda:0")
+    psd, pdd = ps.to(dev).requires_grad_(True), pd.to(dev).requires_grad_(True)
+    feats = [torch.zeros(B, 8, h, w, device=dev) for h, w in sizes]
+    cl = ComputeLoss(fpn_strides=strides, num_classes=80, ori_img_size=img, warmup_epoch=warm, use_dfl=True, reg_max=16, iou_type=iou_type,
+                     distill_weight={"class": 1.0, "dfl": 1.0}, distill_feat=False)
+    loss, items = cl((feats, psd, pdd), (feats, tps.to(dev), tpd.to(dev)), None, None, targets.to(dev), epoch, max_epoch, T, 1, img, img)
+    loss.backward()
+    ref = float(g[f"{name}_loss"])
+    print(name, "loss", float(loss.detach()), "reference", ref, "items", items.tolist())
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref)
+    np.testing.assert_allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=1e-5, atol=1e-7)
+    fg = cl.last_assignment.fg.bool().cpu()
+    assert np.array_equal(np.packbits(fg.numpy()), g[f"{name}_pos"]), "positives differ from the reference"
+    np.testing.assert_allclose(pdd.grad.cpu()[fg].double().numpy(), g[f"{name}_grad_distri_rows"], rtol=2e-4, atol=1e-7)
+    assert float(pdd.grad.cpu()[~fg].abs().max()) == 0.0
+    np.testing.assert_allclose(psd.grad.cpu().flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=2e-4, atol=1e-7)
+    got_abs, ref_abs = float(psd.grad.double().abs().sum()), float(g[f"{name}_grad_scores_abs"])
+    assert abs(got_abs - ref_abs) <= 1e-4 * ref_abs
+    with pytest.raises(NotImplementedError):
+        ComputeLoss(distill_feat=True)

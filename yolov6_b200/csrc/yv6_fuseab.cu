@@ -167,3 +167,77 @@ extern "C" int yv6_ab_boxes_bwd(yv6_handle* h, const float* grad_ltrb, int64_t r
   YV6_CHECK_CUDA(cudaGetLastError());
   return YV6_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Self-distillation terms of yolov6/models/losses/loss_distill.py (second half): both
+// `distill_loss_cls` (:213-222, rows = all B*A anchors, C = classes, "logits" = the post-sigmoid scores) and
+// `distill_loss_dfl` (:351-361, rows = the 4 sides of every positive anchor, C = reg_max + 1 = 17) are
+//     T^2 * KL( softmax(teacher / T) || softmax(student / T) )   summed over rows (the DFL one averaged over its rows).
+// One warp per row; value and gradient d/ds_j = (p_j - q_j) / T in the same pass.  The factor in front -- loss weights, the
+// cosine decay, and for the DFL term 1 / (4 * num_pos) with num_pos on the device -- is `scale` x optional device scalars.
+// ------------------------------------------------------------------------------------------------
+namespace yv6 {
+constexpr int kKlMaxC = 256;
+__global__ void __launch_bounds__(256) kl_rows_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t rows, int C, float inv_T,
+                                                      const uint8_t* __restrict__ mask, int rows_per_mask, double scale,
+                                                      const double* __restrict__ count_ptr, const double* __restrict__ gate_ptr,
+                                                      double* __restrict__ acc, float* __restrict__ grad) {
+  __shared__ double sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  double eff = scale;
+  if (count_ptr != nullptr) {        // mean over the active rows: rows_per_mask * (number of active mask entries)
+    const double n = *count_ptr * (double)rows_per_mask;
+    eff = (n > 0.0) ? scale / n : 0.0;
+  }
+  if (gate_ptr != nullptr && !(*gate_ptr > 0.0)) eff = 0.0;    // loss_distill.py:318-323: the term is multiplied by weights that sum to 0
+  double local = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * warps + warp; r < rows; r += (int64_t)gridDim.x * warps) {
+    if (mask != nullptr && !mask[r / rows_per_mask]) continue;
+    const float* sr = s + r * C;
+    const float* tr = t + r * C;
+    // The row's KL (~1e-4 at T = 20 over sigmoid scores) is a difference of two log-sum-exps of ~4.4: in fp32 their rounding
+    // (~3e-7 each) is a 0.4 % error per row, so the log-sum-exps and log-probabilities are formed in double.
+    const double iT = (double)inv_T;
+    double ms = -INFINITY, mt = -INFINITY;
+    for (int j = lane; j < C; j += 32) { ms = fmax(ms, (double)sr[j] * iT); mt = fmax(mt, (double)tr[j] * iT); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ms = fmax(ms, __shfl_xor_sync(0xffffffffu, ms, o)); mt = fmax(mt, __shfl_xor_sync(0xffffffffu, mt, o)); }
+    double zs = 0.0, zt = 0.0;
+    for (int j = lane; j < C; j += 32) { zs += exp((double)sr[j] * iT - ms); zt += exp((double)tr[j] * iT - mt); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { zs += __shfl_xor_sync(0xffffffffu, zs, o); zt += __shfl_xor_sync(0xffffffffu, zt, o); }
+    const double ls = ms + log(zs), lt = mt + log(zt);           // log-sum-exp of student / teacher
+    double kl = 0.0;
+    for (int j = lane; j < C; j += 32) {
+      const double a = (double)sr[j] * iT - ls, b = (double)tr[j] * iT - lt;  // log p_j, log q_j
+      const double q = exp(b), pj = exp(a);
+      kl += q * (b - a);
+      if (grad != nullptr) grad[r * C + j] += (float)(eff * (pj - q) * iT);
+    }
+    local += kl;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if (lane == 0) sh[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < warps; ++w) tot += sh[w];
+    if (tot != 0.0) atomicAdd(acc, eff * tot);
+  }
+}
+}  // namespace yv6
+
+extern "C" int yv6_kl_rows(yv6_handle* h, const float* student, const float* teacher, int64_t rows, int32_t C, float temperature,
+                           const uint8_t* row_mask, int32_t rows_per_mask, double scale, const double* count_ptr, const double* gate_ptr,
+                           double* acc, float* grad, void* stream) {
+  yv6_device_guard _dev(h);
+  YV6_REQUIRE(h && student && teacher && acc, "kl_rows: null argument");
+  YV6_REQUIRE(C >= 1 && C <= kKlMaxC && temperature > 0.f && rows_per_mask >= 1, "kl_rows: C=%d T=%f", C, (double)temperature);
+  if (rows <= 0) return YV6_OK;
+  const int64_t blocks = std::min<int64_t>((rows + 7) / 8, (int64_t)h->num_sms * 8);
+  kl_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(student, teacher, rows, C, 1.f / temperature, row_mask, rows_per_mask, scale,
+                                                                    count_ptr, gate_ptr, acc, grad);
+  YV6_CHECK_CUDA(cudaGetLastError());
+  return YV6_OK;
+}

@@ -47,6 +47,7 @@ class ComputeLoss:
         self.loss_weight = loss_weight
         self._anchor_key, self._anchors = None, None
         self.last_assignment = None
+        self._norm_gt_zero = 0      # subclasses: 1 = divide by target_scores_sum whenever it is > 0 (loss_distill.py:190-191, 318-323)
 
     def _get_anchors(self, sizes, device):
         key = (tuple(sizes), str(device))
@@ -116,6 +117,7 @@ class ComputeLoss:
         d.grad_scale = float(grad_scale)
         d.grad_scores, d.grad_distri, d.out = grad_scores.data_ptr(), grad_distri.data_ptr(), out.data_ptr()
         d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        d.norm_gt_zero = self._norm_gt_zero
         _lib.check(lib.yv6_det_loss(h, C.byref(d), sp))
         return {"grad_scores": grad_scores, "grad_distri": grad_distri, "out": out, "gt_count": gt_count, "G": G,
                 "keep": (ps, pd, gt, mask, pboxes, ws, tg)}

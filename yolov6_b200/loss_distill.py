@@ -1,0 +1,81 @@
+"""Drop-in `ComputeLoss` of the self-distillation recipe for the M / L models (second half).
+
+Same constructor and call signature as yolov6/models/losses/loss_distill.py:14-211, which the Trainer uses with
+`--distill` (core/engine.py:153-159, 311-322):
+
+    preds, s_featmaps = model(images)
+    with torch.no_grad():
+        t_preds, t_featmaps = teacher_model(images)
+    loss, items = compute_loss_distill(preds, t_preds, s_featmaps, t_featmaps, targets, epoch_num, max_epoch, temperature,
+                                       step_num, batch_height, batch_width)
+
+= the anchor-free detection loss (with the "> 0" normalisation rule of :190-191, 318-323)
+  + distill_weight['class'] * decay * T^2 KL(softmax(t_scores / T) || softmax(s_scores / T))        summed over all anchors (:213-222)
+  + distill_weight['dfl']   * decay * T^2 mean KL over the 4 x 17-bin side distributions of the positives (:351-361),
+    multiplied by sum(bbox_weight) / target_scores_sum (= 1, or 0 when no target score is positive; :318-323)
+with decay = ((1 - cos(epoch * pi / max_epoch)) / 2) * (0.01 - 1) + 1 (:196).  The detection part is `yv6_det_loss` (value +
+gradients in one launch); the two KL terms are `yv6_kl_rows`, which adds its gradients to the same buffers.  The channel-wise
+feature-map term (`distill_feat=True`, :223-245) needs gradients w.r.t. the neck outputs, which the training engine does not
+accept from outside: it raises NotImplementedError.  The N / S variant (loss_distill_ns.py + effidehead_distill_ns.py) is not built.
+"""
+import math
+
+import torch
+
+from . import _lib
+from .assigners import _p
+from .loss import ComputeLoss as _DetLoss
+from .loss import _DetLossFn
+
+
+class ComputeLoss(_DetLoss):
+    def __init__(self, fpn_strides=[8, 16, 32], grid_cell_size=5.0, grid_cell_offset=0.5, num_classes=80, ori_img_size=640,
+                 warmup_epoch=0, use_dfl=True, reg_max=16, iou_type='giou',
+                 loss_weight={'class': 1.0, 'iou': 2.5, 'dfl': 0.5, 'cwd': 10.0},
+                 distill_feat=False, distill_weight={'class': 1.0, 'dfl': 1.0}):
+        super().__init__(fpn_strides, grid_cell_size, grid_cell_offset, num_classes, ori_img_size, warmup_epoch, use_dfl, reg_max,
+                         iou_type, loss_weight)
+        if distill_feat:
+            raise NotImplementedError("distill_feat (channel-wise feature-map KL, loss_distill.py:223-245) is not built: the training "
+                                      "engine takes gradients w.r.t. the head outputs only")
+        self.distill_feat = False
+        self.distill_weight = distill_weight
+        self._norm_gt_zero = 1
+
+    def __call__(self, outputs, t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch, temperature, step_num,
+                 batch_height, batch_width):
+        feats, pred_scores, pred_distri = outputs
+        t_pred_scores, t_pred_distri = t_outputs[-2], t_outputs[-1]            # loss_distill.py:76 (a fuse_ab teacher returns five)
+        sizes = [tuple(f.shape[2:]) for f in feats]
+        state = self.forward_backward(pred_scores, pred_distri, sizes, targets, epoch_num, batch_height, batch_width)
+        dev = pred_scores.device
+        lib, h, sp = _lib.lib(), _lib.handle(dev.index or 0), _lib.stream_ptr()
+        B, A, nc = pred_scores.shape
+        ps, pd = state["keep"][0], state["keep"][1]
+        ts = t_pred_scores.detach().float().contiguous()
+        td = t_pred_distri.detach().float().contiguous()
+        if ts.shape != ps.shape or td.shape != pd.shape:
+            raise RuntimeError(f"teacher outputs {tuple(ts.shape)}, {tuple(td.shape)} do not match the student's {tuple(ps.shape)}, {tuple(pd.shape)}")
+        decay = ((1 - math.cos(epoch_num * math.pi / max_epoch)) / 2) * (0.01 - 1) + 1          # :196
+        T = float(temperature)
+        w_cls, w_dfl = float(self.loss_weight['class']), float(self.loss_weight['dfl'])
+        terms = torch.zeros(2, dtype=torch.float64, device=dev)                 # weighted d_loss_cls, d_loss_dfl
+        out = state["out"]
+        s_cls = w_cls * float(self.distill_weight['class']) * decay * T * T
+        _lib.check(lib.yv6_kl_rows(h, _p(ps), _p(ts), B * A, nc, T, 0, 1, s_cls, 0, 0, terms.data_ptr(), _p(state["grad_scores"]), sp))
+        if self.use_dfl:
+            R = self.reg_max + 1
+            s_dfl = w_dfl * float(self.distill_weight['dfl']) * decay * T * T
+            fg = self.last_assignment.fg
+            # rows = (anchor, side); active = positives; mean over 4 * num_pos rows (out[5]); zero unless target_scores_sum (out[4]) > 0
+            _lib.check(lib.yv6_kl_rows(h, _p(pd), _p(td), B * A * 4, R, T, _p(fg), 4, s_dfl, out.data_ptr() + 5 * 8, out.data_ptr() + 4 * 8,
+                                       terms.data_ptr() + 8, _p(state["grad_distri"]), sp))
+        total = out.clone()
+        total[0] = out[0] + terms[0] + terms[1]
+        total[2] = out[2] + terms[1]               # loss_weight['dfl'] * loss_dfl_all
+        total[3] = out[3] + terms[0]               # loss_weight['class'] * loss_cls_all
+        state["out"] = total
+        state["keep_distill"] = (ts, td, terms)
+        loss = _DetLossFn.apply(pred_scores, pred_distri, state)
+        items = torch.cat([total[1:4], torch.zeros(1, dtype=total.dtype, device=dev)])   # (iou, dfl_all, cls_all, cwd = 0)
+        return loss, items.detach()
