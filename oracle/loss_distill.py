@@ -50,3 +50,36 @@ def compute_loss_distill(sizes, pred_scores, pred_distri, t_pred_scores, t_pred_
     items4 = torch.stack([items[0], items[1] + (lw["dfl"] * dw["dfl"] * d_dfl).detach(), items[2] + (lw["class"] * dw["class"] * d_cls).detach(),
                           torch.zeros(())]).detach()
     return loss, items4
+
+
+def compute_loss_distill_ns(sizes, pred_scores, pred_distri, pred_lrtb, t_pred_scores, t_pred_distri, targets, *, strides, epoch_num,
+                            max_epoch, temperature, num_classes=80, ori_img_size=640, reg_max=16, iou_type="giou", loss_weight=None,
+                            distill_weight=None):
+    """yolov6/models/losses/loss_distill_ns.py:58-211: the M / L distillation loss on (scores, DFL distributions) with the
+    TaskAlignedAssigner at every epoch, plus the IoU loss of the lrtb branch's boxes against the same assignment (:93, :283-292)."""
+    from . import assign
+    lw = loss_weight or {"class": 1.0, "iou": 2.5, "dfl": 0.5, "cwd": 10.0}
+    loss, items = compute_loss_distill(sizes, pred_scores, pred_distri, t_pred_scores, t_pred_distri, targets, strides=strides,
+                                       epoch_num=epoch_num, max_epoch=max_epoch, temperature=temperature, num_classes=num_classes,
+                                       ori_img_size=ori_img_size, warmup_epoch=0, use_dfl=True, reg_max=reg_max, iou_type=iou_type,
+                                       loss_weight=lw, distill_weight=distill_weight)
+    _, _, a = oloss.compute_loss(sizes, pred_scores.detach(), pred_distri.detach(), targets, strides=strides, num_classes=num_classes,
+                                 ori_img_size=ori_img_size, warmup_epoch=0, epoch_num=epoch_num, use_dfl=True, reg_max=reg_max,
+                                 iou_type=iou_type, loss_weight=lw, return_assign=True, norm_gt_zero=True)
+    fg, ts, tb = a["fg"], a["scores"], a["bboxes"]
+    _, anchor_points, _, stride_t = assign.train_anchors(sizes, strides, dtype=pred_scores.dtype)
+    aps = anchor_points / stride_t
+    lt, rb = torch.split(pred_lrtb, 2, -1)                                               # dist2bbox(xyxy), general.py:32-38
+    boxes = torch.cat([aps - lt, aps + rb], -1)
+    tss = ts.sum()
+    if fg.sum() > 0:
+        bw = ts.sum(-1)[fg].unsqueeze(-1)
+        iou_lrtb = (oloss.iou_loss(boxes[fg], tb[fg], iou_type) * bw).sum()
+        if tss != 0:
+            iou_lrtb = iou_lrtb / tss
+    else:
+        iou_lrtb = pred_lrtb.sum() * 0.0
+    loss = loss + lw["iou"] * iou_lrtb
+    items = items.clone()
+    items[0] = items[0] + (lw["iou"] * iou_lrtb).detach()
+    return loss, items

@@ -347,7 +347,18 @@ def decode_eval(cfg, cls, reg, sizes):
     return torch.cat([box, torch.ones(B, A, 1, dtype=reg.dtype), cls], -1)
 
 
-def forward(sd, cfg, x, train_outputs=False, fuse_ab=False):
+def head_dist(sd, cfg, feats):
+    """`reg_preds_dist` branch of the N / S distillation student (effidehead_distill_ns.py:93-101): DFL logits [B,A,4*(reg_max+1)]."""
+    out = []
+    for i, x in enumerate(feats):
+        x = conv_bn_act(sd, f"detect.stems.{i}", x, 1, "silu")
+        rf = conv_bn_act(sd, f"detect.reg_convs.{i}", x, 1, "silu")
+        r = F.conv2d(rf, _wq(sd[f"detect.reg_preds_dist.{i}.weight"].to(x.dtype)), sd[f"detect.reg_preds_dist.{i}.bias"].to(x.dtype))
+        out.append(r.flatten(2).permute(0, 2, 1))
+    return torch.cat(out, 1)
+
+
+def forward(sd, cfg, x, train_outputs=False, fuse_ab=False, distill_ns=False):
     """Model.forward, yolo.py:33-41.  x: [B,3,H,W] in [0,1].  Eval: [B,A,5+nc].
     train_outputs=True returns the train-mode head tensors (cls post-sigmoid, reg raw) computed
     with eval-mode BN -- used to pin the loss / assigner inputs; with fuse_ab also (cls_ab, reg_ab)."""
@@ -357,6 +368,10 @@ def forward(sd, cfg, x, train_outputs=False, fuse_ab=False):
     if train_outputs and fuse_ab:
         cls_ab, reg_ab = head_ab(sd, cfg, feats)
         return cls, reg, sizes, cls_ab, reg_ab
+    if train_outputs and distill_ns:       # (cls, reg_lrtb, sizes, reg_dist): effidehead_distill_ns.py:104
+        return cls, reg, sizes, head_dist(sd, cfg, feats)
+    if distill_ns:                          # eval: plain lrtb distances, no DFL (effidehead_distill_ns.py:105-150)
+        return decode_eval(dict(cfg, use_dfl=False, reg_max=0), cls, reg, sizes)
     if train_outputs:
         return cls, reg, sizes
     return decode_eval(cfg, cls, reg, sizes)

@@ -20,6 +20,7 @@ torch.cuda.is_available = lambda: False
 nn.Module.cuda = lambda self, *a, **k: self
 
 from yolov6.models.losses.loss_distill import ComputeLoss as ComputeLossDistill  # noqa: E402
+from yolov6.models.losses.loss_distill_ns import ComputeLoss as ComputeLossDistillNS  # noqa: E402
 
 from oracle import fabricate as fab  # noqa: E402
 from oracle import loss as oloss  # noqa: E402
@@ -53,6 +54,28 @@ def main():
         nz = pdl.grad.abs().sum(-1) > 0
         store[f"{name}_pos"] = np.packbits(nz.numpy())
         store[f"{name}_grad_distri_rows"] = pdl.grad[nz].double().numpy()
+        print(name, "loss", loss.item(), "items", items.tolist(), "positives", int(nz.sum()))
+    # ---- N / S variant (loss_distill_ns.py): a third student tensor, the lrtb distances of the inference branch
+    for name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop in [["ns_" + c[0]] + c[1:] for c in CASES]:
+        strides = [8, 16, 32]
+        sizes = [(img // s, img // s) for s in strides]
+        ps, pd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed)
+        _, pl = fab.synthetic_head_outputs(B, sizes, 80, 4, seed + 200)
+        tps, tpd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed + 100)
+        targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=80), drop)
+        cl = ComputeLossDistillNS(fpn_strides=strides, num_classes=80, ori_img_size=img, warmup_epoch=warm, use_dfl=True, reg_max=16,
+                                  iou_type=iou_type, distill_weight={"class": 1.0, "dfl": 1.0}, distill_feat=False)
+        psl, pdl, pll = ps.clone().requires_grad_(True), pd.clone().requires_grad_(True), pl.clone().requires_grad_(True)
+        feats = [torch.zeros(B, 8, h, w) for h, w in sizes]
+        loss, items = cl((feats, psl, pdl, pll), (feats, tps, tpd), None, None, targets.clone(), epoch, max_epoch, T, 1, img, img)
+        loss.backward()
+        nz = pll.grad.abs().sum(-1) > 0
+        store[f"{name}_loss"] = np.float64(loss.item())
+        store[f"{name}_items"] = items.double().numpy()
+        store[f"{name}_pos"] = np.packbits(nz.numpy())
+        store[f"{name}_grad_lrtb_rows"] = pll.grad[nz].double().numpy()
+        store[f"{name}_grad_distri_rows"] = pdl.grad[nz].double().numpy()
+        store[f"{name}_grad_scores_abs"] = np.float64(psl.grad.double().abs().sum().item())
         print(name, "loss", loss.item(), "items", items.tolist(), "positives", int(nz.sum()))
     with open(os.path.join(HERE, "distill_cases.json"), "w") as f:
         json.dump(CASES, f)

@@ -70,6 +70,38 @@ def main():
     for k in FULL:
         store["m_grad::" + k] = params[k].grad.numpy()
     print("model: L", L.item(), "cls_ab", tuple(cls_ab.shape), "reg_ab", tuple(reg_ab.shape), "params with grad", len(names))
+    # ---------------- A2: the N / S distillation student head (yolo.py:113-120 -> heads/effidehead_distill_ns.py) ----------------
+    cfg = Config.fromfile("/root/reference/configs/yolov6n.py")
+    if not hasattr(cfg, "training_mode"):
+        setattr(cfg, "training_mode", "repvgg")
+    cfg.model.head.use_dfl, cfg.model.head.reg_max = True, 16      # "set to True / 16 if you want to further train with distillation"
+    m = build_model(cfg, 80, torch.device("cpu"), distill_ns=True)
+    keys = [(k, list(v.shape)) for k, v in m.state_dict().items()]
+    with open(os.path.join(HERE, "keys_yolov6n_distill_ns.json"), "w") as f:
+        json.dump(keys, f)
+    sd = fab.fabricate_state_dict(keys, seed=0)
+    for k in sd:
+        if (".cls_preds" in k or ".reg_preds" in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+    m.load_state_dict(sd, strict=True)
+    m = m.double().train()
+    x = fab.synthetic_images(2, 64, 64, seed=7).double()
+    (feats, cls, reg_dist, reg_lrtb), _ = m(x)
+    g = torch.Generator().manual_seed(17)
+    w0, w1, w2 = (torch.randn(t.shape, generator=g).double() for t in (cls, reg_dist, reg_lrtb))
+    L = (cls * w0).sum() + (reg_dist * w1).sum() + (reg_lrtb * w2).sum()
+    L.backward()
+    params = dict(m.named_parameters())
+    names = [k for k, p in params.items() if p.grad is not None]
+    store.update(ns_cls=cls.detach().numpy(), ns_reg_dist=reg_dist.detach().numpy(), ns_reg_lrtb=reg_lrtb.detach().numpy(), ns_L=np.float64(L.item()),
+                 ns_grad_names=np.array(names), ns_grad_norms=np.array([float(params[k].grad.norm()) for k in names]))
+    for k in ("detect.reg_preds_dist.1.weight", "detect.reg_preds.0.bias", "detect.reg_convs.2.block.conv.weight"):
+        store["ns_grad::" + k] = params[k].grad.numpy()
+    m.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in sd.items()}, strict=True)   # the train forward moved the running statistics
+    m.eval()
+    with torch.no_grad():
+        store["ns_eval"] = m(x)[0].numpy()
+    print("distill_ns model: L", L.item(), "reg_dist", tuple(reg_dist.shape), "reg_lrtb", tuple(reg_lrtb.shape), "params with grad", len(names))
     # ---------------- B: loss ----------------
     for name, img, B, seed, iou_type, drop in LOSS_CASES:
         strides = [8, 16, 32]

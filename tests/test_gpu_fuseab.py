@@ -164,3 +164,85 @@ def test_distill_loss_matches_reference_golden(case):
     assert abs(got_abs - ref_abs) <= 1e-4 * ref_abs
     with pytest.raises(NotImplementedError):
         ComputeLoss(distill_feat=True)
+
+
+@pytest.mark.parametrize("case", golden_json("distill_cases.json"), ids=lambda c: "ns_" + c[0])
+def test_distill_ns_loss_matches_reference_golden(case):
+    """`yolov6_b200.loss_distill.ComputeLossNS` against the reference's loss_distill_ns.py goldens (three student tensors)."""
+    from yolov6_b200.loss_distill import ComputeLossNS
+    name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop = case
+    name = "ns_" + name
+    g = golden_npz("distill.npz")
+    strides = [8, 16, 32]
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed)
+    _, pl = fab.synthetic_head_outputs(B, sizes, 80, 4, seed + 200)
+    tps, tpd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed + 100)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=80), drop)
+    dev = torch.device("cuda:0")
+    psd, pdd, pld = (t.to(dev).requires_grad_(True) for t in (ps, pd, pl))
+    feats = [torch.zeros(B, 8, h, w, device=dev) for h, w in sizes]
+    cl = ComputeLossNS(fpn_strides=strides, num_classes=80, ori_img_size=img, warmup_epoch=warm, use_dfl=True, reg_max=16, iou_type=iou_type,
+                       distill_weight={"class": 1.0, "dfl": 1.0}, distill_feat=False)
+    loss, items = cl((feats, psd, pdd, pld), (feats, tps.to(dev), tpd.to(dev)), None, None, targets.to(dev), epoch, max_epoch, T, 1, img, img)
+    loss.backward()
+    ref = float(g[f"{name}_loss"])
+    print(name, "loss", float(loss.detach()), "reference", ref, "items", items.tolist())
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref)
+    np.testing.assert_allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=1e-5, atol=1e-7)
+    fg = cl.last_assignment.fg.bool().cpu()
+    assert np.array_equal(np.packbits(fg.numpy()), g[f"{name}_pos"]), "positives differ from the reference"
+    np.testing.assert_allclose(pld.grad.cpu()[fg].double().numpy(), g[f"{name}_grad_lrtb_rows"], rtol=2e-4, atol=1e-7)
+    assert float(pld.grad.cpu()[~fg].abs().max()) == 0.0
+    np.testing.assert_allclose(pdd.grad.cpu()[fg].double().numpy(), g[f"{name}_grad_distri_rows"], rtol=2e-4, atol=1e-7)
+    got_abs, ref_abs = float(psd.grad.double().abs().sum()), float(g[f"{name}_grad_scores_abs"])
+    assert abs(got_abs - ref_abs) <= 1e-4 * ref_abs
+
+
+def test_distill_ns_student_with_fuseab_teacher_through_the_dropin_api():
+    """`--distill` for an N / S model (core/engine.py:153-159, 311-322, 429-441): student = build_model(distill_ns=True) on a config with
+    use_dfl / reg_max 16, teacher = build_model(fuse_ab=True) of the same config, loss = loss_distill_ns.  One training step gives every
+    student parameter a finite gradient; the eval forward of the student (lrtb branch, no DFL) matches the oracle within the bf16 bar."""
+    from oracle import model as om
+    from yolov6_b200 import configs
+    from yolov6_b200.loss_distill import ComputeLossNS
+    from yolov6_b200.model import build_model
+    dev = torch.device("cuda:0")
+    cfg = configs.get_config("yolov6n")
+    cfg["head"]["use_dfl"], cfg["head"]["reg_max"] = True, 16
+    keys = golden_keys("yolov6n_distill_ns")
+    sd = fab.fabricate_state_dict(keys, seed=0)
+    for k in sd:
+        if (".cls_preds" in k or ".reg_preds" in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+    student = build_model(cfg, 80, dev, distill_ns=True)
+    student.load_state_dict(sd)
+    teacher = build_model(cfg, 80, dev, fuse_ab=True)          # random init is enough here: its outputs are just inputs of the loss
+    S, B = 128, 2
+    x = fab.synthetic_images(B, S, S, seed=3).to(dev)
+    targets = oloss.synthetic_targets(B, seed=4).to(dev)
+    student.train()
+    teacher.train()
+    preds, s_feats = student(x)
+    with torch.no_grad():
+        t_preds, t_feats = teacher(x)
+    assert len(preds) == 4 and preds[2].shape[2] == 68 and preds[3].shape[2] == 4 and len(t_preds) == 5 and t_preds[-1].shape[2] == 68
+    crit = ComputeLossNS(num_classes=80, ori_img_size=S, warmup_epoch=0, use_dfl=True, reg_max=16, iou_type="siou",
+                         distill_weight={"class": 1.0, "dfl": 1.0}, distill_feat=False)
+    loss, items = crit(preds, t_preds, s_feats, t_feats, targets, 10, 300, 20.0, 0, S, S)
+    assert items.shape == (4,) and bool(torch.isfinite(loss))
+    loss.backward()
+    torch.cuda.synchronize()
+    for n, p in student.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+    assert float(student.detect.reg_preds_dist[1].weight.grad.abs().sum()) > 0 and float(student.detect.reg_preds[1].weight.grad.abs().sum()) > 0
+    student.eval().set_precision("fp32")
+    with torch.no_grad():
+        got = student(x)[0].cpu().double()
+        cur = {k: v.detach().cpu() for k, v in student.state_dict().items()}    # the training forward moved the BatchNorm running statistics
+        ref = om.forward({k: v.double() if v.is_floating_point() else v for k, v in cur.items()}, dict(om.CONFIGS["yolov6n"], use_dfl=True, reg_max=16),
+                         x.cpu().double(), distill_ns=True)
+    err = float(((got - ref).abs() / (1 + ref.abs())).max())
+    print("distill_ns eval (fp32-equivalent mode) vs oracle:", err)
+    assert got.shape == ref.shape and err < 1e-4

@@ -42,9 +42,9 @@ def _q(t):
     return t + (t.to(torch.bfloat16).double() - t).detach()
 
 
-@pytest.mark.parametrize("name,size,batch,fuse_ab", [("yolov6n", 128, 4, False), ("yolov6s", 96, 2, False), ("yolov6m", 96, 2, False),
-                                                     ("yolov6l6", 128, 2, False), ("yolov6n", 128, 2, True)])
-def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
+@pytest.mark.parametrize("name,size,batch,variant", [("yolov6n", 128, 4, ""), ("yolov6s", 96, 2, ""), ("yolov6m", 96, 2, ""),
+                                                     ("yolov6l6", 128, 2, ""), ("yolov6n", 128, 2, "fuse_ab"), ("yolov6n", 128, 2, "distill_ns")])
+def test_train_step_matches_reference_op_by_op(name, size, batch, variant):
     """Forward against the oracle's train-mode network; backward op by op.
 
     Train-mode BatchNorm over randomly initialised weights is chaotic: the float64 oracle and the same oracle
@@ -57,13 +57,19 @@ def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
     import torch.nn.functional as F
     from yolov6_b200.model import build_model
     dev = torch.device("cuda:0")
-    sd = fab.fabricate_state_dict(golden_keys(name + ("_fuseab" if fuse_ab else "")), seed=0)
+    fuse_ab, distill_ns = variant == "fuse_ab", variant == "distill_ns"
+    sd = fab.fabricate_state_dict(golden_keys(name + ("_fuseab" if fuse_ab else "_distill_ns" if distill_ns else "")), seed=0)
     for k in sd:      # batch-stat BN makes the features unit-variance; keep the head logits O(1)
         if (".cls_preds" in k or ".reg_preds" in k) and k.endswith("weight"):
             sd[k] = sd[k] * 0.1
         if k.endswith(".alpha"):
             sd[k] = sd[k] * 0.75
-    m = build_model(name, 80, dev, fuse_ab=fuse_ab)
+    cfg = name
+    if distill_ns:       # the N / S distillation student is configured with a DFL branch (configs/yolov6n.py: "set to True / 16 ...")
+        from yolov6_b200 import configs
+        cfg = configs.get_config(name)
+        cfg["head"]["use_dfl"], cfg["head"]["reg_max"] = True, 16
+    m = build_model(cfg, 80, dev, fuse_ab=fuse_ab, distill_ns=distill_ns)
     m.load_state_dict(sd)
     m.train()
     eng = m.train_engine()
@@ -73,6 +79,8 @@ def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
     g = torch.Generator().manual_seed(5)
     if fuse_ab:       # anchor-aided branch (effidehead_fuseab.py:94-140): five training outputs, all of them in the scalar
         (feats, cls_ab, reg_ab, cls, reg), _ = m(xd)
+    elif distill_ns:  # effidehead_distill_ns.py:104: (x, cls, reg_distri, reg_lrtb)
+        (feats, cls, reg_dist, reg), _ = m(xd)
     else:
         (feats, cls, reg), _ = m(xd)
     wc, wr = torch.randn(cls.shape, generator=g).to(dev), torch.randn(reg.shape, generator=g).to(dev)
@@ -80,6 +88,9 @@ def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
     if fuse_ab:
         w1, w2 = torch.randn(cls_ab.shape, generator=g).to(dev), torch.randn(reg_ab.shape, generator=g).to(dev)
         L = L + (cls_ab * w1).sum() + (reg_ab * w2).sum()
+    if distill_ns:
+        wd = torch.randn(reg_dist.shape, generator=g).to(dev)
+        L = L + (reg_dist * wd).sum()
     L.backward()
     torch.cuda.synchronize()
     assert [tuple(f.shape[2:]) for f in feats] == [(size // s, size // s) for s in om.CONFIGS[name]["strides"]]
@@ -93,6 +104,13 @@ def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
         e2 = _rel(reg_ab.detach().cpu(), oreg_ab)
         print(f"{name} fuse_ab: forward vs oracle: cls_ab rms {e1:.2e}, reg_ab rel L2 {e2:.2e}")
         assert cls_ab.shape == ocls_ab.shape and reg_ab.shape == oreg_ab.shape and e1 < 2e-2 and e2 < 5e-2
+    elif distill_ns:
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+        with torch.no_grad(), om.train_mode(), om.bf16_storage():
+            ocls, oreg, _, odist = om.forward(sd64, dict(om.CONFIGS[name], use_dfl=True, reg_max=16), x.double(), train_outputs=True, distill_ns=True)
+        e3 = _rel(reg_dist.detach().cpu(), odist)
+        print(f"{name} distill_ns: forward vs oracle: reg_dist rel L2 {e3:.2e}")
+        assert reg_dist.shape == odist.shape and e3 < 5e-2
     else:
         ocls, oreg = oracle_forward(name, sd, x)
     # (rounding differences between fp32 and float64 accumulation are amplified layer by layer by the
@@ -171,7 +189,7 @@ def test_train_step_matches_reference_op_by_op(name, size, batch, fuse_ab):
             b = P[op.name + ".bias"].detach().double().requires_grad_(True)
             y = F.conv2d(src, w, b)
             y = torch.sigmoid(y) if which == "cls" else y
-            out, wt = (eng.cls, wc) if which == "cls" else (eng.reg, wr)
+            out, wt = {"cls": (eng.cls, wc), "reg": (eng.reg, wr)}[which] if which != "reg_dist" else (eng.reg_dist, wd)
             lo, hi = eng.offs[lvl], eng.offs[lvl + 1]
             yf = y.flatten(2).permute(0, 2, 1)
             worst["fwd"] = max(worst["fwd"], _rel(out[:, lo:hi], yf.detach()))

@@ -38,3 +38,24 @@ def test_distill_loss_matches_reference(case):
     np.testing.assert_allclose(pdl.grad[nz].double().numpy(), g[f"{name}_grad_distri_rows"], rtol=2e-4, atol=1e-7)
     np.testing.assert_allclose(psl.grad.flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=2e-4, atol=1e-7)   # fp32 softmax at T = 20: differences of ~4e-8 absolute
     assert abs(float(psl.grad.double().abs().sum()) - float(g[f"{name}_grad_scores_abs"])) <= 1e-4 * float(g[f"{name}_grad_scores_abs"])
+
+
+@pytest.mark.parametrize("case", golden_json("distill_cases.json"), ids=lambda c: "ns_" + c[0])
+def test_distill_ns_loss_matches_reference(case):
+    """loss_distill_ns.ComputeLoss: TaskAlignedAssigner at every epoch, DFL distillation branch + IoU of the lrtb branch."""
+    name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop = case
+    name = "ns_" + name
+    g = golden_npz("distill.npz")
+    strides, sizes, ps, pd, tps, tpd, targets = make_inputs(case)
+    _, pl = fab.synthetic_head_outputs(B, sizes, 80, 4, seed + 200)
+    psl, pdl, pll = ps.clone().requires_grad_(True), pd.clone().requires_grad_(True), pl.clone().requires_grad_(True)
+    loss, items = odist.compute_loss_distill_ns(sizes, psl, pdl, pll, tps, tpd, targets, strides=strides, epoch_num=epoch, max_epoch=max_epoch,
+                                                temperature=T, ori_img_size=img, iou_type=iou_type)
+    assert abs(loss.item() - float(g[f"{name}_loss"])) <= 1e-5 * abs(float(g[f"{name}_loss"]))
+    np.testing.assert_allclose(items.double().numpy(), g[f"{name}_items"], rtol=1e-5, atol=1e-7)
+    loss.backward()
+    nz = (pll.grad.abs().sum(-1) > 0)
+    assert np.array_equal(np.packbits(nz.numpy()), g[f"{name}_pos"])
+    np.testing.assert_allclose(pll.grad[nz].double().numpy(), g[f"{name}_grad_lrtb_rows"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(pdl.grad[nz].double().numpy(), g[f"{name}_grad_distri_rows"], rtol=2e-4, atol=1e-7)
+    assert abs(float(psl.grad.double().abs().sum()) - float(g[f"{name}_grad_scores_abs"])) <= 1e-4 * float(g[f"{name}_grad_scores_abs"])

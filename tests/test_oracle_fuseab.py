@@ -87,3 +87,40 @@ def test_fuseab_graph_matches_reference_state_dict_layout():
     want = {k: tuple(s) for k, s in golden_json("keys_yolov6n_fuseab.json")}
     assert have == want
     assert tuple(m.detect.anchors_init.shape) == (3, 3, 2) and m.detect.na == 3
+
+
+def test_distill_ns_head_matches_reference():
+    """N / S distillation student (heads/effidehead_distill_ns.py): training outputs (cls, DFL logits, lrtb distances), gradients,
+    the eval-mode prediction (lrtb branch, no DFL) and the state_dict layout of Model(distill_ns=True)."""
+    from yolov6_b200 import configs
+    from yolov6_b200.model import Model
+    g = golden_npz("fuseab.npz")
+    keys = [(k, tuple(s)) for k, s in golden_json("keys_yolov6n_distill_ns.json")]
+    cfg = configs.get_config("yolov6n")
+    cfg["head"]["use_dfl"], cfg["head"]["reg_max"] = True, 16
+    m = Model(cfg, num_classes=80, distill_ns=True)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(keys)
+    sd = fab.fabricate_state_dict(keys, seed=0)
+    for k in sd:
+        if (".cls_preds" in k or ".reg_preds" in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+    x = fab.synthetic_images(2, 64, 64, seed=7)
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    ocfg = dict(om.CONFIGS["yolov6n"], use_dfl=True, reg_max=16)
+    with om.train_mode():
+        cls, reg, _, reg_dist = om.forward(sd64, ocfg, x.double(), train_outputs=True, distill_ns=True)
+    for got, key in ((cls, "ns_cls"), (reg, "ns_reg_lrtb"), (reg_dist, "ns_reg_dist")):
+        assert got.shape == g[key].shape and rel_err(got.detach().numpy(), g[key]) < 1e-9, key
+    gen = torch.Generator().manual_seed(17)
+    w0, w1, w2 = (torch.randn(t.shape, generator=gen).double() for t in (cls, reg_dist, reg))
+    L = (cls * w0).sum() + (reg_dist * w1).sum() + (reg * w2).sum()
+    assert abs(L.item() - float(g["ns_L"])) < 1e-8 * max(1.0, abs(float(g["ns_L"])))
+    L.backward()
+    for n, ref in zip([str(n) for n in g["ns_grad_names"]], g["ns_grad_norms"]):
+        assert abs(float(sd64[n].grad.norm()) - ref) <= 1e-7 * max(1.0, ref), n
+    for k in g.files:
+        if k.startswith("ns_grad::"):
+            np.testing.assert_allclose(sd64[k[9:]].grad.numpy().reshape(g[k].shape), g[k], rtol=1e-7, atol=1e-9 * (1 + np.abs(g[k]).max()))
+    with torch.no_grad():
+        ev = om.forward({k: v.detach() for k, v in sd64.items()}, ocfg, x.double(), distill_ns=True)
+    assert rel_err(ev.numpy(), g["ns_eval"]) < 1e-9

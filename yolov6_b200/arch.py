@@ -63,6 +63,8 @@ class Graph:
     feat: List[T] = field(default_factory=list)   # neck outputs (reference `featmaps`, yolo.py:37-39)
     fuse_ab: bool = False
     anchors_init: Optional[list] = None           # fuse_ab: per level [w0, h0, w1, h1, w2, h2] in pixels
+    distill_ns: bool = False
+    dist_reg_ch: int = 0                          # distill_ns: channels of the DFL (reg_preds_dist) branch
 
     # -- builders ---------------------------------------------------------------------------
     def buf(self, level, c_total, name=""):
@@ -173,15 +175,20 @@ def _bifusion(g, name, x0, x1, x2, cout):
     return g.conv(name + ".cv3", "cba", T(cat, 0, 3 * cout), cout, 1, 1, "relu")
 
 
-def build_graph(cfg, num_classes=80, name="yolov6", fuse_ab=False):
+def build_graph(cfg, num_classes=80, name="yolov6", fuse_ab=False, distill_ns=False):
     """cfg: dict with the fields of the reference's `config.model` (see configs.py / config_from_reference).
-    fuse_ab: add the anchor-aided training branch of effidehead_fuseab.py (two more 1x1 pred convs per level)."""
+    fuse_ab: add the anchor-aided training branch of effidehead_fuseab.py (two more 1x1 pred convs per level).
+    distill_ns: the N / S student head of effidehead_distill_ns.py -- `reg_preds` emits the 4 (l, r, t, b) distances used at
+    inference, `reg_preds_dist` the 4 * (reg_max + 1) DFL logits used by the distillation loss (training only)."""
     depth, width = cfg["depth_multiple"], cfg["width_multiple"]
     bb, nk, hd = cfg["backbone"], cfg["neck"], cfg["head"]
     reps = [(max(round(i * depth), 1) if i > 1 else i) for i in bb["num_repeats"] + nk["num_repeats"]]   # yolo.py:66
     ch = [make_divisible(i * width, 8) for i in bb["out_channels"] + nk["out_channels"]]                # yolo.py:67
     nl = hd["num_layers"]
-    g = Graph(name, num_classes, list(hd["strides"]), bool(hd["use_dfl"]), int(hd["reg_max"]), cfg["training_mode"])
+    g = Graph(name, num_classes, list(hd["strides"]), bool(hd["use_dfl"]) and not distill_ns, 0 if distill_ns else int(hd["reg_max"]),
+              cfg["training_mode"])
+    if distill_ns and (fuse_ab or nl != 3):
+        raise ValueError("distill_ns is the 3-level N / S student head (yolo.py:113-120); it excludes fuse_ab")
     csp = "CSP" in bb["type"]
     p6 = bb["type"].endswith("P6")
     nstage = 6 if p6 else 5
@@ -263,11 +270,15 @@ def build_graph(cfg, num_classes=80, name="yolov6", fuse_ab=False):
         cf = g.conv(f"detect.cls_convs.{i}", "cba", st, c, 3, 1, "silu")
         rf = g.conv(f"detect.reg_convs.{i}", "cba", st, c, 3, 1, "silu")
         g.ops.append(Op("pred", f"detect.cls_preds.{i}", "plain", cf, None, c, num_classes, 1, 1, "sigmoid", head=("cls", i)))
+        if distill_ns:      # effidehead_distill_ns.py:36-46,87-96: module order cls_preds, reg_preds_dist, reg_preds
+            g.ops.append(Op("pred", f"detect.reg_preds_dist.{i}", "plain", rf, None, c, 4 * (int(hd["reg_max"]) + 1), 1, 1, None, head=("reg_dist", i)))
         g.ops.append(Op("pred", f"detect.reg_preds.{i}", "plain", rf, None, c, reg_ch, 1, 1, None, head=("reg", i)))
         if fuse_ab:     # effidehead_fuseab.py:44-55,112-118: num_anchors = 3 class / box predictions per pixel, training only
             g.ops.append(Op("pred", f"detect.cls_preds_ab.{i}", "plain", cf, None, c, num_classes * AB_ANCHORS, 1, 1, "sigmoid", head=("cls_ab", i)))
             g.ops.append(Op("pred", f"detect.reg_preds_ab.{i}", "plain", rf, None, c, 4 * AB_ANCHORS, 1, 1, None, head=("reg_ab", i)))
     g.fuse_ab = bool(fuse_ab)
+    g.distill_ns = bool(distill_ns)
+    g.dist_reg_ch = 4 * (int(hd["reg_max"]) + 1) if distill_ns else 0
     if fuse_ab:
         ai = hd.get("anchors_init")
         if ai is None or len(ai) != nl or any(len(a) != 2 * AB_ANCHORS for a in ai):

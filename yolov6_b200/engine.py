@@ -74,7 +74,7 @@ class InferEngine:
         self.sibling = self._siblings() if self.fuse_siblings else {}
         self.sibling_second = {j: i for i, j in self.sibling.items()}
         for i, op in enumerate(self.g.ops):
-            if op.kind == "pool" or (op.kind == "pred" and op.head[0].endswith("_ab")):   # fuse_ab preds: training only
+            if op.kind == "pool" or (op.kind == "pred" and op.head[0] not in ("cls", "reg")):   # fuse_ab / distillation preds: training only
                 continue
             w, b = fold_op(sd, op)
             ent = {}
@@ -191,8 +191,8 @@ class InferEngine:
                 plan["calls"].append(("stem", d))
                 plan["deps"].append(dict(reads=[], writes=[span(op.dst)]))
             elif op.kind in ("conv", "pred", "convT"):
-                if op.kind == "pred" and op.head[0].endswith("_ab"):
-                    continue                      # eval forward uses the anchor-free branch only (effidehead_fuseab.py:141-199)
+                if op.kind == "pred" and op.head[0] not in ("cls", "reg"):
+                    continue                      # eval forward: anchor-free (cls, reg) branches only (effidehead_fuseab.py:141-199, _distill_ns.py:105-150)
                 if i in self.sibling_second:
                     continue                      # computed by its sibling's launch
                 sbuf, sh, sw, sct = view(op.src)

@@ -64,12 +64,14 @@ class ComputeLoss:
         return loss, state["out"][1:4].detach().clone()
 
     def forward_backward(self, pred_scores, pred_distri, sizes, targets, epoch_num, batch_height, batch_width, max_gt=None,
-                         grad_scores=None, grad_distri=None, grad_scale=1.0):
+                         grad_scores=None, grad_distri=None, grad_scale=1.0, reuse=None, weights=None):
         """Loss value and its gradients w.r.t. the head outputs in one pass (no autograd): returns
         {"out": float64[8] (loss, iou, dfl, cls, target_scores_sum, num_pos), "grad_scores", "grad_distri", "gt_count"}.
         `max_gt` fixes the padded target count G (static shapes for CUDA-graph capture; images with more boxes are
         reported through gt_count > G); otherwise G is the largest per-image count, as in loss.py:184-192 (one small
-        host read when `targets` lives on the device).  `grad_*` let the caller provide the output buffers."""
+        host read when `targets` lives on the device).  `grad_*` let the caller provide the output buffers.
+        `reuse` = the state of an earlier call: its padded targets and label assignment are used as they are (a second box
+        branch scored against the same assignment, loss_distill_ns.py:93,150-160); `weights` overrides the (class, iou, dfl) weights."""
         dev = pred_scores.device
         if dev.type != "cuda":
             raise RuntimeError("yolov6_b200.ComputeLoss runs on CUDA tensors only (no CPU fallback)")
@@ -80,8 +82,13 @@ class ComputeLoss:
         ps = pred_scores.detach().float().contiguous()
         pd = pred_distri.detach().float().contiguous()
         strides = stride_t.reshape(-1).contiguous()
-        n = targets.shape[0]
-        if max_gt is not None:
+        if reuse is not None:
+            gt, gt_count, G, c, mask, tg = reuse["gt"], reuse["gt_count"], reuse["G"], reuse["assignment"], reuse["mask"], None
+            pboxes = None
+        n = targets.shape[0] if reuse is None else 0
+        if reuse is not None:
+            pass
+        elif max_gt is not None:
             G = max(int(max_gt), 1)
         elif n == 0:
             G = 1
@@ -89,19 +96,20 @@ class ComputeLoss:
             img = targets[:, 0].detach()
             valid = img[(img >= 0) & (img < B)].long()
             G = max(int(torch.bincount(valid, minlength=1).max()), 1) if valid.numel() else 1
-        tg = targets.detach().float().contiguous().to(dev)
-        gt = torch.empty(B, G, 5, dtype=torch.float64, device=dev)
-        gt_count = torch.empty(B, dtype=torch.int32, device=dev)
-        _lib.check(lib.yv6_targets_pad(h, _p(tg), n, B, G, float(batch_width), float(batch_height), _p(gt), _p(gt_count), sp))
-        mask = (gt[:, :, 1:].sum(-1) > 0).to(torch.uint8).contiguous()          # loss.py:79
-        # predicted boxes in pixels for the assigner (loss.py:82-83, 94/100)
-        pboxes = torch.empty(B, A, 4, dtype=torch.float32, device=dev)
-        _lib.check(lib.yv6_box_decode(h, _p(pd), _p(anchor_points), _p(strides), B, A, R, 1, _p(pboxes), sp))
-        if epoch_num < self.warmup_epoch:
-            c = atss_compact(anchors, n_list, gt, mask, pboxes, nc, 9)
-        else:
-            c = tal_compact(ps, pboxes, anchor_points, gt, mask, 13, 1.0, 6.0)
-        self.last_assignment = c
+        if reuse is None:
+            tg = targets.detach().float().contiguous().to(dev)
+            gt = torch.empty(B, G, 5, dtype=torch.float64, device=dev)
+            gt_count = torch.empty(B, dtype=torch.int32, device=dev)
+            _lib.check(lib.yv6_targets_pad(h, _p(tg), n, B, G, float(batch_width), float(batch_height), _p(gt), _p(gt_count), sp))
+            mask = (gt[:, :, 1:].sum(-1) > 0).to(torch.uint8).contiguous()          # loss.py:79
+            # predicted boxes in pixels for the assigner (loss.py:82-83, 94/100)
+            pboxes = torch.empty(B, A, 4, dtype=torch.float32, device=dev)
+            _lib.check(lib.yv6_box_decode(h, _p(pd), _p(anchor_points), _p(strides), B, A, R, 1, _p(pboxes), sp))
+            if epoch_num < self.warmup_epoch:
+                c = atss_compact(anchors, n_list, gt, mask, pboxes, nc, 9)
+            else:
+                c = tal_compact(ps, pboxes, anchor_points, gt, mask, 13, 1.0, 6.0)
+            self.last_assignment = c
         d = _lib.LossDesc()
         if grad_scores is None:
             grad_scores = torch.empty_like(ps)
@@ -114,10 +122,12 @@ class ComputeLoss:
         d.B, d.A, d.G, d.nc, d.reg_ch = B, A, G, nc, R
         d.iou_type = IOU_TYPES[self.iou_type]
         d.w_cls, d.w_iou, d.w_dfl = float(self.loss_weight['class']), float(self.loss_weight['iou']), float(self.loss_weight['dfl'])
+        if weights is not None:
+            d.w_cls, d.w_iou, d.w_dfl = (float(v) for v in weights)
         d.grad_scale = float(grad_scale)
         d.grad_scores, d.grad_distri, d.out = grad_scores.data_ptr(), grad_distri.data_ptr(), out.data_ptr()
         d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         d.norm_gt_zero = self._norm_gt_zero
         _lib.check(lib.yv6_det_loss(h, C.byref(d), sp))
-        return {"grad_scores": grad_scores, "grad_distri": grad_distri, "out": out, "gt_count": gt_count, "G": G,
-                "keep": (ps, pd, gt, mask, pboxes, ws, tg)}
+        return {"grad_scores": grad_scores, "grad_distri": grad_distri, "out": out, "gt_count": gt_count, "G": G, "gt": gt, "mask": mask,
+                "assignment": c, "keep": (ps, pd, gt, mask, pboxes, ws, tg)}

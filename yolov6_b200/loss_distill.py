@@ -16,7 +16,8 @@ Same constructor and call signature as yolov6/models/losses/loss_distill.py:14-2
 with decay = ((1 - cos(epoch * pi / max_epoch)) / 2) * (0.01 - 1) + 1 (:196).  The detection part is `yv6_det_loss` (value +
 gradients in one launch); the two KL terms are `yv6_kl_rows`, which adds its gradients to the same buffers.  The channel-wise
 feature-map term (`distill_feat=True`, :223-245) needs gradients w.r.t. the neck outputs, which the training engine does not
-accept from outside: it raises NotImplementedError.  The N / S variant (loss_distill_ns.py + effidehead_distill_ns.py) is not built.
+accept from outside: it raises NotImplementedError.  `ComputeLossNS` below is the N / S variant (loss_distill_ns.py, for the
+student head of effidehead_distill_ns.py).
 """
 import math
 
@@ -76,6 +77,52 @@ class ComputeLoss(_DetLoss):
         total[3] = out[3] + terms[0]               # loss_weight['class'] * loss_cls_all
         state["out"] = total
         state["keep_distill"] = (ts, td, terms)
+        self._last_state = state
         loss = _DetLossFn.apply(pred_scores, pred_distri, state)
         items = torch.cat([total[1:4], torch.zeros(1, dtype=total.dtype, device=dev)])   # (iou, dfl_all, cls_all, cwd = 0)
+        return loss, items.detach()
+
+
+class _NsLossFn(torch.autograd.Function):
+    """Three differentiable inputs (scores, DFL distributions, lrtb distances) -> the scalar loss of loss_distill_ns."""
+
+    @staticmethod
+    def forward(ctx, pred_scores, pred_distri, pred_lrtb, state):
+        ctx.save_for_backward(state["grad_scores"], state["grad_distri"], state["grad_lrtb"])
+        ctx.dtypes = (pred_scores.dtype, pred_distri.dtype, pred_lrtb.dtype)
+        return state["out"][0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gs, gd, gl = ctx.saved_tensors
+        return (gs * grad_out).to(ctx.dtypes[0]), (gd * grad_out).to(ctx.dtypes[1]), (gl * grad_out).to(ctx.dtypes[2]), None
+
+
+class ComputeLossNS(ComputeLoss):
+    """yolov6/models/losses/loss_distill_ns.py:14-211 -- the N / S recipe: the student head (heads/effidehead_distill_ns.py) emits
+    DFL distributions for the distillation and plain (l, r, t, b) distances for inference; the loss is the M / L one on
+    (scores, distributions) -- TaskAlignedAssigner at every epoch (:95-103) -- plus a second IoU term of the lrtb boxes against
+    the same assignment (BboxLoss :283-292, `loss_iou + loss_iou_lrtb`)."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.warmup_epoch = 0          # loss_distill_ns.py never calls its warm-up assigner
+
+    def __call__(self, outputs, t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch, temperature, step_num,
+                 batch_height, batch_width):
+        feats, pred_scores, pred_distri, pred_lrtb = outputs
+        loss, items = super().__call__((feats, pred_scores, pred_distri), t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch,
+                                       temperature, step_num, batch_height, batch_width)
+        state = self._last_state
+        sizes = [tuple(f.shape[2:]) for f in feats]
+        # IoU of the lrtb branch against the same targets / assignment; no class or DFL term (reg_ch = 4)
+        st2 = self.forward_backward(pred_scores, pred_lrtb, sizes, targets, epoch_num, batch_height, batch_width, reuse=state,
+                                    weights=(0.0, float(self.loss_weight['iou']), 0.0))
+        total = state["out"].clone()
+        total[0] = total[0] + st2["out"][0]
+        total[1] = total[1] + st2["out"][1]
+        state = dict(state, out=total, grad_lrtb=st2["grad_distri"], keep_lrtb=st2)
+        # (the class-score gradient of the second call is exactly zero: w_cls = 0)
+        loss = _NsLossFn.apply(pred_scores, pred_distri, pred_lrtb, state)
+        items = torch.cat([total[1:4], torch.zeros(1, dtype=total.dtype, device=total.device)])
         return loss, items.detach()

@@ -73,6 +73,10 @@ class Detect(Node):
         for conv in self.reg_preds:
             conv.bias.data.fill_(1.0)
             conv.weight.data.fill_(0.)
+        if "reg_preds_dist" in self._modules:       # effidehead_distill_ns.py:59-66
+            for conv in self.reg_preds_dist:
+                conv.bias.data.fill_(1.0)
+                conv.weight.data.fill_(0.)
         if "cls_preds_ab" in self._modules:         # effidehead_fuseab.py:65-87
             for conv in self.cls_preds_ab:
                 conv.bias.data.fill_(-math.log((1 - self.prior_prob) / self.prior_prob))
@@ -89,10 +93,9 @@ class Model(nn.Module):
 
     def __init__(self, config, channels=3, num_classes=None, fuse_ab=False, distill_ns=False):
         super().__init__()
-        if distill_ns:
-            raise NotImplementedError("the distill_ns head (effidehead_distill_ns.py) is not built (SURVEY.md 8f N3, second half)")
         assert channels == 3
         self.fuse_ab = bool(fuse_ab)
+        self.distill_ns = bool(distill_ns)
         self.cfg = configs.normalize(config)
         self.num_classes = int(num_classes if num_classes is not None else 80)
         g = self.graph
@@ -100,7 +103,8 @@ class Model(nn.Module):
         self.backbone, self.neck = Node(), Node()
         # build_network passes use_dfl but not reg_max to Detect (yolo.py:130-131)
         self.detect = Detect(self.num_classes, hd["num_layers"], bool(hd["use_dfl"]), arch.DETECT_DEFAULT_REG_MAX)
-        for name in ("stems", "cls_convs", "reg_convs", "cls_preds", "reg_preds") + (("cls_preds_ab", "reg_preds_ab") if self.fuse_ab else ()):
+        for name in (("stems", "cls_convs", "reg_convs", "cls_preds") + (("reg_preds_dist",) if self.distill_ns else ()) + ("reg_preds",) +
+                     (("cls_preds_ab", "reg_preds_ab") if self.fuse_ab else ())):
             self.detect.add_module(name, Node())
         if self.fuse_ab:        # effidehead_fuseab.py:20-35
             self.detect.na = arch.AB_ANCHORS
@@ -121,7 +125,8 @@ class Model(nn.Module):
     def graph(self):
         g = self.__dict__.get("_graph")
         if g is None:
-            g = arch.build_graph(self.cfg, self.num_classes, fuse_ab=self.__dict__.get("fuse_ab", False))
+            g = arch.build_graph(self.cfg, self.num_classes, fuse_ab=self.__dict__.get("fuse_ab", False),
+                                 distill_ns=self.__dict__.get("distill_ns", False))
             self.__dict__["_graph"] = g
         return g
 
@@ -215,6 +220,9 @@ class Model(nn.Module):
             if self.fuse_ab:       # effidehead_fuseab.py:140: (x, cls_ab, reg_ab, cls_af, reg_af); engine.py:161-166 slices it
                 cls, reg, cls_ab, reg_ab = outs
                 return [(feats, cls_ab, reg_ab, cls, reg), feats]
+            if self.distill_ns:    # effidehead_distill_ns.py:104: (x, cls, reg_distri, reg_lrtb)
+                cls, reg, reg_dist = outs
+                return [(feats, cls, reg_dist, reg), feats]
             cls, reg = outs
             return [(feats, cls, reg), feats]
         export_mode = torch.onnx.is_in_onnx_export() or self.export

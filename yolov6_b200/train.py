@@ -420,6 +420,9 @@ class TrainEngine:
         self.reg = torch.empty(N, A, 4 * (g.reg_max + 1), dtype=torch.float32, device=dev)
         self.grad_cls = torch.zeros_like(self.cls)
         self.grad_reg = torch.zeros_like(self.reg)
+        if getattr(g, "distill_ns", False):   # N / S distillation student: DFL logits next to the 4 lrtb distances
+            self.reg_dist = torch.empty(N, A, g.dist_reg_ch, dtype=torch.float32, device=dev)
+            self.grad_reg_dist = torch.zeros_like(self.reg_dist)
         if getattr(g, "fuse_ab", False):      # anchor-aided branch (effidehead_fuseab.py:94-140): 3 anchors per pixel, rows (level, anchor, pixel)
             from .arch import AB_ANCHORS
             self.cls_ab = torch.empty(N, AB_ANCHORS * A, g.num_classes, dtype=torch.float32, device=dev)
@@ -483,7 +486,8 @@ class TrainEngine:
             if op.kind == "pred":
                 src, gsrc = view(op.src)
                 which, lvl = op.head
-                out, grad = (self.cls, self.grad_cls) if which == "cls" else (self.reg, self.grad_reg)
+                out, grad = {"cls": (self.cls, self.grad_cls), "reg": (self.reg, self.grad_reg),
+                             "reg_dist": (getattr(self, "reg_dist", None), getattr(self, "grad_reg_dist", None))}[which]
                 ch = out.shape[2]
                 chp = (ch + 15) // 16 * 16
                 lh, lw = self.sizes[lvl]
@@ -737,7 +741,7 @@ class TrainEngine:
                                                  lh * lw, AB_ANCHORS, nc, st["anchors"], off3, A3, st["dl_cls"].shape[3], st["dl_reg"].shape[3],
                                                  _p(st["dl_cls"]), _p(st["dl_reg"]), sp))
 
-    def backward(self, grad_cls, grad_reg, accumulate=False, first=0, last=None, grad_cls_ab=None, grad_reg_ab=None):
+    def backward(self, grad_cls, grad_reg, accumulate=False, first=0, last=None, grad_cls_ab=None, grad_reg_ab=None, grad_reg_dist=None):
         """Writes d(loss)/d(parameter) of every trainable parameter into the flat gradient buffer (`accumulate`: adds to it)
         given d(loss)/d(cls), d(loss)/d(reg) ([N,A,*] fp32).  `first`/`last` restrict the run to a slice of the call list
         (graph capture in bucket-sized segments)."""
@@ -745,6 +749,8 @@ class TrainEngine:
             self.grad_cls.copy_(grad_cls)
         if grad_reg is not None and grad_reg.data_ptr() != self.grad_reg.data_ptr():
             self.grad_reg.copy_(grad_reg)
+        if getattr(self.g, "distill_ns", False) and first == 0 and grad_reg_dist is not None and grad_reg_dist.data_ptr() != self.grad_reg_dist.data_ptr():
+            self.grad_reg_dist.copy_(grad_reg_dist)
         if getattr(self.g, "fuse_ab", False) and first == 0:      # None = the engine's own buffers were filled by the loss kernels
             for buf, gr in ((self.grad_cls_ab, grad_cls_ab), (self.grad_reg_ab, grad_reg_ab)):
                 if gr is not None and gr.data_ptr() != buf.data_ptr():
@@ -837,11 +843,17 @@ class _HeadFn(torch.autograd.Function):
         cls, reg = engine.forward(x)
         if getattr(engine.g, "fuse_ab", False):
             return cls.clone(), reg.clone(), engine.cls_ab.clone(), engine.reg_ab.clone()
+        if getattr(engine.g, "distill_ns", False):
+            return cls.clone(), reg.clone(), engine.reg_dist.clone()
         return cls.clone(), reg.clone()
 
     @staticmethod
-    def backward(ctx, g_cls, g_reg, g_cls_ab=None, g_reg_ab=None):
+    def backward(ctx, g_cls, g_reg, g_x1=None, g_x2=None):
         eng = ctx.engine
+        g_cls_ab, g_reg_ab, g_reg_dist = g_x1, g_x2, None
+        if getattr(eng.g, "distill_ns", False):       # third output = the DFL branch
+            g_cls_ab, g_reg_ab = None, None
+            g_reg_dist = torch.zeros_like(eng.grad_reg_dist) if g_x1 is None else g_x1.contiguous().float()
         f = lambda t: None if t is None else t.contiguous().float()   # noqa: E731
         # an output the loss did not use has no gradient: zero (None would mean "the engine's own buffer is already filled")
         g_cls = torch.zeros_like(eng.grad_cls) if g_cls is None else g_cls
@@ -849,7 +861,7 @@ class _HeadFn(torch.autograd.Function):
         if getattr(eng.g, "fuse_ab", False):
             g_cls_ab = torch.zeros_like(eng.grad_cls_ab) if g_cls_ab is None else g_cls_ab
             g_reg_ab = torch.zeros_like(eng.grad_reg_ab) if g_reg_ab is None else g_reg_ab
-        eng.backward(f(g_cls), f(g_reg), grad_cls_ab=f(g_cls_ab), grad_reg_ab=f(g_reg_ab))
+        eng.backward(f(g_cls), f(g_reg), grad_cls_ab=f(g_cls_ab), grad_reg_ab=f(g_reg_ab), grad_reg_dist=g_reg_dist)
         flat = eng.flat
         g = flat.gflat.clone()          # autograd may keep (steal) what it is given; the flat buffer is reused next step
         grads = []
