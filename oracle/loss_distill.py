@@ -20,10 +20,21 @@ def kl_rows(student, teacher, temperature):
     return F.kl_div(torch.log(ps), pt, reduction="none").sum(1)
 
 
+def cw_loss(s_feats, t_feats, temperature=1.0):
+    """distill_loss_cw, loss_distill.py:223-245: per level, KL over the H*W positions of every (image, channel) row, / (N*C)."""
+    total = 0.0
+    for sf, tf in zip(s_feats[:3], t_feats[:3]):
+        N, C, H, W = sf.shape
+        total = total + F.kl_div(F.log_softmax(sf.reshape(N, C, H * W) / temperature, dim=2),
+                                 F.log_softmax(tf.reshape(N, C, H * W).detach() / temperature, dim=2), reduction="sum",
+                                 log_target=True) * (temperature * temperature) / (N * C)
+    return total
+
+
 def compute_loss_distill(sizes, pred_scores, pred_distri, t_pred_scores, t_pred_distri, targets, *, strides, epoch_num, max_epoch,
                          temperature, num_classes=80, ori_img_size=640, warmup_epoch=0, use_dfl=True, reg_max=16, iou_type="giou",
-                         loss_weight=None, distill_weight=None):
-    """Returns (loss, items[iou, dfl_all, cls_all, cwd = 0]) like the reference with distill_feat=False."""
+                         loss_weight=None, distill_weight=None, s_feats=None, t_feats=None):
+    """Returns (loss, items[iou, dfl_all, cls_all, cwd]) like the reference; the feature term is on when s_feats / t_feats are given."""
     lw = loss_weight or {"class": 1.0, "iou": 2.5, "dfl": 0.5, "cwd": 10.0}
     dw = distill_weight or {"class": 1.0, "dfl": 1.0}
     base, items, a = oloss.compute_loss(sizes, pred_scores, pred_distri, targets, strides=strides, num_classes=num_classes,
@@ -46,9 +57,10 @@ def compute_loss_distill(sizes, pred_scores, pred_distri, t_pred_scores, t_pred_
         d_dfl = pred_distri.sum() * 0.0
     decay = ((1 - math.cos(epoch_num * math.pi / max_epoch)) / 2) * (0.01 - 1) + 1                                       # :196
     d_cls, d_dfl = d_cls * decay, d_dfl * decay
-    loss = base + lw["class"] * dw["class"] * d_cls + lw["dfl"] * dw["dfl"] * d_dfl
+    d_cw = cw_loss(s_feats, t_feats) * decay if s_feats is not None else torch.zeros(())
+    loss = base + lw["class"] * dw["class"] * d_cls + lw["dfl"] * dw["dfl"] * d_dfl + lw["cwd"] * d_cw
     items4 = torch.stack([items[0], items[1] + (lw["dfl"] * dw["dfl"] * d_dfl).detach(), items[2] + (lw["class"] * dw["class"] * d_cls).detach(),
-                          torch.zeros(())]).detach()
+                          (lw["cwd"] * d_cw).detach().to(items.dtype) if torch.is_tensor(d_cw) else torch.zeros(())]).detach()
     return loss, items4
 
 

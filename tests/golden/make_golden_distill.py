@@ -55,6 +55,30 @@ def main():
         store[f"{name}_pos"] = np.packbits(nz.numpy())
         store[f"{name}_grad_distri_rows"] = pdl.grad[nz].double().numpy()
         print(name, "loss", loss.item(), "items", items.tolist(), "positives", int(nz.sum()))
+    # ---- feature-map term (distill_feat=True, loss_distill.py:223-245) on seeded stand-ins for the three neck outputs
+    name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop = ["feat_" + CASES[0][0]] + CASES[0][1:]
+    strides = [8, 16, 32]
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed)
+    tps, tpd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed + 100)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=80), drop)
+    gf = torch.Generator().manual_seed(seed + 300)
+    s_feats = [torch.randn(B, c, h, w, generator=gf) for c, (h, w) in zip((32, 64, 128), sizes)]
+    t_feats = [torch.randn(B, c, h, w, generator=gf) * 1.3 for c, (h, w) in zip((32, 64, 128), sizes)]
+    cl = ComputeLossDistill(fpn_strides=strides, num_classes=80, ori_img_size=img, warmup_epoch=warm, use_dfl=True, reg_max=16,
+                            iou_type=iou_type, distill_weight={"class": 1.0, "dfl": 1.0}, distill_feat=True)
+    psl, pdl = ps.clone().requires_grad_(True), pd.clone().requires_grad_(True)
+    sfl = [f.clone().requires_grad_(True) for f in s_feats]
+    feats = [torch.zeros(B, 8, h, w) for h, w in sizes]
+    loss, items = cl((feats, psl, pdl), (feats, tps, tpd), sfl, t_feats, targets.clone(), epoch, max_epoch, T, 1, img, img)
+    loss.backward()
+    store[f"{name}_loss"] = np.float64(loss.item())
+    store[f"{name}_items"] = items.double().numpy()
+    store[f"{name}_feat_checksum"] = np.float64(sum(fab.checksum(f) for f in s_feats + t_feats))
+    for l, f in enumerate(sfl):
+        store[f"{name}_grad_feat{l}_abs"] = np.float64(f.grad.double().abs().sum().item())
+        store[f"{name}_grad_feat{l}_head"] = f.grad.flatten()[:2048].double().numpy()
+    print(name, "loss", loss.item(), "items", items.tolist())
     # ---- N / S variant (loss_distill_ns.py): a third student tensor, the lrtb distances of the inference branch
     for name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop in [["ns_" + c[0]] + c[1:] for c in CASES]:
         strides = [8, 16, 32]

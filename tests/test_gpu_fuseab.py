@@ -162,8 +162,6 @@ def test_distill_loss_matches_reference_golden(case):
     np.testing.assert_allclose(psd.grad.cpu().flatten()[:4096].double().numpy(), g[f"{name}_grad_scores_head"], rtol=2e-4, atol=1e-7)
     got_abs, ref_abs = float(psd.grad.double().abs().sum()), float(g[f"{name}_grad_scores_abs"])
     assert abs(got_abs - ref_abs) <= 1e-4 * ref_abs
-    with pytest.raises(NotImplementedError):
-        ComputeLoss(distill_feat=True)
 
 
 @pytest.mark.parametrize("case", golden_json("distill_cases.json"), ids=lambda c: "ns_" + c[0])
@@ -246,3 +244,81 @@ def test_distill_ns_student_with_fuseab_teacher_through_the_dropin_api():
     err = float(((got - ref).abs() / (1 + ref.abs())).max())
     print("distill_ns eval (fp32-equivalent mode) vs oracle:", err)
     assert got.shape == ref.shape and err < 1e-4
+
+
+def test_distill_feature_term_matches_reference_golden():
+    """distill_feat=True on the GPU path: loss / items 1e-5 and the gradient w.r.t. the student's feature maps (yv6_kl_rows over
+    (image, channel) rows of H*W positions) against the reference golden."""
+    from yolov6_b200.loss_distill import ComputeLoss
+    case = golden_json("distill_cases.json")[0]
+    name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop = case
+    g = golden_npz("distill.npz")
+    strides = [8, 16, 32]
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed)
+    tps, tpd = fab.synthetic_head_outputs(B, sizes, 80, 68, seed + 100)
+    targets = oloss.drop_targets(oloss.synthetic_targets(B, seed=seed + 1, num_classes=80), drop)
+    gf = torch.Generator().manual_seed(seed + 300)
+    s_feats = [torch.randn(B, c, h, w, generator=gf) for c, (h, w) in zip((32, 64, 128), sizes)]
+    t_feats = [torch.randn(B, c, h, w, generator=gf) * 1.3 for c, (h, w) in zip((32, 64, 128), sizes)]
+    dev = torch.device("cuda:0")
+    psd, pdd = ps.to(dev).requires_grad_(True), pd.to(dev).requires_grad_(True)
+    sfd = [f.to(dev).requires_grad_(True) for f in s_feats]
+    feats = [torch.zeros(B, 8, h, w, device=dev) for h, w in sizes]
+    cl = ComputeLoss(fpn_strides=strides, num_classes=80, ori_img_size=img, warmup_epoch=warm, use_dfl=True, reg_max=16, iou_type=iou_type,
+                     distill_weight={"class": 1.0, "dfl": 1.0}, distill_feat=True)
+    loss, items = cl((feats, psd, pdd), (feats, tps.to(dev), tpd.to(dev)), sfd, [f.to(dev) for f in t_feats], targets.to(dev), epoch, max_epoch,
+                     T, 1, img, img)
+    loss.backward()
+    ref = float(g[f"feat_{name}_loss"])
+    print("feat loss", float(loss.detach()), "reference", ref, items.tolist())
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref)
+    np.testing.assert_allclose(items.cpu().numpy(), g[f"feat_{name}_items"], rtol=1e-5, atol=1e-7)
+    for l, f in enumerate(sfd):
+        np.testing.assert_allclose(f.grad.cpu().flatten()[:2048].double().numpy(), g[f"feat_{name}_grad_feat{l}_head"], rtol=2e-4, atol=1e-9)
+        assert abs(float(f.grad.double().abs().sum()) - float(g[f"feat_{name}_grad_feat{l}_abs"])) <= 1e-4 * float(g[f"feat_{name}_grad_feat{l}_abs"])
+
+
+def test_feature_maps_are_differentiable_outputs_of_the_training_forward():
+    """model.return_featmaps = True: the training forward returns the real neck outputs (yolo.py:37-39) and a loss on them reaches
+    the backbone / neck parameters; the head-only gradients are unchanged by the extra outputs."""
+    from yolov6_b200.model import build_model
+    dev = torch.device("cuda:0")
+    sd = fab.fabricate_state_dict(golden_keys("yolov6n"), seed=0)
+    for k in sd:
+        if (".cls_preds." in k or ".reg_preds." in k) and k.endswith("weight"):
+            sd[k] = sd[k] * 0.1
+    x = fab.synthetic_images(2, 128, 128, seed=3).to(dev)
+    gen = torch.Generator().manual_seed(9)
+
+    def run(with_feats, feat_loss):
+        m = build_model("yolov6n", 80, dev)
+        m.load_state_dict(sd)
+        m.train()
+        m.return_featmaps = with_feats
+        (feats, cls, reg), fmaps = m(x)
+        L = (cls * wc).sum() + (reg * wr).sum()
+        if feat_loss:
+            L = L + sum((f * w).sum() for f, w in zip(fmaps, wf))
+        L.backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}, fmaps
+
+    m0 = build_model("yolov6n", 80, dev)
+    m0.load_state_dict(sd)
+    m0.train()
+    (f0, c0, r0), _ = m0(x)
+    wc, wr = torch.randn(c0.shape, generator=gen).to(dev), torch.randn(r0.shape, generator=gen).to(dev)
+    sizes = [tuple(f.shape[2:]) for f in f0]
+    chans = [t.c for t in m0.graph.feat]
+    wf = [torch.randn(2, c, h, w, generator=gen).to(dev) for c, (h, w) in zip(chans, sizes)]
+    base, _ = run(False, False)
+    same, fm = run(True, False)
+    assert [tuple(f.shape) for f in fm] == [(2, c, h, w) for c, (h, w) in zip(chans, sizes)] and all(f.requires_grad for f in fm)
+    worst = max(float((same[n] - base[n]).norm() / (base[n].norm() + 1e-30)) for n in base)
+    print("head-only gradients with / without feature-map outputs: worst rel diff", worst)
+    assert worst < 5e-3
+    both, _ = run(True, True)
+    moved = float((both["neck.Rep_n4.conv1.rbr_dense.conv.weight"] - base["neck.Rep_n4.conv1.rbr_dense.conv.weight"]).norm())
+    head_same = float((both["detect.cls_preds.0.weight"] - base["detect.cls_preds.0.weight"]).norm() / base["detect.cls_preds.0.weight"].norm())
+    assert moved > 0 and head_same < 5e-3          # the feature loss reaches the neck, the preds see only the head loss

@@ -59,3 +59,31 @@ def test_distill_ns_loss_matches_reference(case):
     np.testing.assert_allclose(pll.grad[nz].double().numpy(), g[f"{name}_grad_lrtb_rows"], rtol=2e-4, atol=1e-7)
     np.testing.assert_allclose(pdl.grad[nz].double().numpy(), g[f"{name}_grad_distri_rows"], rtol=2e-4, atol=1e-7)
     assert abs(float(psl.grad.double().abs().sum()) - float(g[f"{name}_grad_scores_abs"])) <= 1e-4 * float(g[f"{name}_grad_scores_abs"])
+
+
+def _feat_inputs(case):
+    name, img, B, seed = case[0], case[1], case[2], case[3]
+    sizes = [(img // s, img // s) for s in (8, 16, 32)]
+    gf = torch.Generator().manual_seed(seed + 300)
+    s_feats = [torch.randn(B, c, h, w, generator=gf) for c, (h, w) in zip((32, 64, 128), sizes)]
+    t_feats = [torch.randn(B, c, h, w, generator=gf) * 1.3 for c, (h, w) in zip((32, 64, 128), sizes)]
+    return s_feats, t_feats
+
+
+def test_distill_feature_term_matches_reference():
+    """distill_feat=True (loss_distill.py:223-245): loss, the four items and the gradient w.r.t. the student's feature maps."""
+    case = golden_json("distill_cases.json")[0]
+    name, img, B, seed, iou_type, warm, epoch, max_epoch, T, drop = case
+    g = golden_npz("distill.npz")
+    strides, sizes, ps, pd, tps, tpd, targets = make_inputs(case)
+    s_feats, t_feats = _feat_inputs(case)
+    assert abs(sum(fab.checksum(f) for f in s_feats + t_feats) - float(g[f"feat_{name}_feat_checksum"])) < 1e-6 * abs(float(g[f"feat_{name}_feat_checksum"]))
+    sfl = [f.clone().requires_grad_(True) for f in s_feats]
+    loss, items = odist.compute_loss_distill(sizes, ps, pd, tps, tpd, targets, strides=strides, epoch_num=epoch, max_epoch=max_epoch, temperature=T,
+                                             ori_img_size=img, warmup_epoch=warm, iou_type=iou_type, s_feats=sfl, t_feats=t_feats)
+    assert abs(loss.item() - float(g[f"feat_{name}_loss"])) <= 1e-5 * abs(float(g[f"feat_{name}_loss"]))
+    np.testing.assert_allclose(items.double().numpy(), g[f"feat_{name}_items"], rtol=1e-5, atol=1e-7)
+    loss.backward()
+    for l, f in enumerate(sfl):
+        np.testing.assert_allclose(f.grad.flatten()[:2048].double().numpy(), g[f"feat_{name}_grad_feat{l}_head"], rtol=2e-4, atol=1e-9)
+        assert abs(float(f.grad.double().abs().sum()) - float(g[f"feat_{name}_grad_feat{l}_abs"])) <= 1e-4 * float(g[f"feat_{name}_grad_feat{l}_abs"])

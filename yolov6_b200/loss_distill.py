@@ -15,8 +15,8 @@ Same constructor and call signature as yolov6/models/losses/loss_distill.py:14-2
     multiplied by sum(bbox_weight) / target_scores_sum (= 1, or 0 when no target score is positive; :318-323)
 with decay = ((1 - cos(epoch * pi / max_epoch)) / 2) * (0.01 - 1) + 1 (:196).  The detection part is `yv6_det_loss` (value +
 gradients in one launch); the two KL terms are `yv6_kl_rows`, which adds its gradients to the same buffers.  The channel-wise
-feature-map term (`distill_feat=True`, :223-245) needs gradients w.r.t. the neck outputs, which the training engine does not
-accept from outside: it raises NotImplementedError.  `ComputeLossNS` below is the N / S variant (loss_distill_ns.py, for the
+feature-map term (`distill_feat=True`, :223-245) is the same kernel over (image, channel) rows of H*W positions; it needs the real,
+differentiable neck outputs: set `model.return_featmaps = True` on the student and the teacher.  `ComputeLossNS` below is the N / S variant (loss_distill_ns.py, for the
 student head of effidehead_distill_ns.py).
 """
 import math
@@ -26,7 +26,6 @@ import torch
 from . import _lib
 from .assigners import _p
 from .loss import ComputeLoss as _DetLoss
-from .loss import _DetLossFn
 
 
 class ComputeLoss(_DetLoss):
@@ -36,12 +35,29 @@ class ComputeLoss(_DetLoss):
                  distill_feat=False, distill_weight={'class': 1.0, 'dfl': 1.0}):
         super().__init__(fpn_strides, grid_cell_size, grid_cell_offset, num_classes, ori_img_size, warmup_epoch, use_dfl, reg_max,
                          iou_type, loss_weight)
-        if distill_feat:
-            raise NotImplementedError("distill_feat (channel-wise feature-map KL, loss_distill.py:223-245) is not built: the training "
-                                      "engine takes gradients w.r.t. the head outputs only")
-        self.distill_feat = False
+        self.distill_feat = bool(distill_feat)       # needs `model.return_featmaps = True` on student and teacher (real neck outputs)
         self.distill_weight = distill_weight
         self._norm_gt_zero = 1
+        self._defer_fn = False
+
+    def _cw_term(self, s_featmaps, t_featmaps, decay, terms):
+        """distill_loss_cw (:223-245), temperature 1: per level KL over the H*W positions of every (image, channel) row, / (N*C).
+        Returns the gradients w.r.t. the student's feature maps; adds the weighted term to terms[2]."""
+        if len(s_featmaps) < 3 or any(f.dim() != 4 or f.shape[1] <= 1 for f in s_featmaps[:3]):
+            raise RuntimeError("distill_feat needs the real neck outputs: set model.return_featmaps = True on the student and the teacher")
+        lib = _lib.lib()
+        grads = []
+        for sf, tf in zip(s_featmaps[:3], t_featmaps[:3]):      # the reference sums levels 0..2
+            N, C, H, W = sf.shape
+            s32, t32 = sf.detach().float().contiguous(), tf.detach().float().contiguous()
+            if t32.shape != s32.shape:
+                raise RuntimeError(f"teacher feature map {tuple(t32.shape)} vs student {tuple(s32.shape)}")
+            g = torch.zeros_like(s32)
+            scale = float(self.loss_weight['cwd']) * decay / float(N * C)
+            _lib.check(lib.yv6_kl_rows(_lib.handle(sf.device.index or 0), _p(s32), _p(t32), N * C, H * W, 1.0, 0, 1, scale, 0, 0,
+                                       terms.data_ptr() + 16, _p(g), _lib.stream_ptr()))
+            grads.append(g)
+        return grads
 
     def __call__(self, outputs, t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch, temperature, step_num,
                  batch_height, batch_width):
@@ -60,7 +76,7 @@ class ComputeLoss(_DetLoss):
         decay = ((1 - math.cos(epoch_num * math.pi / max_epoch)) / 2) * (0.01 - 1) + 1          # :196
         T = float(temperature)
         w_cls, w_dfl = float(self.loss_weight['class']), float(self.loss_weight['dfl'])
-        terms = torch.zeros(2, dtype=torch.float64, device=dev)                 # weighted d_loss_cls, d_loss_dfl
+        terms = torch.zeros(3, dtype=torch.float64, device=dev)                 # weighted d_loss_cls, d_loss_dfl, d_loss_cw
         out = state["out"]
         s_cls = w_cls * float(self.distill_weight['class']) * decay * T * T
         _lib.check(lib.yv6_kl_rows(h, _p(ps), _p(ts), B * A, nc, T, 0, 1, s_cls, 0, 0, terms.data_ptr(), _p(state["grad_scores"]), sp))
@@ -71,31 +87,37 @@ class ComputeLoss(_DetLoss):
             # rows = (anchor, side); active = positives; mean over 4 * num_pos rows (out[5]); zero unless target_scores_sum (out[4]) > 0
             _lib.check(lib.yv6_kl_rows(h, _p(pd), _p(td), B * A * 4, R, T, _p(fg), 4, s_dfl, out.data_ptr() + 5 * 8, out.data_ptr() + 4 * 8,
                                        terms.data_ptr() + 8, _p(state["grad_distri"]), sp))
+        feat_grads = self._cw_term(s_featmaps, t_featmaps, decay, terms) if self.distill_feat else []
         total = out.clone()
-        total[0] = out[0] + terms[0] + terms[1]
+        total[0] = out[0] + terms[0] + terms[1] + terms[2]
         total[2] = out[2] + terms[1]               # loss_weight['dfl'] * loss_dfl_all
         total[3] = out[3] + terms[0]               # loss_weight['class'] * loss_cls_all
         state["out"] = total
+        state["cwd"] = terms[2:3]
         state["keep_distill"] = (ts, td, terms)
+        state["feat_grads"] = feat_grads
         self._last_state = state
-        loss = _DetLossFn.apply(pred_scores, pred_distri, state)
-        items = torch.cat([total[1:4], torch.zeros(1, dtype=total.dtype, device=dev)])   # (iou, dfl_all, cls_all, cwd = 0)
+        if self._defer_fn:                           # ComputeLossNS adds its third tensor and builds the function itself
+            return None, None
+        loss = _GradsFn.apply(state, [state["grad_scores"], state["grad_distri"]] + feat_grads, pred_scores, pred_distri,
+                              *list(s_featmaps[:3] if self.distill_feat else []))
+        items = torch.cat([total[1:4], terms[2:3]])   # (iou, dfl_all, cls_all, cwd)
         return loss, items.detach()
 
 
-class _NsLossFn(torch.autograd.Function):
-    """Three differentiable inputs (scores, DFL distributions, lrtb distances) -> the scalar loss of loss_distill_ns."""
+class _GradsFn(torch.autograd.Function):
+    """Scalar loss whose gradients w.r.t. its tensor inputs were produced by the kernels already: forward returns state['out'][0],
+    backward hands out the stored gradients scaled by the incoming one."""
 
     @staticmethod
-    def forward(ctx, pred_scores, pred_distri, pred_lrtb, state):
-        ctx.save_for_backward(state["grad_scores"], state["grad_distri"], state["grad_lrtb"])
-        ctx.dtypes = (pred_scores.dtype, pred_distri.dtype, pred_lrtb.dtype)
+    def forward(ctx, state, grads, *tensors):
+        ctx.save_for_backward(*grads)
+        ctx.dtypes = [t.dtype for t in tensors]
         return state["out"][0].clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        gs, gd, gl = ctx.saved_tensors
-        return (gs * grad_out).to(ctx.dtypes[0]), (gd * grad_out).to(ctx.dtypes[1]), (gl * grad_out).to(ctx.dtypes[2]), None
+        return (None, None, *[(g * grad_out).to(dt) for g, dt in zip(ctx.saved_tensors, ctx.dtypes)])
 
 
 class ComputeLossNS(ComputeLoss):
@@ -111,8 +133,12 @@ class ComputeLossNS(ComputeLoss):
     def __call__(self, outputs, t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch, temperature, step_num,
                  batch_height, batch_width):
         feats, pred_scores, pred_distri, pred_lrtb = outputs
-        loss, items = super().__call__((feats, pred_scores, pred_distri), t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch,
-                                       temperature, step_num, batch_height, batch_width)
+        self._defer_fn = True
+        try:
+            super().__call__((feats, pred_scores, pred_distri), t_outputs, s_featmaps, t_featmaps, targets, epoch_num, max_epoch,
+                             temperature, step_num, batch_height, batch_width)
+        finally:
+            self._defer_fn = False
         state = self._last_state
         sizes = [tuple(f.shape[2:]) for f in feats]
         # IoU of the lrtb branch against the same targets / assignment; no class or DFL term (reg_ch = 4)
@@ -121,8 +147,10 @@ class ComputeLossNS(ComputeLoss):
         total = state["out"].clone()
         total[0] = total[0] + st2["out"][0]
         total[1] = total[1] + st2["out"][1]
-        state = dict(state, out=total, grad_lrtb=st2["grad_distri"], keep_lrtb=st2)
+        state = dict(state, out=total, keep_lrtb=st2)
         # (the class-score gradient of the second call is exactly zero: w_cls = 0)
-        loss = _NsLossFn.apply(pred_scores, pred_distri, pred_lrtb, state)
-        items = torch.cat([total[1:4], torch.zeros(1, dtype=total.dtype, device=total.device)])
+        fg = state["feat_grads"]
+        loss = _GradsFn.apply(state, [state["grad_scores"], state["grad_distri"], st2["grad_distri"]] + fg, pred_scores, pred_distri, pred_lrtb,
+                              *list(s_featmaps[:3] if self.distill_feat else []))
+        items = torch.cat([total[1:4], state["cwd"]])
         return loss, items.detach()

@@ -96,6 +96,7 @@ class Model(nn.Module):
         assert channels == 3
         self.fuse_ab = bool(fuse_ab)
         self.distill_ns = bool(distill_ns)
+        self.return_featmaps = False      # True: the training forward returns the real, differentiable neck outputs (feature distillation)
         self.cfg = configs.normalize(config)
         self.num_classes = int(num_classes if num_classes is not None else 80)
         g = self.graph
@@ -215,16 +216,25 @@ class Model(nn.Module):
             # effidehead.py:72-92); `feats` carry only the level shapes ComputeLoss needs (loss.py:63-68)
             from .train import train_forward
             eng = self.train_engine()
+            want = bool(self.__dict__.get("return_featmaps", False))
+            if eng.external_feat_grads != want:       # differentiable neck outputs change the backward plan (train.py)
+                eng.external_feat_grads = want
+                eng._shape = None
             outs = train_forward(eng, x)
             feats = [torch.empty(x.shape[0], 1, h, w, device=x.device) for h, w in eng.sizes]
+            if want:                                  # the real feature maps (yolo.py:37-39), differentiable: feature distillation
+                nf = len(self.graph.feat)
+                outs, fmaps = outs[:-nf], list(outs[-nf:])
+            else:
+                fmaps = feats
             if self.fuse_ab:       # effidehead_fuseab.py:140: (x, cls_ab, reg_ab, cls_af, reg_af); engine.py:161-166 slices it
                 cls, reg, cls_ab, reg_ab = outs
-                return [(feats, cls_ab, reg_ab, cls, reg), feats]
+                return [(feats, cls_ab, reg_ab, cls, reg), fmaps]
             if self.distill_ns:    # effidehead_distill_ns.py:104: (x, cls, reg_distri, reg_lrtb)
                 cls, reg, reg_dist = outs
-                return [(feats, cls, reg_dist, reg), feats]
+                return [(feats, cls, reg_dist, reg), fmaps]
             cls, reg = outs
-            return [(feats, cls, reg), feats]
+            return [(feats, cls, reg), fmaps]
         export_mode = torch.onnx.is_in_onnx_export() or self.export
         eng = self.engine()
         # the engine owns (and reuses) its output buffers; callers of the drop-in API get their own tensors, as with the

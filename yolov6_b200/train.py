@@ -127,6 +127,10 @@ class TrainEngine:
         self.bucket_hook = None     # callable(k) invoked (eager mode) right after bucket k's gradients are unpacked
         self.overlap_wgrad = os.environ.get("YV6_WGRAD_OVERLAP", "1") != "0"   # weight gradients on a side stream (see backward)
         self._wg_stream = None
+        # the neck outputs as differentiable outputs of the training forward (feature-map distillation, loss_distill.py:223-245):
+        # off by default -- it changes the backward plan (every writer of those gradient slices accumulates onto the external one)
+        self.external_feat_grads = False
+        self._feat_grads = None
         self._build_state()
 
     # ================================================================== parameter-level state (shape independent)
@@ -632,6 +636,9 @@ class TrainEngine:
         cov = [np.zeros(b.c_total, dtype=bool) for b in self.g.bufs]
         need_zero = set()
         group_decision = {}
+        if self.external_feat_grads:         # backward() writes the external gradient (or zeros) into these slices first
+            for t in self.g.feat:
+                cov[t.buf][t.c_off:t.c_off + t.c] = True
 
         def decide(m):
             seg = cov[m["buf"]][m["off"]:m["off"] + m["n"]]
@@ -760,6 +767,15 @@ class TrainEngine:
         if first == 0:
             for gb in self.zero_gbufs:
                 gb.zero_()
+        if self.external_feat_grads and first == 0:       # after the clears above: these slices start from the external gradient
+            fg = self._feat_grads or [None] * len(self.g.feat)
+            for t, gr in zip(self.g.feat, fg):
+                sl = self.gbufs[t.buf][..., t.c_off:t.c_off + t.c]
+                if gr is None:
+                    sl.zero_()
+                else:
+                    sl.copy_(gr.permute(0, 2, 3, 1))                 # NCHW fp32 -> NHWC bf16
+            self._feat_grads = None
         calls = self.bwd_calls if last is None else self.bwd_calls[:last]
         # Weight gradients leave the critical path: a wgrad only feeds the gradient buffer, so it runs on a side stream next to
         # the dgrad of its own op and the (HBM-bound) BatchNorm backward of the next one.  Hazards: its dY operand lives in the
@@ -841,19 +857,28 @@ class _HeadFn(torch.autograd.Function):
     def forward(ctx, engine, x, *params):
         ctx.engine = engine
         cls, reg = engine.forward(x)
+        heads = [cls.clone(), reg.clone()]
         if getattr(engine.g, "fuse_ab", False):
-            return cls.clone(), reg.clone(), engine.cls_ab.clone(), engine.reg_ab.clone()
+            heads += [engine.cls_ab.clone(), engine.reg_ab.clone()]
         if getattr(engine.g, "distill_ns", False):
-            return cls.clone(), reg.clone(), engine.reg_dist.clone()
-        return cls.clone(), reg.clone()
+            heads += [engine.reg_dist.clone()]
+        ctx.n_heads = len(heads)
+        feats = []
+        if engine.external_feat_grads:       # neck outputs, NCHW fp32 copies (reference `featmaps`, yolo.py:37-39)
+            feats = [engine.bufs[t.buf][..., t.c_off:t.c_off + t.c].permute(0, 3, 1, 2).float().contiguous() for t in engine.g.feat]
+        return (*heads, *feats)
 
     @staticmethod
-    def backward(ctx, g_cls, g_reg, g_x1=None, g_x2=None):
+    def backward(ctx, *grads):
         eng = ctx.engine
-        g_cls_ab, g_reg_ab, g_reg_dist = g_x1, g_x2, None
+        g_cls, g_reg = grads[0], grads[1]
+        extra = list(grads[2:ctx.n_heads])
+        g_feats = list(grads[ctx.n_heads:])
+        g_cls_ab = g_reg_ab = g_reg_dist = None
+        if getattr(eng.g, "fuse_ab", False):
+            g_cls_ab, g_reg_ab = extra[0], extra[1]
         if getattr(eng.g, "distill_ns", False):       # third output = the DFL branch
-            g_cls_ab, g_reg_ab = None, None
-            g_reg_dist = torch.zeros_like(eng.grad_reg_dist) if g_x1 is None else g_x1.contiguous().float()
+            g_reg_dist = torch.zeros_like(eng.grad_reg_dist) if extra[0] is None else extra[0].contiguous().float()
         f = lambda t: None if t is None else t.contiguous().float()   # noqa: E731
         # an output the loss did not use has no gradient: zero (None would mean "the engine's own buffer is already filled")
         g_cls = torch.zeros_like(eng.grad_cls) if g_cls is None else g_cls
@@ -861,6 +886,8 @@ class _HeadFn(torch.autograd.Function):
         if getattr(eng.g, "fuse_ab", False):
             g_cls_ab = torch.zeros_like(eng.grad_cls_ab) if g_cls_ab is None else g_cls_ab
             g_reg_ab = torch.zeros_like(eng.grad_reg_ab) if g_reg_ab is None else g_reg_ab
+        if eng.external_feat_grads:
+            eng._feat_grads = g_feats
         eng.backward(f(g_cls), f(g_reg), grad_cls_ab=f(g_cls_ab), grad_reg_ab=f(g_reg_ab), grad_reg_dist=g_reg_dist)
         flat = eng.flat
         g = flat.gflat.clone()          # autograd may keep (steal) what it is given; the flat buffer is reused next step
