@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YV6_ABI_VERSION 3
+#define YV6_ABI_VERSION 4
 
 enum {
   YV6_OK = 0,
@@ -105,6 +105,12 @@ typedef struct yv6_conv_desc {
                              * staging half of the weight tile): 0 = auto (3x3 stride-1 layers over >= 128 input channels),
                              * 1 = on whenever the layer has >= 2 M tiles, -1 = off.
                              * Occupies what used to be tail padding: the struct size is unchanged. */
+  /* ABI 4.  pair_view = 1: this 3x2 / stride (2, 1) descriptor is the column-pair view of a 3x3 stride-2 conv (see stride_w) and
+   * its weights are zero where the view has no tap -- w[:, :, 0, 0 .. Cin/2) (left tap, even pixel of the pair).  The halo-reuse
+   * mainloop (one 9 x 33 input box per 8 x 16 output tile instead of one box per tap) then skips the all-zero 64-channel
+   * blocks, so the view costs no extra MACs when Cin/2 % 64 == 0.  0 = no promise (every block is multiplied). */
+  int32_t pair_view;
+  int32_t reserved0;        /* keeps the struct size a multiple of 8; must be 0 */
 } yv6_conv_desc;
 
 int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);

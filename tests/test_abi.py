@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/yv6.h but not exported"
     assert set(_lib.exported_symbols()) <= set(names)
-    assert lib.yv6_abi_version() == 3
+    assert lib.yv6_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

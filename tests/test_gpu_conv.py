@@ -97,6 +97,59 @@ def test_conv_fwd(case, pair):
     assert err <= tol, f"{name}: rel err {err:.3e} > {tol:.1e}"
 
 
+PAIR_VIEW_CASES = [
+    # name, N, H, W, Cin, Cout, act, nsplit, residual, force, expect (halo, resident weights)
+    ("c32_one_block", 2, 64, 64, 32, 64, "relu", 1, False, None, (2, 1)),                 # 2*Cin = 64: a single channel block, nothing skipped
+    ("c64_skip_resident", 2, 32, 48, 64, 64, "silu", 1, False, None, (2, 1)),             # zero block of the left tap skipped, 9 resident tiles
+    ("c64_cout128_streamed", 1, 64, 64, 64, 128, "relu", 1, True, None, (2, 0)),          # weights through the ring
+    ("c64_ragged", 3, 34, 20, 64, 96, "relu", 1, False, dict(halo=1), (2, 0)),            # Ho = 17, Wo = 10: partial tiles in both directions
+    ("c128_forced", 2, 64, 32, 128, 128, "relu", 1, False, dict(halo=1), (2, 0)),         # four channel blocks, two of them skipped on the left taps
+    ("c64_x3", 2, 32, 32, 64, 64, "relu", 3, False, None, (2, 0)),                        # bf16x3 planes
+    ("c64_many_tiles", 8, 160, 160, 64, 64, "relu", 1, False, None, (2, 1)),              # persistent loop, resident weights reused
+    ("c64_generic_fallback", 2, 20, 20, 64, 64, "relu", 1, False, None, (0, 0)),          # 10 x 10 output: the fixed tile wastes too much
+]
+
+
+@pytest.mark.parametrize("pair", [1, -1], ids=["cta_pair", "single_cta"])
+@pytest.mark.parametrize("case", PAIR_VIEW_CASES, ids=[c[0] for c in PAIR_VIEW_CASES])
+def test_conv_stride2_pair_view(case, pair):
+    """A 3x3 stride-2 conv run as the 3x2 / stride (2, 1) conv on the column-pair view [N, H, W/2, 2*Cin] of its input
+    (include/yv6.h `stride_w`, `pair_view`; the halo-reuse mainloop MODE 3 / 4 of yv6_conv_igemm.cu) against the fp64
+    convolution of the ORIGINAL 3x3 stride-2 problem."""
+    from yolov6_b200 import ops
+    name, N, H, W, Cin, Cout, act, nsplit, use_res, force, expect = case
+    force = dict(force or {}, pair=pair)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.randn(Cout, 3, 3, Cin, generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = H // 2, W // 2
+    res = torch.randn(N, Ho, Wo, Cout, generator=g) if use_res else None
+    bias = ops.pad_bias(b.to(dev), Cout)
+    wv = ops.pair_view_weights(w)
+    plan = ops.conv_plan((N, H, W // 2, 2 * Cin), tuple(wv.shape), 2, nsplit, force, stride_w=1, pad=(1, 1), out_hw=(0, Wo), pair_view=1)
+    assert plan["halo"] == expect[0], plan
+    if pair < 0:        # (a CTA pair stages half of the weight tile per CTA, so more layers keep their weights resident)
+        assert plan["a_res"] % 10 == expect[1], plan
+    kw = dict(stride=2, stride_w=1, pad=(1, 1), out_hw=(0, Wo), pair_view=1, act=act, alpha=0.5, force=force)
+    if nsplit == 1:
+        xb, wb = x.to(torch.bfloat16), wv.to(torch.bfloat16)
+        resb = res.to(torch.bfloat16) if use_res else None
+        y = torch.zeros(N, Ho, Wo, Cout, dtype=torch.bfloat16, device=dev)
+        ops.conv_fwd(xb.view(N, H, W // 2, 2 * Cin).to(dev), wb.to(dev), bias, y, res=resb.to(dev) if use_res else None, **kw)
+        ref = ref_conv(xb.float(), w.to(torch.bfloat16).float(), b, 2, act, resb.float() if use_res else None, 0.5)
+        got, tol = y.float().cpu().double(), 2.0 ** -8
+    else:
+        x3, w3 = ops.split3(x), ops.split3(wv)
+        y = torch.zeros(3, N, Ho, Wo, Cout, dtype=torch.bfloat16, device=dev)
+        ops.conv_fwd(x3.view(3, N, H, W // 2, 2 * Cin).to(dev), w3.to(dev), bias, y, nsplit=3, **kw)
+        ref = ref_conv(x, w, b, 2, act, None, 0.5)
+        got, tol = y.float().sum(0).cpu().double(), 5e-6
+    err = ((got - ref).abs() / (1.0 + ref.abs())).max().item()
+    assert err <= tol, f"{name}: rel err {err:.3e} > {tol:.1e}"
+
+
 def test_conv_rejects_bad_arguments():
     from yolov6_b200 import ops
     dev = torch.device("cuda:0")

@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
         ("force_bw", C.c_int32), ("force_bh", C.c_int32), ("force_bi", C.c_int32), ("force_bn", C.c_int32),
         ("force_stages", C.c_int32), ("force_grid", C.c_int32), ("force_direct", C.c_int32), ("force_halo", C.c_int32),
         ("pad_w", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32), ("force_groups", C.c_int32),
-        ("trace", C.c_void_p), ("stride_w", C.c_int32), ("force_pair", C.c_int32),
+        ("trace", C.c_void_p), ("stride_w", C.c_int32), ("force_pair", C.c_int32), ("pair_view", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -59,7 +59,8 @@ struct ConvKParams {
   int32_t c_chunk;        // output columns per staged chunk: 64 (bf16) or 32 (fp32) -> 128-byte rows
   // halo mode (3x3 stride-1, Cin % 64 == 0): one (BH+2)x(BW+2) input box per channel block feeds all
   // nine taps through UMMA descriptors offset into it; B tiles ride their own ring (or stay resident).
-  int32_t halo, a_stages, b_stages, b_resident;
+  int32_t halo, a_stages, b_stages, b_resident;   // halo: 1 = 3x3 stride 1, 2 = column-pair view of a 3x3 stride-2 conv
+  int32_t skip_cb;                                // halo 2: the first skip_cb channel blocks of the s = 0 taps are all-zero weights (skipped)
   int32_t a_region_bytes, b_region_bytes;  // smem carve: [A ring][B ring][2 C buffers][barriers]
   // CTA-pair mode (cluster of two CTAs, tcgen05 cta_group::2): one schedule unit = two consecutive M tiles (one per CTA)
   // x one N tile; every CTA stages its own input tile and HALF of the weight tile (b_rows = BN / 2 rows), one
@@ -77,6 +78,16 @@ struct ConvKParams {
 constexpr int kHaloW = 10, kHaloH = 18;                   // BW = 8, BH = 16 output tile + 1-pixel border
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;         // 23040
 constexpr int kHaloStageBytes = 24 * 1024;                // rounded up to the 1024-byte swizzle atom
+// Halo geometry of a kernel variant.  S2 = false: 3x3 stride 1 (above).  S2 = true: 3x2 kernel with stride (2, 1) and padding
+// (1, 1) -- a 3x3 stride-2 conv on the column-pair view [N, H, W/2, 2C] of its input: the same 8 x 16 output tile reads a
+// 9 x 33 box; tap (r, s) starts (9 r + s) pixels into it and consecutive output rows are TWO box rows apart (the UMMA
+// descriptor's stride between 8-row groups), so the stride costs nothing at issue time.
+template <bool S2>
+struct HaloGeom {
+  static constexpr int W = S2 ? 9 : kHaloW, H = S2 ? 33 : kHaloH, KW = S2 ? 2 : 3, TAPS = S2 ? 6 : 9, SH = S2 ? 2 : 1;
+  static constexpr int kBytes = W * H * 128;
+  static constexpr int kStageBytes = ((kBytes + 1023) / 1024) * 1024;     // 24 KB / 38 KB
+};
 constexpr int kMaxAStages = 6, kMaxBStages = 40;
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
@@ -384,7 +395,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr bool HALO = (MODE != 0);
-  constexpr bool BRES = (MODE == 2);
+  constexpr bool BRES = (MODE == 2 || MODE == 4);
+  using HG = HaloGeom<(MODE >= 3)>;
   // schedule: CTA (or CTA pair) takes units unit0, unit0 + ustep, ...; in pair mode this CTA computes M tile `rank` of a unit
   const int rank = CP ? (int)cluster_ctarank() : 0;
   const int unit0 = CP ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -435,7 +447,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // pair mode: both CTAs fill their own rings; all completion bytes land on the LEADER's full barriers, which the
       // leader's producer arms with the byte count of both CTAs (a peer's bytes may arrive before the arming: the
       // transaction count is signed, the phase cannot complete before the leader's own arrival)
-      const uint32_t a_tx = (uint32_t)kHaloBytes * (CP ? 2u : 1u), b_tx = (uint32_t)(p.b_rows * 128) * (CP ? 2u : 1u);
+      const uint32_t a_tx = (uint32_t)HG::kBytes * (CP ? 2u : 1u), b_tx = (uint32_t)(p.b_rows * 128) * (CP ? 2u : 1u);
       const int nrow0 = rank * p.b_rows;                      // this CTA's half of the weight tile's rows
       for (int tile = unit0; tile < p.num_tiles; tile += ustep) {
         const TileCoord t = CP ? decode_unit(p, tile, rank) : decode_tile(p, tile);
@@ -450,12 +462,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (elect_one()) {
               if (leader) mbar_expect_tx(&a_full[sa], a_tx);
-              if (CP) tma_load_5d_pair(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 - 1, t.i0, pa);
-              else tma_load_5d(sA + (size_t)sa * kHaloStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 - 1, t.i0, pa);
+              if (CP) tma_load_5d_pair(sA + (size_t)sa * HG::kStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 * HG::SH - 1, t.i0, pa);
+              else tma_load_5d(sA + (size_t)sa * HG::kStageBytes, &tmA, &a_full[sa], cb * 64, t.w0 - 1, t.h0 * HG::SH - 1, t.i0, pa);
             }
             __syncwarp();
             if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
-            for (int tap = 0; tap < 9; ++tap, ++slot) {
+            for (int tap = 0; tap < HG::TAPS; ++tap) {
+              if (HG::SH == 2 && (tap % HG::KW) == 0 && cb < p.skip_cb) continue;     // all-zero weight block
               if constexpr (BRES) {
                 if (first && elect_one()) {
                   if (leader) mbar_expect_tx(&b_full[slot], b_tx);
@@ -473,6 +486,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 __syncwarp();
                 if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
               }
+              ++slot;
             }
           }
         }
@@ -548,9 +562,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if constexpr (HALO) {
       // A descriptors walk the halo tile: 8-row groups are the 8 pixels of one output row, one halo row
       // (10 pixels = 1280 bytes) apart; tap (r,s) just shifts the start address by (10 r + s) pixels.
-      const uint64_t desc_a = umma_smem_desc(0, (uint32_t)(kHaloW * 128), 2u);
+      const uint64_t desc_a = umma_smem_desc(0, (uint32_t)(HG::W * 128 * HG::SH), 2u);
       const uint64_t desc_b = umma_smem_desc(0, 1024u, 2u);
-      const uint32_t halo_step = (uint32_t)kHaloStageBytes >> 4;
+      const uint32_t halo_step = (uint32_t)HG::kStageBytes >> 4;
+      const int skip_cb = p.skip_cb, cin_blocks = p.cin_blocks;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       bool first = true;
@@ -564,15 +579,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&a_full[sa], pha);
           tc_fence_after();
           const uint32_t a0 = a_base + (uint32_t)sa * halo_step;
+          const bool skip_s0 = (HG::SH == 2) && (pc % cin_blocks) < skip_cb;      // this channel block of the s = 0 taps is all zero
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap, ++slot) {
+          for (int tap = 0; tap < HG::TAPS; ++tap) {
+            if (HG::SH == 2 && (tap % HG::KW) == 0 && skip_s0) continue;
             const int bs = b_resident ? slot : sb;
             // resident weights were loaded (and waited for) during this CTA's first tile
             if (!b_resident || first) {
               mbar_wait(&b_full[bs], b_resident ? 0u : phb);
               tc_fence_after();
             }
-            const uint64_t ad = desc_a | (uint64_t)(a0 + (uint32_t)((tap / 3) * kHaloW + (tap % 3)) * 8u);
+            const uint64_t ad = desc_a | (uint64_t)(a0 + (uint32_t)((tap / HG::KW) * HG::W + (tap % HG::KW)) * 8u);
             const uint64_t bd = desc_b | (uint64_t)(b_base + (uint32_t)bs * b_step);
             if (elect_one()) {
               mma(d_tmem, ad, bd, started);
@@ -584,6 +601,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             started = 1u;
             if (!b_resident && ++sb == b_stages) { sb = 0; phb ^= 1; }
+            ++slot;
           }
           if (elect_one()) commit(&a_empty[sa]);
           __syncwarp();
@@ -967,6 +985,23 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
       k.BI = 1;
     }
   }
+  // halo 2: the column-pair view of a 3x3 stride-2 conv (3x2 kernel, stride (2, 1), pad (1, 1), out_w = W), same 8 x 16 tile
+  // over a 9 x 33 box: ~2.6x fewer A bytes from L2 than one box per tap.  pair_view additionally promises that the weights of
+  // the left tap are zero over the even pixel's channels [0, Cin/2): whole 64-channel blocks of zeros are skipped.
+  k.skip_cb = 0;
+  if (d->kh == 3 && d->kw == 2 && d->stride == 2 && stride_w == 1 && d->pad == 1 && pad_w == 1 && d->out_w == d->W && d->out_h == 0 &&
+      d->Cin % 64 == 0 && d->force_bw == 0 && d->force_halo >= 0 && d->H % 2 == 0) {
+    const long generic = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
+    const long halo_tiles = (long)ceil_div(k.Wo, 8) * ceil_div(k.Ho, 16) * d->N;
+    // auto: where the input operand dominates the L2 traffic (<= 64 real input channels) and the fixed tile wastes < 25 %
+    if (d->force_halo > 0 || (halo_tiles * 4 <= generic * 5 && d->Cin <= 128)) {
+      k.halo = 2;
+      k.BW = 8;
+      k.BH = 16;
+      k.BI = 1;
+      if (d->pair_view && (d->Cin / 2) % 64 == 0) k.skip_cb = d->Cin / 128;
+    }
+  }
   const long m_tiles = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
   // N tiling: BN <= 256, multiple of 16; pick the split whose wave count x tile cost is smallest
   // (a 448-tile layer on 148 SMs runs 4 waves at BN=256 but 7 half-cost waves at BN=128).
@@ -1018,20 +1053,23 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   k.b_stage_bytes = ((k.b_rows * k.kb_bytes + 1023) / 1024) * 1024;
   const int budget = h->max_smem_optin - 1024 - 1024 - kCBufCount * kCBufBytes - kBiasSmemFloats * (int)sizeof(float);
   if (k.halo) {
-    const int b_tiles = k.npairs * k.cin_blocks * 9;   // B tiles one output tile consumes
+    const int halo_stage = (k.halo == 2) ? HaloGeom<true>::kStageBytes : HaloGeom<false>::kStageBytes;
+    const int min_a = (k.halo == 2) ? 2 : 3;          // A stages that must fit next to resident weights
+    // B tiles one output tile consumes (halo 2: six taps, minus the all-zero blocks of the three left taps)
+    const int b_tiles = (k.halo == 2) ? k.npairs * (k.cin_blocks * 6 - 3 * k.skip_cb) : k.npairs * k.cin_blocks * 9;
     k.b_resident = (k.tiles_n == 1 && b_tiles <= kMaxBStages && d->force_stages == 0 &&
-                    (long)b_tiles * k.b_stage_bytes + 3 * kHaloStageBytes <= budget) ? 1 : 0;
+                    (long)b_tiles * k.b_stage_bytes + min_a * halo_stage <= budget) ? 1 : 0;
     if (k.b_resident) {
       k.b_stages = b_tiles;
-      k.a_stages = std::min(kMaxAStages, (budget - b_tiles * k.b_stage_bytes) / kHaloStageBytes);
+      k.a_stages = std::min(kMaxAStages, (budget - b_tiles * k.b_stage_bytes) / halo_stage);
     } else {
-      k.a_stages = (budget - 3 * kHaloStageBytes >= 3 * k.b_stage_bytes) ? 3 : 2;
-      k.b_stages = std::min(kMaxBStages, (budget - k.a_stages * kHaloStageBytes) / k.b_stage_bytes);
+      k.a_stages = (k.halo == 1 && budget - 3 * halo_stage >= 3 * k.b_stage_bytes) ? 3 : 2;
+      k.b_stages = std::min(kMaxBStages, (budget - k.a_stages * halo_stage) / k.b_stage_bytes);
       if (d->force_stages > 0) k.b_stages = std::min(k.b_stages, std::max(2, d->force_stages));
     }
     YV6_REQUIRE(k.a_stages >= 2 && k.b_stages >= 2, "conv(halo): not enough shared memory");
     k.stages = k.b_stages;
-    k.a_region_bytes = k.a_stages * kHaloStageBytes;
+    k.a_region_bytes = k.a_stages * halo_stage;
     k.b_region_bytes = k.b_stages * k.b_stage_bytes;
   } else {
     const int stage_bytes = k.a_stage_bytes + k.b_stage_bytes;
@@ -1090,11 +1128,15 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
 using namespace yv6;
 
 using ConvKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
-static const ConvKernelFn kConvKernels[2][2][3] = {
-    {{conv_igemm_kernel<2, 0, false>, conv_igemm_kernel<2, 1, false>, conv_igemm_kernel<2, 2, false>},
-     {conv_igemm_kernel<4, 0, false>, conv_igemm_kernel<4, 1, false>, conv_igemm_kernel<4, 2, false>}},
-    {{conv_igemm_kernel<2, 0, true>, conv_igemm_kernel<2, 1, true>, conv_igemm_kernel<2, 2, true>},
-     {conv_igemm_kernel<4, 0, true>, conv_igemm_kernel<4, 1, true>, conv_igemm_kernel<4, 2, true>}}};
+static const ConvKernelFn kConvKernels[2][2][5] = {
+    {{conv_igemm_kernel<2, 0, false>, conv_igemm_kernel<2, 1, false>, conv_igemm_kernel<2, 2, false>, conv_igemm_kernel<2, 3, false>,
+      conv_igemm_kernel<2, 4, false>},
+     {conv_igemm_kernel<4, 0, false>, conv_igemm_kernel<4, 1, false>, conv_igemm_kernel<4, 2, false>, conv_igemm_kernel<4, 3, false>,
+      conv_igemm_kernel<4, 4, false>}},
+    {{conv_igemm_kernel<2, 0, true>, conv_igemm_kernel<2, 1, true>, conv_igemm_kernel<2, 2, true>, conv_igemm_kernel<2, 3, true>,
+      conv_igemm_kernel<2, 4, true>},
+     {conv_igemm_kernel<4, 0, true>, conv_igemm_kernel<4, 1, true>, conv_igemm_kernel<4, 2, true>, conv_igemm_kernel<4, 3, true>,
+      conv_igemm_kernel<4, 4, true>}}};
 
 // Once per device: opt the kernels in to the large dynamic shared memory and ask how many 2-CTA clusters of the conv
 // kernel (one CTA per SM) can be co-resident -- the grid of the pair variants.
@@ -1102,7 +1144,7 @@ static int conv_configure(yv6_handle* h) {
   if (h->configured & YV6_CFG_CONV) return YV6_OK;
   for (int c = 0; c < 2; ++c)
     for (int g = 0; g < 2; ++g)
-      for (int m = 0; m < 3; ++m)
+      for (int m = 0; m < 5; ++m)
         YV6_CHECK_CUDA(cudaFuncSetAttribute(kConvKernels[c][g][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem_optin));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1169,11 +1211,12 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
     cuuint64_t strides[4] = {pix, pix * d->W, pix * d->W * d->H, plane_stride};
     cuuint32_t box[5] = {(cuuint32_t)k.kb_elems, (cuuint32_t)(k.BW * k.stride_w), (cuuint32_t)(k.BH * d->stride),
                          (cuuint32_t)k.BI, 1};
-    if (k.halo) {
-      box[1] = kHaloW;
-      box[2] = kHaloH;
-    }
     cuuint32_t estr[5] = {1, (cuuint32_t)k.stride_w, (cuuint32_t)d->stride, 1, 1};
+    if (k.halo) {       // one dense box per channel block
+      box[1] = (k.halo == 2) ? HaloGeom<true>::W : HaloGeom<false>::W;
+      box[2] = (k.halo == 2) ? HaloGeom<true>::H : HaloGeom<false>::H;
+      estr[1] = estr[2] = 1;
+    }
     CUresult cr = h->encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->x), dims,
                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, plan.swz,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1230,7 +1273,7 @@ extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream)
     tmC = tmA;  // unused by the kernel
   }
 
-  const int mode = k.halo ? (k.b_resident ? 2 : 1) : 0;
+  const int mode = k.halo ? (k.halo == 2 ? 3 : 1) + (k.b_resident ? 1 : 0) : 0;
   ConvKernelFn fn = kConvKernels[k.cpair][k.groups == 4 ? 1 : 0][mode];
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops
 from ._lib import ACT_CODES, DT_BF16, DT_F32, DT_U8, ConvDesc, StemDesc
 from .fold import fold_op
 
@@ -88,14 +88,9 @@ class InferEngine:
                     wi = wi.float().to(dev)
                     packed.append(_split3(wi).contiguous() if self.nsplit == 3 else wi.to(torch.bfloat16).contiguous())
                 ent["w"] = packed
-                if op.kind == "conv" and op.k == 3 and op.s == 2 and op.cin <= 32:
+                if op.kind == "conv" and op.k == 3 and op.s == 2 and op.cin <= 64:
                     # column-pair view (see _plan): [Cout][3][2][2*Cin]; tap 0 = input columns (2j-2 | 2j-1), tap 1 = (2j | 2j+1)
-                    w33 = ws[0].float()
-                    wf = torch.zeros(op.cout, 3, 2, 2 * op.cin)
-                    wf[:, :, 0, op.cin:] = w33[:, :, 0]
-                    wf[:, :, 1, :op.cin] = w33[:, :, 1]
-                    wf[:, :, 1, op.cin:] = w33[:, :, 2]
-                    wf = wf.to(dev)
+                    wf = ops.pair_view_weights(ws[0].float()).to(dev)
                     ent["w_pair"] = _split3(wf).contiguous() if self.nsplit == 3 else wf.to(torch.bfloat16).contiguous()
                 bias = torch.zeros((op.cout + 255) // 256 * 256, dtype=torch.float32, device=dev)
                 bias[:op.cout] = b.float().to(dev)
@@ -221,15 +216,6 @@ class InferEngine:
                                                   k=d.kh, s=d.stride, ho=oh, wo=ow, h=sh, w=sw,
                                                   flops=2.0 * N * oh * ow * d.Cout * op.cin * d.kh * d.kw,
                                                   y_f32=op.kind == "pred"))
-                    if "w_pair" in ent and op.src.c_off == 0 and sct == op.cin and sw % 2 == 0:
-                        # 3x3 stride-2 conv over <= 32 channels: 64-byte pixels fetched with an element stride of 2 keep the
-                        # TMA unit, not the tensor pipe, busy (ERBlock_2.0 of YOLOv6-S: 170 us for 0.9 GFLOP/img).  On the
-                        # column-pair view of the same memory, [N, H, W/2, 2*Cin], it is a 3x2 conv with stride (2, 1):
-                        # contiguous 2*Cin-channel rows, 4/3 of the MACs (the extra quarter multiplies zero weights).
-                        d.W, d.Cin, d.x_c_total = sw // 2, 2 * op.cin, 2 * op.cin
-                        d.w = ent["w_pair"].data_ptr()
-                        d.w_plane_stride = ent["w_pair"].stride(0) if P == 3 else 0
-                        d.kw, d.stride_w, d.pad_w, d.out_w = 2, 1, 1, sw // 2
                     if op.kind == "pred":
                         which, lvl = op.head
                         out = plan[which]
@@ -256,6 +242,24 @@ class InferEngine:
                         d.res_img_stride, d.res_h_stride, d.res_w_stride = rh * rw * rct, rw * rct, rct
                         d.res_plane_stride = rbuf.stride(0) if P == 3 else 0
                         d.alpha = ent["alpha"]
+                    if "w_pair" in ent and op.src.c_off == 0 and sct == op.cin and sw % 2 == 0:
+                        # 3x3 stride-2 conv over <= 64 channels.  On the column-pair view of the same memory, [N, H, W/2, 2*Cin],
+                        # it is a 3x2 conv with stride (2, 1) over contiguous 2*Cin-channel rows.  <= 32 channels: 64-byte pixels
+                        # fetched with an element stride of 2 keep the TMA unit, not the tensor pipe, busy (ERBlock_2.0 of
+                        # YOLOv6-S: 170 -> 135 us).  And where the library's halo-reuse mainloop takes the view (one 9 x 33 input
+                        # box per 8 x 16 output tile instead of one box per tap, include/yv6.h `pair_view`) the input operand
+                        # crosses L2 -> shared memory 2.6x less often, which is what bounds these small-K layers.
+                        keep = (d.W, d.Cin, d.x_c_total, d.w, d.w_plane_stride, d.kw, d.stride_w, d.pad_w, d.out_w)
+                        d.W, d.Cin, d.x_c_total = sw // 2, 2 * op.cin, 2 * op.cin
+                        d.w = ent["w_pair"].data_ptr()
+                        d.w_plane_stride = ent["w_pair"].stride(0) if P == 3 else 0
+                        d.kw, d.stride_w, d.pad_w, d.out_w = 2, 1, 1, sw // 2
+                        d.pair_view = 1
+                        out10 = (C.c_int32 * 10)()
+                        _lib.check(self.lib.yv6_conv_plan(self.handle, C.byref(d), out10))
+                        if op.cin > 32 and out10[8] != 2:       # generic mainloop: the plain stride-2 conv moves fewer bytes
+                            d.W, d.Cin, d.x_c_total, d.w, d.w_plane_stride, d.kw, d.stride_w, d.pad_w, d.out_w = keep
+                            d.pair_view = 0
                     if "neck_start" not in plan and op.name.startswith("neck."):
                         plan["neck_start"] = len(plan["calls"])     # first launch after the backbone (pipeline.DetectStream forks here)
                     plan["calls"].append(("conv", d))

@@ -34,9 +34,21 @@ def split3(t):
     return torch.stack([p0, p1, p2])
 
 
+def pair_view_weights(w33):
+    """[Cout, 3, 3, Cin] weights of a 3x3 stride-2 conv -> [Cout, 3, 2, 2*Cin] weights of the same conv on the column-pair view
+    [N, H, W/2, 2*Cin] of its input (3x2 kernel, stride (2, 1), pad (1, 1)): tap 0 = input columns (2j-2 | 2j-1), of which only the
+    odd one is under the 3x3 window; tap 1 = (2j | 2j+1).  See include/yv6.h `stride_w` / `pair_view`."""
+    cout, _, _, cin = w33.shape
+    wf = torch.zeros(cout, 3, 2, 2 * cin, dtype=w33.dtype, device=w33.device)
+    wf[:, :, 0, cin:] = w33[:, :, 0]
+    wf[:, :, 1, :cin] = w33[:, :, 1]
+    wf[:, :, 1, cin:] = w33[:, :, 2]
+    return wf
+
+
 def conv_fwd(x, w, bias, y, *, cin=None, x_c_offset=0, stride=1, act=None, y_c_offset=0,
              y_img_stride=None, y_h_stride=None, y_w_stride=None, y_elem_offset=0,
-             res=None, res_c_offset=0, alpha=1.0, nsplit=1, force=None, stream=None, pad=None, out_hw=None):
+             res=None, res_c_offset=0, alpha=1.0, nsplit=1, force=None, stream=None, pad=None, out_hw=None, stride_w=0, pair_view=0):
     """y[..., y_c_offset:+Cout] = act(conv(x[..., x_c_offset:+Cin], w) + bias) (+ alpha*res).
 
     x: [N,H,W,Ct] bf16 (nsplit=1) or [3,N,H,W,Ct] (nsplit=3); w: [Cout,kh,kw,Cin] bf16 (or [3,...]);
@@ -62,6 +74,7 @@ def conv_fwd(x, w, bias, y, *, cin=None, x_c_offset=0, stride=1, act=None, y_c_o
     d.pad_w = _lib.PAD_SAME if pad is None else pad[1]
     if out_hw is not None:
         d.out_h, d.out_w = out_hw
+    d.stride_w, d.pair_view = int(stride_w), int(pair_view)
     d.act = ACT_CODES[act]
     y_planes = planes and y.dtype == torch.bfloat16
     ysh = y.shape[1:] if y_planes else y.shape
@@ -90,7 +103,7 @@ def conv_fwd(x, w, bias, y, *, cin=None, x_c_offset=0, stride=1, act=None, y_c_o
     return y
 
 
-def conv_plan(x_shape, w_shape, stride=1, nsplit=1, force=None, device=0):
+def conv_plan(x_shape, w_shape, stride=1, nsplit=1, force=None, device=0, stride_w=0, pad=None, out_hw=None, pair_view=0):
     """Tile plan (BW,BH,BI,BN,KB,stages,grid,tiles) the kernel would use for a shape."""
     N, H, W, Ct = x_shape
     Cout, kh, kw, Cin = w_shape
@@ -99,6 +112,11 @@ def conv_plan(x_shape, w_shape, stride=1, nsplit=1, force=None, device=0):
     d.N, d.H, d.W, d.Cin, d.x_c_total = N, H, W, Cin, Ct
     d.Cout, d.kh, d.kw, d.stride, d.pad = Cout, kh, kw, stride, kh // 2
     d.pad_w = _lib.PAD_SAME
+    if pad is not None:
+        d.pad, d.pad_w = pad
+    if out_hw is not None:
+        d.out_h, d.out_w = out_hw
+    d.stride_w, d.pair_view = int(stride_w), int(pair_view)
     d.nsplit = nsplit
     if force:
         for k, v in force.items():
