@@ -102,7 +102,7 @@ typedef struct yv6_conv_desc {
    * every other Cin-channel pixel (see yolov6_b200/engine.py). */
   int32_t stride_w;
   int32_t force_pair;       /* CTA pairs (clusters of two CTAs, tcgen05 cta_group::2: one M256 instruction over two M tiles, each CTA
-                             * staging half of the weight tile): 0 = auto (3x3 stride-1 layers over >= 128 input channels),
+                             * staging half of the weight tile): 0 = auto (3x3 stride-1 layers over >= 128 input channels; stride-2 pair_view layers from 128 output channels),
                              * 1 = on whenever the layer has >= 2 M tiles, -1 = off.
                              * Occupies what used to be tail padding: the struct size is unchanged. */
   /* ABI 4.  pair_view = 1: this 3x2 / stride (2, 1) descriptor is the column-pair view of a 3x3 stride-2 conv (see stride_w) and

@@ -993,8 +993,9 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
       d->Cin % 64 == 0 && d->force_bw == 0 && d->force_halo >= 0 && d->H % 2 == 0) {
     const long generic = (long)ceil_div(k.Wo, k.BW) * ceil_div(k.Ho, k.BH) * ceil_div(d->N, k.BI);
     const long halo_tiles = (long)ceil_div(k.Wo, 8) * ceil_div(k.Ho, 16) * d->N;
-    // auto: where the input operand dominates the L2 traffic (<= 64 real input channels) and the fixed tile wastes < 25 %
-    if (d->force_halo > 0 || (halo_tiles * 4 <= generic * 5 && d->Cin <= 128)) {
+    // auto (profiles/r02_s2_halo_sweep.md): up to 128 real input channels and where the fixed tile wastes < 25 %; beyond that the
+    // weight operand dominates the L2 -> shared-memory traffic and the plain stride-2 mainloop (fewer, wider K blocks) wins
+    if (d->force_halo > 0 || (halo_tiles * 4 <= generic * 5 && d->Cin <= 256)) {
       k.halo = 2;
       k.BW = 8;
       k.BH = 16;
@@ -1042,7 +1043,10 @@ static int plan_conv(const yv6_handle* h, const yv6_conv_desc* d, ConvPlan* plan
   // layers over >= 128 input channels (128->128 @80x80: 57.5 -> 52.0 us) -- are neutral on the stride-2 layers and LOSE on
   // the HBM-bound 1x1 layers (two SMs in lockstep hide less latency; 64->64 @160x160: 50 -> 67 us) and on the
   // resident-weight 64-channel 3x3 layers (73 -> 93 us), so auto mode takes them only for the first kind.
-  const bool pair_auto = (d->kh == 3 && d->kw == 3 && d->stride == 1 && stride_w == 1 && d->Cin >= 128 && d->Cout <= d->Cin);
+  // ... and for the stride-2 halo mainloop from 128 output channels on: half a weight tile per CTA keeps the 64->128 layer's
+  // weights resident and halves the streamed weight bytes of the wider ones (64->128 @160: 46.4 -> 43.7 us, 128->256 @80: 42.8 -> 36.7).
+  const bool pair_auto = (d->kh == 3 && d->kw == 3 && d->stride == 1 && stride_w == 1 && d->Cin >= 128 && d->Cout <= d->Cin) ||
+                         (k.halo == 2 && d->Cout >= 128);
   k.cpair = (m_tiles >= 2 && h->max_clusters > 0 && (d->force_pair > 0 || (d->force_pair == 0 && pair_auto))) ? 1 : 0;
   k.b_rows = k.cpair ? k.BN / 2 : k.BN;
   // schedule units: tiles, or (two consecutive M tiles) x N tile for CTA pairs

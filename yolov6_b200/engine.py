@@ -88,7 +88,7 @@ class InferEngine:
                     wi = wi.float().to(dev)
                     packed.append(_split3(wi).contiguous() if self.nsplit == 3 else wi.to(torch.bfloat16).contiguous())
                 ent["w"] = packed
-                if op.kind == "conv" and op.k == 3 and op.s == 2 and op.cin <= 64:
+                if op.kind == "conv" and op.k == 3 and op.s == 2 and (op.cin <= 32 or op.cin in (64, 128)):     # (64 | 128: the view's zero blocks are skipped)
                     # column-pair view (see _plan): [Cout][3][2][2*Cin]; tap 0 = input columns (2j-2 | 2j-1), tap 1 = (2j | 2j+1)
                     wf = ops.pair_view_weights(ws[0].float()).to(dev)
                     ent["w_pair"] = _split3(wf).contiguous() if self.nsplit == 3 else wf.to(torch.bfloat16).contiguous()
@@ -243,7 +243,7 @@ class InferEngine:
                         d.res_plane_stride = rbuf.stride(0) if P == 3 else 0
                         d.alpha = ent["alpha"]
                     if "w_pair" in ent and op.src.c_off == 0 and sct == op.cin and sw % 2 == 0:
-                        # 3x3 stride-2 conv over <= 64 channels.  On the column-pair view of the same memory, [N, H, W/2, 2*Cin],
+                        # 3x3 stride-2 conv over <= 128 channels.  On the column-pair view of the same memory, [N, H, W/2, 2*Cin],
                         # it is a 3x2 conv with stride (2, 1) over contiguous 2*Cin-channel rows.  <= 32 channels: 64-byte pixels
                         # fetched with an element stride of 2 keep the TMA unit, not the tensor pipe, busy (ERBlock_2.0 of
                         # YOLOv6-S: 170 -> 135 us).  And where the library's halo-reuse mainloop takes the view (one 9 x 33 input
