@@ -82,21 +82,19 @@ class ComputeLoss:
         ps = pred_scores.detach().float().contiguous()
         pd = pred_distri.detach().float().contiguous()
         strides = stride_t.reshape(-1).contiguous()
-        if reuse is not None:
-            gt, gt_count, G, c, mask, tg = reuse["gt"], reuse["gt_count"], reuse["G"], reuse["assignment"], reuse["mask"], None
-            pboxes = None
-        n = targets.shape[0] if reuse is None else 0
-        if reuse is not None:
-            pass
-        elif max_gt is not None:
-            G = max(int(max_gt), 1)
-        elif n == 0:
-            G = 1
-        else:   # loss.py:184-192 pads to the largest per-image count
-            img = targets[:, 0].detach()
-            valid = img[(img >= 0) & (img < B)].long()
-            G = max(int(torch.bincount(valid, minlength=1).max()), 1) if valid.numel() else 1
-        if reuse is None:
+        if reuse is not None:       # second box branch against the first call's padded targets and assignment
+            gt, gt_count, G, c, mask = reuse["gt"], reuse["gt_count"], reuse["G"], reuse["assignment"], reuse["mask"]
+            tg = pboxes = None
+        else:
+            n = targets.shape[0]
+            if max_gt is not None:
+                G = max(int(max_gt), 1)
+            elif n == 0:
+                G = 1
+            else:   # loss.py:184-192 pads to the largest per-image count
+                img = targets[:, 0].detach()
+                valid = img[(img >= 0) & (img < B)].long()
+                G = max(int(torch.bincount(valid, minlength=1).max()), 1) if valid.numel() else 1
             tg = targets.detach().float().contiguous().to(dev)
             gt = torch.empty(B, G, 5, dtype=torch.float64, device=dev)
             gt_count = torch.empty(B, dtype=torch.int32, device=dev)
