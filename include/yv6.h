@@ -117,6 +117,10 @@ int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream);
 /* Reports the tile plan yv6_conv_fwd would use: out[0..9] = BW,BH,BI,BN,KB,stages,grid,tiles,halo,
  * (A stages * 100 + B resident). */
 int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out10);
+/* Host-only twin: the plan for a device with the stated properties (B200: 148 SMs, 232448 bytes of opt-in shared memory, 74
+ * co-resident 2-CTA clusters), no CUDA call -- the tile planner can be exercised where there is no GPU (tests/test_conv_planner.py).
+ * out[0..9] as above, out[10] = dynamic shared memory in bytes, out[11] = TMEM columns; fails if either exceeds the device. */
+int yv6_conv_plan_host(int num_sms, int max_smem_optin, int max_clusters, const yv6_conv_desc* d, int32_t* out12);
 
 /* ------------------------------------------------------------------------------------------------
  * Stem: first 3x3 stride-2 conv on the 3-channel NCHW image, deploy form of `backbone.stem`

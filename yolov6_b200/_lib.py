@@ -127,6 +127,7 @@ _SIGNATURES = {
     "yv6_abi_version": (C.c_int, []),
     "yv6_conv_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p]),
     "yv6_conv_plan": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.POINTER(C.c_int32)]),
+    "yv6_conv_plan_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(ConvDesc), C.POINTER(C.c_int32)]),
     "yv6_stem_fwd": (C.c_int, [C.c_void_p, C.POINTER(StemDesc), C.c_void_p]),
     "yv6_sppf_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_int64, C.c_void_p]),

@@ -1193,6 +1193,37 @@ extern "C" int yv6_conv_plan(yv6_handle* h, const yv6_conv_desc* d, int32_t* out
   return YV6_OK;
 }
 
+// Host-only twin of yv6_conv_plan: plans against stated device properties instead of a handle, makes no CUDA call.
+extern "C" int yv6_conv_plan_host(int num_sms, int max_smem_optin, int max_clusters, const yv6_conv_desc* d, int32_t* out12) {
+  YV6_REQUIRE(out12 != nullptr, "conv_plan_host: null argument");
+  YV6_REQUIRE(num_sms > 0 && max_smem_optin > 0 && max_clusters >= 0, "conv_plan_host: bad device properties");
+  yv6_handle fake;
+  memset(&fake, 0, sizeof(fake));
+  fake.device = -1;
+  fake.num_sms = num_sms;
+  fake.max_smem_optin = max_smem_optin;
+  fake.max_clusters = max_clusters;
+  ConvPlan plan;
+  int rc = plan_conv(&fake, d, &plan);
+  if (rc != YV6_OK) return rc;
+  YV6_REQUIRE(plan.smem_bytes <= (size_t)max_smem_optin, "conv_plan_host: plan needs %zu bytes of shared memory, device offers %d",
+              plan.smem_bytes, max_smem_optin);
+  YV6_REQUIRE(plan.k.tmem_cols <= 512, "conv_plan_host: plan needs %d TMEM columns", plan.k.tmem_cols);
+  out12[0] = plan.k.BW;
+  out12[1] = plan.k.BH;
+  out12[2] = plan.k.BI;
+  out12[3] = plan.k.BN;
+  out12[4] = plan.k.kb_elems;
+  out12[5] = plan.k.stages;
+  out12[6] = plan.grid;
+  out12[7] = plan.k.num_tiles;
+  out12[8] = plan.k.halo;
+  out12[9] = (plan.k.halo ? plan.k.a_stages * 100 + plan.k.b_resident : 0) + 10 * plan.k.cpair;
+  out12[10] = (int32_t)plan.smem_bytes;
+  out12[11] = plan.k.tmem_cols;
+  return YV6_OK;
+}
+
 extern "C" int yv6_conv_fwd(yv6_handle* h, const yv6_conv_desc* d, void* stream) {
   yv6_device_guard _dev(h);
   YV6_REQUIRE(h != nullptr, "conv_fwd: null handle");
