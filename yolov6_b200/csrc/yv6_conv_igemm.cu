@@ -23,6 +23,10 @@
 //     tile i overlaps the mainloop of tile i+1.
 //   * bf16x3 mode (nsplit=3): same kernel, K loop additionally runs over six (plane_a, plane_b)
 //     pairs, giving fp32-equivalent products with fp32 accumulation.
+//   * halo variants (MODE 1 / 2: 3x3 stride 1; MODE 3 / 4: 3x3 stride 2 on the column-pair view of the input): ONE input box
+//     per channel block feeds every tap through shifted UMMA descriptors; weights streamed through their own ring or resident.
+//   * CTA-pair variants (CP = true): clusters of two CTAs, tcgen05 cta_group::2, M = 256 per instruction, half a weight tile
+//     staged per CTA.  DESIGN.md section 4 has the measurements behind each of these.
 #include <algorithm>
 #include <cstdarg>
 
