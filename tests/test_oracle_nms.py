@@ -1,6 +1,7 @@
 """Pins oracle/nms.py (incl. the restated torchvision greedy NMS) bit-exactly against the reference's
 non_max_suppression outputs stored by tests/golden/make_golden.py."""
 import numpy as np
+import pytest
 
 from conftest import golden_json, golden_npz, same_up_to_score_ties
 from oracle import fabricate as fab
@@ -80,3 +81,47 @@ def test_oracle_matches_reference_at_eval_batch_settings():
             assert out[b].shape[0] == counts[b]
             assert same_up_to_score_ties(out[b], rows[off:off + counts[b]])
             off += counts[b]
+
+
+def _iou(a, b):
+    x1, y1 = np.maximum(a[:, None, 0], b[None, :, 0]), np.maximum(a[:, None, 1], b[None, :, 1])
+    x2, y2 = np.minimum(a[:, None, 2], b[None, :, 2]), np.minimum(a[:, None, 3], b[None, :, 3])
+    inter = np.clip(x2 - x1, 0, None) * np.clip(y2 - y1, 0, None)
+    aa, ab = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]), (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    return inter / (aa[:, None] + ab[None, :] - inter)
+
+
+@pytest.mark.parametrize("seed,kw", [(3, dict(conf_thres=0.25, iou_thres=0.45)),
+                                     (4, dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300)),
+                                     (5, dict(conf_thres=0.1, iou_thres=0.5, agnostic=True, max_det=20)),
+                                     (6, dict(conf_thres=0.2, iou_thres=0.6, classes=[1, 3]))])
+def test_nms_size_independent_properties(seed, kw):
+    """Properties every output of nms.py:31-105 has whatever the input size (the GPU tests check the same at A = 8400, B = 32
+    through bit-exactness with this oracle): rows sorted by score, at most max_det of them, all above conf_thres, kept boxes of a
+    class (of any class when agnostic) never overlap by more than iou_thres, class filter honoured, and the function is
+    idempotent on its own output."""
+    p = fab.synthetic_predictions(3, 400, 6, seed=seed).numpy()
+    outs = onms.non_max_suppression(p, **kw)
+    assert len(outs) == 3 and any(o.shape[0] for o in outs)
+    for o in outs:
+        assert o.shape[1] == 6 and o.shape[0] <= kw.get("max_det", 300)
+        if not o.shape[0]:
+            continue
+        assert np.all(np.diff(o[:, 4]) <= 0), "rows are sorted by score"
+        assert np.all(o[:, 4] > kw["conf_thres"])
+        if "classes" in kw:
+            assert set(o[:, 5].astype(int)) <= set(kw["classes"])
+        iou = _iou(o[:, :4], o[:, :4])
+        same = np.ones_like(iou, bool) if kw.get("agnostic") else (o[:, 5][:, None] == o[:, 5][None, :])
+        np.fill_diagonal(same, False)
+        assert not np.any((iou > kw["iou_thres"] + 1e-6) & same), "a kept box overlaps a better kept box of its class"
+        # idempotence: the kept detections, fed back as predictions (obj = 1, one-hot class score), all survive in the same order
+        q = np.zeros((1, o.shape[0], 5 + 6), np.float32)
+        q[0, :, 0], q[0, :, 1] = (o[:, 0] + o[:, 2]) / 2, (o[:, 1] + o[:, 3]) / 2
+        q[0, :, 2], q[0, :, 3] = o[:, 2] - o[:, 0], o[:, 3] - o[:, 1]
+        q[0, :, 4] = 1.0
+        q[0, np.arange(o.shape[0]), 5 + o[:, 5].astype(int)] = o[:, 4]
+        again = onms.non_max_suppression(q, **kw)[0]
+        assert again.shape == o.shape
+        np.testing.assert_allclose(again[:, 4:], o[:, 4:], rtol=0, atol=0)
+        np.testing.assert_allclose(again[:, :4], o[:, :4], rtol=0, atol=1e-3)
