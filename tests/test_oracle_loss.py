@@ -80,3 +80,43 @@ def test_loss_at_640_batch_32_matches_reference():
     np.testing.assert_allclose(items.double().numpy(), g["loss640_items"], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(g_pd[asg["fg"]].double().numpy(), g["loss640_grad_distri_fg"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(g_ps.double().abs().sum(-1)[:, ::64].numpy(), g["loss640_grad_scores_rowabs"], rtol=1e-9, atol=1e-12)
+
+
+def _small_case(seed=5, B=3, img=256, nc=8, reg_max=16):
+    strides = [8, 16, 32]
+    sizes = [(img // s, img // s) for s in strides]
+    ps, pd = fab.synthetic_head_outputs(B, sizes, nc, 4 * (reg_max + 1), seed)
+    targets = oloss.synthetic_targets(B, seed=seed + 1, num_classes=nc)
+    kw = dict(strides=strides, num_classes=nc, ori_img_size=img, use_dfl=True, reg_max=reg_max, iou_type="giou", epoch_num=5)
+    return sizes, ps, pd, targets, kw
+
+
+def test_loss_size_independent_properties():
+    """Properties of ComputeLoss (loss.py:57-182) that hold at every size -- the GPU path is held to the same through its parity
+    with this oracle: the order of the target rows does not matter (preprocess groups them per image, loss.py:184-192), the three
+    terms scale linearly with their loss weights (:171-177), an image without targets contributes no positives, and removing
+    every target leaves the class term alone (background-only VarifocalLoss, :161-169)."""
+    sizes, ps, pd, targets, kw = _small_case()
+    loss, items, asg = oloss.compute_loss(sizes, ps, pd, targets, return_assign=True, **kw)
+    assert loss.item() > 0 and int(asg["fg"].sum()) > 0
+    # (a) permuting the target rows (keeping each image's relative order, which decides ties between identical boxes)
+    shuffled = torch.cat([targets[targets[:, 0] == b] for b in reversed(range(ps.shape[0]))])
+    assert not torch.equal(shuffled, targets) and shuffled.shape == targets.shape
+    loss_p, items_p = oloss.compute_loss(sizes, ps, pd, shuffled, **kw)
+    assert abs(loss_p.item() - loss.item()) <= 1e-12 * abs(loss.item())
+    # (b) linear in the loss weights
+    w2 = {"class": 2.0, "iou": 7.5, "dfl": 0.25}
+    loss_w, items_w = oloss.compute_loss(sizes, ps, pd, targets, loss_weight=w2, **kw)
+    base = {"class": 1.0, "iou": 2.5, "dfl": 0.5}
+    scale = torch.tensor([w2["iou"] / base["iou"], w2["dfl"] / base["dfl"], w2["class"] / base["class"]], dtype=items.dtype)
+    np.testing.assert_allclose(items_w.numpy(), (items * scale).numpy(), rtol=1e-12)
+    assert abs(loss_w.item() - float(items_w.sum())) <= 1e-12 * abs(loss_w.item())
+    # (c) an image without targets has no positive anchors
+    no_img1 = targets[targets[:, 0] != 1]
+    _, _, asg1 = oloss.compute_loss(sizes, ps, pd, no_img1, return_assign=True, **kw)
+    assert int(asg1["fg"][1].sum()) == 0 and int(asg1["fg"][0].sum()) == int(asg["fg"][0].sum())
+    # (d) no targets at all: IoU and DFL terms vanish, the class term is the background VarifocalLoss, not normalised (sum <= 1)
+    loss0, items0 = oloss.compute_loss(sizes, ps, pd, targets[:0], **kw)
+    bg = (torch.nn.functional.binary_cross_entropy(ps, torch.zeros_like(ps), reduction="none") * 0.75 * ps.pow(2)).sum()
+    assert items0[0].item() == 0 and items0[1].item() == 0
+    assert abs(items0[2].item() - bg.item()) <= 1e-12 * bg.item() and abs(loss0.item() - bg.item()) <= 1e-12 * bg.item()
